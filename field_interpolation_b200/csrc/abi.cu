@@ -1,0 +1,769 @@
+// C ABI of libfi_b200 (declared in include/fi_b200.h): the LatticeField handle, the constraint builders, the
+// triplet view, the solvers and the coarse-to-fine driver.  Everything crosses the boundary as plain pointers
+// and sizes; C++ exceptions stop here and become status codes.
+#include <algorithm>
+#include <cmath>
+#include <exception>
+#include <new>
+
+#include "solver.hpp"
+
+namespace fi {
+
+int64_t                   g_launches = 0;
+static thread_local std::string t_last_error;
+
+void set_last_error(const std::string& s) { t_last_error = s; }
+
+int sm_count()
+{
+	static thread_local int cached_dev = -1, cached = 0;
+	int dev = 0;
+	if (cudaGetDevice(&dev) != cudaSuccess) { return 148; }
+	if (dev != cached_dev) {
+		cudaDeviceProp prop;
+		if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) { cached = prop.multiProcessorCount; } else { cached = 148; }
+		cached_dev = dev;
+	}
+	return cached;
+}
+
+template <typename F>
+int guarded(F&& f)
+{
+	try {
+		f();
+		return FI_OK;
+	} catch (const Error& e) {
+		set_last_error(e.what);
+		return e.code;
+	} catch (const std::bad_alloc&) {
+		set_last_error("host allocation failed");
+		return FI_ERR_INVALID;
+	} catch (const std::exception& e) {
+		set_last_error(e.what());
+		return FI_ERR_INVALID;
+	}
+}
+
+struct Segment
+{
+	enum Kind { kModel, kPoints, kRows } kind;
+	fi_weights w{};          // kModel
+	int64_t    p0 = 0, p1 = 0;  // kPoints: range in the point store
+	int64_t    r0 = 0, r1 = 0;  // kRows: row range in the caller-row store
+	int64_t    rows = -1, trips = -1;  // cached counts (-1: not computed yet)
+};
+
+}  // namespace fi
+
+struct fi_field
+{
+	fi::Geom                               g;
+	cudaStream_t                           stream = nullptr;
+	std::vector<fi::Segment>               segs;
+	fi::PointStore                         pts;
+	fi::HostRows                           rows;
+	fi::ModelAccum                         model;
+	std::unique_ptr<fi::Operator<float>>   op32;
+	std::unique_ptr<fi::Operator<double>>  op64;
+
+	void invalidate()
+	{
+		op32.reset();
+		op64.reset();
+	}
+	fi::Operator<float>& get32()
+	{
+		if (!op32) { op32 = fi::build_operator<float>(g, model, pts, rows, stream); }
+		return *op32;
+	}
+	fi::Operator<double>& get64()
+	{
+		if (!op64) { op64 = fi::build_operator<double>(g, model, pts, rows, stream); }
+		return *op64;
+	}
+	~fi_field()
+	{
+		op32.reset();
+		op64.reset();
+		if (stream) { cudaStreamDestroy(stream); }
+	}
+};
+
+namespace fi {
+
+namespace {
+
+// Stages a caller buffer on the device when it lives on the host.
+template <typename T>
+struct Staged
+{
+	DevBuf<T> own;
+	const T*  ptr = nullptr;
+	Staged(const T* src, size_t n, int loc, cudaStream_t s)
+	{
+		if (!src || n == 0) { return; }
+		if (loc == FI_DEVICE) {
+			ptr = src;
+		} else {
+			own.resize(n);
+			FI_CUDA(cudaMemcpyAsync(own.data(), src, n * sizeof(T), cudaMemcpyHostToDevice, s));
+			ptr = own.data();
+		}
+	}
+};
+
+void model_counts_closed_form(const Geom& g, const fi_weights& w, int64_t* rows, int64_t* trips)
+{
+	const float wk[5] = {w.model_0, w.model_1, w.model_2, w.model_3, w.model_4};
+	int64_t     r = 0, t = 0;
+	for (int d = 0; d < g.ndim; ++d) {
+		const int64_t others = g.N / g.size[d];
+		for (int k = 0; k <= 4; ++k) {
+			if (wk[k] > 0 && g.size[d] > k) {
+				r += (g.size[d] - k) * others;
+				t += (g.size[d] - k) * others * (k + 1);
+			}
+		}
+		if (w.gradient_smoothness > 0) {
+			for (int o = 0; o < g.ndim; ++o) {
+				if (o == d) { continue; }
+				const int64_t n = static_cast<int64_t>(g.size[d] - 1) * (g.size[o] - 1) * (g.N / g.size[d] / g.size[o]);
+				r += n;
+				t += 4 * n;
+			}
+		}
+	}
+	*rows  = r;
+	*trips = t;
+}
+
+void segment_counts(fi_field* f, Segment& sg)
+{
+	if (sg.rows >= 0) { return; }
+	if (sg.kind == Segment::kModel) {
+		model_counts_closed_form(f->g, sg.w, &sg.rows, &sg.trips);
+	} else if (sg.kind == Segment::kPoints) {
+		const int64_t    n = sg.p1 - sg.p0;
+		DevBuf<uint64_t> ro(std::max<int64_t>(n, 1)), to(std::max<int64_t>(n, 1));
+		uint64_t         hr = 0, ht = 0;
+		count_point_rows(f->g, view(f->pts), sg.p0, sg.p1, ro.data(), to.data(), &hr, &ht, f->stream);
+		sg.rows  = static_cast<int64_t>(hr);
+		sg.trips = static_cast<int64_t>(ht);
+	} else {
+		sg.rows  = sg.r1 - sg.r0;
+		sg.trips = static_cast<int64_t>(f->rows.ptr[sg.r1] - f->rows.ptr[sg.r0]);
+	}
+}
+
+void check_weights(const fi_weights* w)
+{
+	FI_REQUIRE(w != nullptr, FI_ERR_INVALID, "weights is null");
+	FI_REQUIRE(w->value_kernel == 0 || w->value_kernel == 1, FI_ERR_INVALID, "unknown value kernel");
+	FI_REQUIRE(w->gradient_kernel >= 0 && w->gradient_kernel <= 2, FI_ERR_INVALID, "unknown gradient kernel");
+}
+
+void add_model_impl(fi_field* f, const fi_weights* w)
+{
+	check_weights(w);
+	Segment sg;
+	sg.kind = Segment::kModel;
+	sg.w    = *w;
+	f->segs.push_back(sg);
+	const float wk[5] = {w->model_0, w->model_1, w->model_2, w->model_3, w->model_4};
+	for (int k = 0; k <= 4; ++k) {
+		if (wk[k] > 0) { f->model.wsq[k] += static_cast<double>(wk[k]) * static_cast<double>(wk[k]); }
+	}
+	if (w->gradient_smoothness > 0) {
+		f->model.gs_sq += static_cast<double>(w->gradient_smoothness) * static_cast<double>(w->gradient_smoothness);
+	}
+	f->invalidate();
+}
+
+void add_points_impl(fi_field* f, float value_weight, int value_kernel, float gradient_weight, int gradient_kernel,
+                     int64_t n, const float* pos, const float* nrm, const float* pw, const float* val, int loc,
+                     int64_t* rows_added)
+{
+	FI_REQUIRE(n >= 0, FI_ERR_INVALID, "negative point count");
+	FI_REQUIRE(value_kernel == 0 || value_kernel == 1, FI_ERR_INVALID, "unknown value kernel");
+	FI_REQUIRE(gradient_kernel >= 0 && gradient_kernel <= 2, FI_ERR_INVALID, "unknown gradient kernel");
+	FI_REQUIRE(n == 0 || pos != nullptr, FI_ERR_INVALID, "positions is null");
+	// the reference CHECK-aborts when the nearest-neighbour value kernel is used without normals (:361)
+	FI_REQUIRE(n == 0 || value_kernel != FI_VALUE_NEAREST_NEIGHBOR || nrm != nullptr, FI_ERR_INVALID,
+	           "nearest-neighbour value kernel needs normals");
+	FI_REQUIRE(f->pts.count + n < (1ll << 32), FI_ERR_RANGE, "more than 2^32 points in one field");
+	if (rows_added) { *rows_added = 0; }
+	if (n == 0) { return; }
+	const int     D = f->g.ndim;
+	Staged<float> dpos(pos, static_cast<size_t>(n) * D, loc, f->stream), dnrm(nrm, static_cast<size_t>(n) * D, loc, f->stream);
+	Staged<float> dpw(pw, n, loc, f->stream), dval(val, n, loc, f->stream);
+	Segment       sg;
+	sg.kind = Segment::kPoints;
+	sg.p0   = f->pts.count;
+	canonicalise_points(f->g, f->pts, value_weight, value_kernel, gradient_weight, gradient_kernel, n, dpos.ptr, dnrm.ptr,
+	                    dpw.ptr, dval.ptr, f->stream);
+	sg.p1 = f->pts.count;
+	FI_CUDA(cudaStreamSynchronize(f->stream));
+	f->segs.push_back(sg);
+	f->invalidate();
+	if (rows_added) {
+		segment_counts(f, f->segs.back());
+		*rows_added = f->segs.back().rows;
+	}
+}
+
+fi_field* create_impl(int32_t ndim, const int32_t* sizes)
+{
+	FI_REQUIRE(1 <= ndim && ndim <= kMaxDim, FI_ERR_INVALID, "ndim must be 1..3");
+	FI_REQUIRE(sizes != nullptr, FI_ERR_INVALID, "sizes is null");
+	int64_t n = 1;
+	for (int d = 0; d < ndim; ++d) {
+		FI_REQUIRE(sizes[d] >= 1, FI_ERR_INVALID, "lattice size must be >= 1");
+		n *= sizes[d];
+		FI_REQUIRE(n < (1ll << 40), FI_ERR_RANGE, "lattice too large");
+	}
+	int count = 0;
+	FI_CUDA(cudaGetDeviceCount(&count));
+	FI_REQUIRE(count > 0, FI_ERR_CUDA, "no CUDA device");
+	auto f = std::make_unique<fi_field>();
+	f->g   = make_geom(ndim, sizes);
+	FI_CUDA(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
+	return f.release();
+}
+
+void fill_stats(fi_solve_stats* st, const PcgResult& r, double setup_ms, int64_t nocc, int64_t grows)
+{
+	if (!st) { return; }
+	st->iterations        = r.iterations;
+	st->relative_residual = r.rel_residual;
+	st->true_residual     = r.true_residual;
+	st->initial_residual  = r.initial_residual;
+	st->setup_ms          = setup_ms;
+	st->solve_ms          = r.solve_ms;
+	st->converged         = r.converged ? 1 : 0;
+	st->outer_sweeps      = 0;
+	st->occupied_cells    = nocc;
+	st->generic_rows      = grows;
+}
+
+// Solves into d_out (device, N floats) from d_guess (device, nullable).
+void solve_device(fi_field* f, const fi_solve_options& o, const float* d_guess, float* d_out, fi_solve_stats* st)
+{
+	const int64_t N = f->g.N;
+	cudaStream_t  s = f->stream;
+	const bool    fast = o.use_fast_stencil != 0;
+	if (o.precision == FI_F32) {
+		const bool fresh = !f->op32;
+		Operator<float>& op = f->get32();
+		op.use_fast = fast;
+		if (d_guess) {
+			if (d_guess != d_out) { FI_CUDA(cudaMemcpyAsync(d_out, d_guess, N * sizeof(float), cudaMemcpyDeviceToDevice, s)); }
+		} else {
+			FI_CUDA(cudaMemsetAsync(d_out, 0, N * sizeof(float), s));
+		}
+		const PcgResult r = pcg_solve<float>(op, nullptr, d_out, o.tolerance, o.max_iterations, o.check_every, true, s);
+		fill_stats(st, r, fresh ? op.setup_ms : 0.0, op.data.nocc, op.data.nrows);
+	} else if (o.precision == FI_F64) {
+		const bool fresh = !f->op64;
+		Operator<double>& op = f->get64();
+		op.use_fast = fast;
+		DevBuf<double> x(N);
+		if (d_guess) { convert(d_guess, x.data(), N, s); } else { x.zero(s); }
+		const PcgResult r = pcg_solve<double>(op, nullptr, x.data(), o.tolerance, o.max_iterations, o.check_every, true, s);
+		convert(x.data(), d_out, N, s);
+		fill_stats(st, r, fresh ? op.setup_ms : 0.0, op.data.nocc, op.data.nrows);
+	} else if (o.precision == FI_MIXED) {
+		// fp64 iterative refinement around fp32 PCG: x += solve32(b - A64 x)
+		const bool fresh = !f->op64 || !f->op32;
+		Operator<double>& op64 = f->get64();
+		Operator<float>&  op32 = f->get32();
+		op64.use_fast = op32.use_fast = fast;
+		DevBuf<double> x(N), r64(N);
+		DevBuf<float>  r32(N), e32(N);
+		if (d_guess) { convert(d_guess, x.data(), N, s); } else { x.zero(s); }
+		const double tol   = o.tolerance > 0 ? o.tolerance : 2.220446049250313e-16;
+		const double itol  = o.refine_inner_tolerance > 0 ? o.refine_inner_tolerance : 1e-3;
+		const int    outer = o.refine_max_outer > 0 ? o.refine_max_outer : 20;
+		long long    max_it = o.max_iterations > 0 ? o.max_iterations : 2 * N;
+		PcgResult    tot;
+		cudaEvent_t  e0, e1;
+		FI_CUDA(cudaEventCreate(&e0));
+		FI_CUDA(cudaEventCreate(&e1));
+		FI_CUDA(cudaEventRecord(e0, s));
+		int sweeps = 0;
+		for (;; ++sweeps) {
+			double rr = 0, bb = 0;
+			residual<double>(op64, nullptr, x.data(), r64.data(), &rr, &bb, s);
+			const double rel = bb > 0 ? std::sqrt(rr / bb) : 0.0;
+			if (sweeps == 0) { tot.initial_residual = rel; }
+			tot.rel_residual = tot.true_residual = rel;
+			if (bb == 0.0) { x.zero(s); tot.zero_rhs = tot.converged = true; break; }
+			if (rel <= tol) { tot.converged = true; break; }
+			if (sweeps >= outer || tot.iterations >= max_it) { break; }
+			convert(r64.data(), r32.data(), N, s);
+			e32.zero(s);
+			// never ask the inner solve for more than the outer target needs
+			const double    inner = std::max(itol, 0.5 * tol / rel);
+			const PcgResult r = pcg_solve<float>(op32, r32.data(), e32.data(), inner, max_it - tot.iterations, o.check_every, false, s);
+			tot.iterations += r.iterations;
+			axpy_f32_into_f64(e32.data(), x.data(), N, s);
+			if (r.iterations == 0) { break; }
+		}
+		FI_CUDA(cudaEventRecord(e1, s));
+		FI_CUDA(cudaEventSynchronize(e1));
+		float ms = 0;
+		FI_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+		cudaEventDestroy(e0);
+		cudaEventDestroy(e1);
+		tot.solve_ms = ms;
+		convert(x.data(), d_out, N, s);
+		fill_stats(st, tot, fresh ? op64.setup_ms + op32.setup_ms : 0.0, op64.data.nocc, op64.data.nrows);
+		if (st) { st->outer_sweeps = sweeps; }
+	} else {
+		throw Error{FI_ERR_INVALID, "unknown precision"};
+	}
+	FI_CUDA(cudaStreamSynchronize(s));
+}
+
+__global__ void scale_positions_kernel(int D, int64_t n, const float* __restrict__ unit, float* __restrict__ out, float sx, float sy, float sz)
+{
+	const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (i >= n * D) { return; }
+	const int   d = static_cast<int>(i % D);
+	const float s = d == 0 ? sx : (d == 1 ? sy : sz);
+	out[i]        = unit[i] * s;  // on_lattice, reference src/sdf_field.cpp:198-210: pos *= (resolution - 1.0f)
+}
+
+}  // namespace
+
+}  // namespace fi
+
+using namespace fi;
+
+extern "C" {
+
+int fi_abi_version(void) { return FI_B200_ABI_VERSION; }
+
+const char* fi_last_error(void) { return t_last_error.c_str(); }
+
+int fi_device_count(int32_t* count)
+{
+	return guarded([&] {
+		FI_REQUIRE(count != nullptr, FI_ERR_INVALID, "count is null");
+		int c = 0;
+		FI_CUDA(cudaGetDeviceCount(&c));
+		*count = c;
+	});
+}
+
+int fi_set_device(int32_t device)
+{
+	return guarded([&] { FI_CUDA(cudaSetDevice(device)); });
+}
+
+void fi_weights_default(fi_weights* w)
+{
+	if (!w) { return; }
+	*w = fi_weights{1.0f, 1.0f, 0.0f, 0.0f, 0.5f, 0.0f, 0.0f, 0.0f, FI_VALUE_LINEAR_INTERPOLATION, FI_GRADIENT_CELL_EDGES};
+}
+
+void fi_solve_options_default(fi_solve_options* o)
+{
+	if (!o) { return; }
+	std::memset(o, 0, sizeof(*o));
+	o->precision              = FI_F32;
+	o->max_iterations         = 0;
+	o->tolerance              = 1e-3;  // SolveOptions::error_tolerance, reference sparse_linear.hpp:72
+	o->check_every            = 32;
+	o->use_fast_stencil       = 1;
+	o->refine_max_outer       = 20;
+	o->refine_inner_tolerance = 1e-3;
+}
+
+int fi_field_create(int32_t ndim, const int32_t* sizes, fi_field** out)
+{
+	return guarded([&] {
+		FI_REQUIRE(out != nullptr, FI_ERR_INVALID, "out is null");
+		*out = nullptr;
+		*out = create_impl(ndim, sizes);
+	});
+}
+
+int fi_field_destroy(fi_field* f)
+{
+	return guarded([&] { delete f; });
+}
+
+int fi_field_add_model(fi_field* f, const fi_weights* w)
+{
+	return guarded([&] {
+		FI_REQUIRE(f != nullptr, FI_ERR_INVALID, "field is null");
+		add_model_impl(f, w);
+	});
+}
+
+int fi_field_add_points(fi_field* f, float value_weight, int32_t value_kernel, float gradient_weight, int32_t gradient_kernel,
+                        int64_t num_points, const float* positions, const float* normals, const float* point_weights,
+                        const float* values, int32_t loc, int64_t* rows_added)
+{
+	return guarded([&] {
+		FI_REQUIRE(f != nullptr, FI_ERR_INVALID, "field is null");
+		add_points_impl(f, value_weight, value_kernel, gradient_weight, gradient_kernel, num_points, positions, normals,
+		                point_weights, values, loc, rows_added);
+	});
+}
+
+int fi_field_add_rows(fi_field* f, int64_t num_rows, int64_t num_triplets, const int32_t* trip_row, const int32_t* trip_col,
+                      const float* trip_val, const float* rhs)
+{
+	return guarded([&] {
+		FI_REQUIRE(f != nullptr, FI_ERR_INVALID, "field is null");
+		FI_REQUIRE(num_rows >= 0 && num_triplets >= 0, FI_ERR_INVALID, "negative count");
+		if (num_rows == 0) { return; }
+		FI_REQUIRE(trip_row && trip_col && trip_val && rhs, FI_ERR_INVALID, "null row arrays");
+		HostRows& R  = f->rows;
+		const int64_t r0 = R.rows();
+		int64_t       at = 0;
+		for (int64_t r = 0; r < num_rows; ++r) {
+			while (at < num_triplets && trip_row[at] == r) {
+				FI_REQUIRE(0 <= trip_col[at] && trip_col[at] < f->g.N, FI_ERR_INVALID, "column out of range");
+				R.col.push_back(trip_col[at]);
+				R.val.push_back(trip_val[at]);
+				++at;
+			}
+			R.ptr.push_back(R.col.size());
+			R.rhs.push_back(rhs[r]);
+		}
+		FI_REQUIRE(at == num_triplets, FI_ERR_INVALID, "trip_row must be non-decreasing and < num_rows");
+		Segment sg;
+		sg.kind = Segment::kRows;
+		sg.r0   = r0;
+		sg.r1   = R.rows();
+		f->segs.push_back(sg);
+		f->invalidate();
+	});
+}
+
+int fi_sdf_from_points(int32_t ndim, const int32_t* sizes, const fi_weights* w, int64_t num_points, const float* positions,
+                       const float* normals, const float* point_weights, int32_t loc, fi_field** out)
+{
+	return guarded([&] {
+		FI_REQUIRE(out != nullptr, FI_ERR_INVALID, "out is null");
+		*out = nullptr;
+		check_weights(w);
+		FI_REQUIRE(positions != nullptr || num_points == 0, FI_ERR_INVALID, "positions is null");  // CHECK_NOTNULL_F, :382
+		std::unique_ptr<fi_field> f(create_impl(ndim, sizes));
+		add_model_impl(f.get(), w);
+		add_points_impl(f.get(), w->data_pos, w->value_kernel, w->data_gradient, w->gradient_kernel, num_points, positions,
+		                normals, point_weights, nullptr, loc, nullptr);
+		*out = f.release();
+	});
+}
+
+int fi_field_counts(fi_field* f, int64_t* num_rows, int64_t* num_triplets)
+{
+	return guarded([&] {
+		FI_REQUIRE(f != nullptr, FI_ERR_INVALID, "field is null");
+		int64_t r = 0, t = 0;
+		for (Segment& sg : f->segs) {
+			segment_counts(f, sg);
+			r += sg.rows;
+			t += sg.trips;
+		}
+		if (num_rows) { *num_rows = r; }
+		if (num_triplets) { *num_triplets = t; }
+	});
+}
+
+int fi_field_export(fi_field* f, fi_triplet* triplets, float* rhs)
+{
+	return guarded([&] {
+		FI_REQUIRE(f != nullptr, FI_ERR_INVALID, "field is null");
+		int64_t R = 0, T = 0;
+		for (Segment& sg : f->segs) {
+			segment_counts(f, sg);
+			R += sg.rows;
+			T += sg.trips;
+		}
+		FI_REQUIRE(R <= INT32_MAX && T <= INT32_MAX && f->g.N <= INT32_MAX, FI_ERR_RANGE,
+		           "system does not fit the reference's int32 triplet view");
+		if (R == 0 && T == 0) { return; }
+		FI_REQUIRE((triplets || T == 0) && (rhs || R == 0), FI_ERR_INVALID, "output buffers are null");
+		cudaStream_t       s = f->stream;
+		DevBuf<fi_triplet> d_trips(std::max<int64_t>(T, 1));
+		DevBuf<float>      d_rhs(std::max<int64_t>(R, 1));
+		int64_t            row_base = 0, trip_base = 0;
+		for (Segment& sg : f->segs) {
+			if (sg.kind == Segment::kModel) {
+				DevBuf<uint64_t> ro(f->g.N), to(f->g.N);
+				uint64_t         hr = 0, ht = 0;
+				count_model_rows(f->g, sg.w, ro.data(), to.data(), &hr, &ht, s);
+				FI_REQUIRE(static_cast<int64_t>(hr) == sg.rows && static_cast<int64_t>(ht) == sg.trips, FI_ERR_INVALID,
+				           "internal: model row count mismatch");
+				emit_model_rows(f->g, sg.w, ro.data(), to.data(), row_base, trip_base, d_trips.data(), d_rhs.data(), s);
+				FI_CUDA(cudaStreamSynchronize(s));
+			} else if (sg.kind == Segment::kPoints) {
+				const int64_t    n = sg.p1 - sg.p0;
+				DevBuf<uint64_t> ro(std::max<int64_t>(n, 1)), to(std::max<int64_t>(n, 1));
+				uint64_t         hr = 0, ht = 0;
+				count_point_rows(f->g, view(f->pts), sg.p0, sg.p1, ro.data(), to.data(), &hr, &ht, s);
+				emit_point_rows(f->g, view(f->pts), sg.p0, sg.p1, ro.data(), to.data(), row_base, trip_base, d_trips.data(),
+				                d_rhs.data(), s);
+				FI_CUDA(cudaStreamSynchronize(s));
+			} else {
+				std::vector<fi_triplet> ht(static_cast<size_t>(sg.trips));
+				size_t                  at = 0;
+				for (int64_t r = sg.r0; r < sg.r1; ++r) {
+					for (uint64_t k = f->rows.ptr[r]; k < f->rows.ptr[r + 1]; ++k) {
+						ht[at++] = fi_triplet{static_cast<int32_t>(row_base + (r - sg.r0)), f->rows.col[k], f->rows.val[k]};
+					}
+				}
+				if (!ht.empty()) {
+					FI_CUDA(cudaMemcpyAsync(d_trips.data() + trip_base, ht.data(), ht.size() * sizeof(fi_triplet), cudaMemcpyHostToDevice, s));
+				}
+				if (sg.rows > 0) {
+					FI_CUDA(cudaMemcpyAsync(d_rhs.data() + row_base, f->rows.rhs.data() + sg.r0, sg.rows * sizeof(float), cudaMemcpyHostToDevice, s));
+				}
+				FI_CUDA(cudaStreamSynchronize(s));
+			}
+			row_base += sg.rows;
+			trip_base += sg.trips;
+		}
+		if (T > 0) { FI_CUDA(cudaMemcpyAsync(triplets, d_trips.data(), T * sizeof(fi_triplet), cudaMemcpyDeviceToHost, s)); }
+		if (R > 0) { FI_CUDA(cudaMemcpyAsync(rhs, d_rhs.data(), R * sizeof(float), cudaMemcpyDeviceToHost, s)); }
+		FI_CUDA(cudaStreamSynchronize(s));
+	});
+}
+
+int fi_field_apply(fi_field* f, int32_t precision, const void* x, void* y)
+{
+	return guarded([&] {
+		FI_REQUIRE(f && x && y, FI_ERR_INVALID, "null argument");
+		const int64_t N = f->g.N;
+		cudaStream_t  s = f->stream;
+		if (precision == FI_F32) {
+			Operator<float>& op = f->get32();
+			DevBuf<float>    dx(N), dy(N);
+			FI_CUDA(cudaMemcpyAsync(dx.data(), x, N * sizeof(float), cudaMemcpyHostToDevice, s));
+			op.apply(dx.data(), dy.data(), nullptr, nullptr, s);
+			FI_CUDA(cudaMemcpyAsync(y, dy.data(), N * sizeof(float), cudaMemcpyDeviceToHost, s));
+		} else if (precision == FI_F64) {
+			Operator<double>& op = f->get64();
+			DevBuf<double>    dx(N), dy(N);
+			FI_CUDA(cudaMemcpyAsync(dx.data(), x, N * sizeof(double), cudaMemcpyHostToDevice, s));
+			op.apply(dx.data(), dy.data(), nullptr, nullptr, s);
+			FI_CUDA(cudaMemcpyAsync(y, dy.data(), N * sizeof(double), cudaMemcpyDeviceToHost, s));
+		} else {
+			throw Error{FI_ERR_INVALID, "precision must be FI_F32 or FI_F64"};
+		}
+		FI_CUDA(cudaStreamSynchronize(s));
+	});
+}
+
+static int copy_vector(fi_field* f, int32_t precision, void* out, int which)
+{
+	return guarded([&] {
+		FI_REQUIRE(f && out, FI_ERR_INVALID, "null argument");
+		const int64_t N = f->g.N;
+		if (precision == FI_F32) {
+			Operator<float>& op = f->get32();
+			FI_CUDA(cudaMemcpy(out, which == 0 ? op.atb.data() : op.diag.data(), N * sizeof(float), cudaMemcpyDeviceToHost));
+		} else if (precision == FI_F64) {
+			Operator<double>& op = f->get64();
+			FI_CUDA(cudaMemcpy(out, which == 0 ? op.atb.data() : op.diag.data(), N * sizeof(double), cudaMemcpyDeviceToHost));
+		} else {
+			throw Error{FI_ERR_INVALID, "precision must be FI_F32 or FI_F64"};
+		}
+	});
+}
+
+int fi_field_rhs(fi_field* f, int32_t precision, void* atb) { return copy_vector(f, precision, atb, 0); }
+int fi_field_diagonal(fi_field* f, int32_t precision, void* diag) { return copy_vector(f, precision, diag, 1); }
+
+int fi_field_solve(fi_field* f, const fi_solve_options* opt, const float* guess, float* solution, int32_t loc, fi_solve_stats* stats)
+{
+	return guarded([&] {
+		FI_REQUIRE(f && solution, FI_ERR_INVALID, "null argument");
+		fi_solve_options o;
+		if (opt) { o = *opt; } else { fi_solve_options_default(&o); }
+		const int64_t N = f->g.N;
+		if (loc == FI_DEVICE) {
+			solve_device(f, o, guess, solution, stats);
+		} else {
+			DevBuf<float> d(N);
+			if (guess) { FI_CUDA(cudaMemcpyAsync(d.data(), guess, N * sizeof(float), cudaMemcpyHostToDevice, f->stream)); }
+			solve_device(f, o, guess ? d.data() : nullptr, d.data(), stats);
+			FI_CUDA(cudaMemcpyAsync(solution, d.data(), N * sizeof(float), cudaMemcpyDeviceToHost, f->stream));
+			FI_CUDA(cudaStreamSynchronize(f->stream));
+		}
+	});
+}
+
+int fi_field_jacobi(fi_field* f, const float* guess, int32_t num_iterations, float weight, float* solution)
+{
+	return guarded([&] {
+		FI_REQUIRE(f && guess && solution, FI_ERR_INVALID, "null argument");
+		const int64_t N = f->g.N;
+		if (num_iterations <= 0) {  // reference sparse_linear.cpp:220: returns the guess
+			if (solution != guess) { std::memcpy(solution, guess, N * sizeof(float)); }
+			return;
+		}
+		Operator<float>& op = f->get32();
+		DevBuf<float>    x(N);
+		FI_CUDA(cudaMemcpyAsync(x.data(), guess, N * sizeof(float), cudaMemcpyHostToDevice, f->stream));
+		jacobi_sweeps<float>(op, x.data(), num_iterations, weight, f->stream);
+		FI_CUDA(cudaMemcpyAsync(solution, x.data(), N * sizeof(float), cudaMemcpyDeviceToHost, f->stream));
+		FI_CUDA(cudaStreamSynchronize(f->stream));
+	});
+}
+
+int fi_upscale_field(int32_t ndim, const int32_t* small_sizes, const int32_t* large_sizes, const float* small_field,
+                     float* large_field, int32_t loc)
+{
+	return guarded([&] {
+		FI_REQUIRE(1 <= ndim && ndim <= kMaxDim, FI_ERR_INVALID, "ndim must be 1..3");
+		FI_REQUIRE(small_sizes && large_sizes && small_field && large_field, FI_ERR_INVALID, "null argument");
+		for (int d = 0; d < ndim; ++d) { FI_REQUIRE(small_sizes[d] >= 1 && large_sizes[d] >= 1, FI_ERR_INVALID, "size must be >= 1"); }
+		const Geom gs = make_geom(ndim, small_sizes), gl = make_geom(ndim, large_sizes);
+		if (loc == FI_DEVICE) {
+			upscale_device(gs, gl, small_field, large_field, 1.0f, nullptr);
+			FI_CUDA(cudaStreamSynchronize(nullptr));
+		} else {
+			DevBuf<float> a(gs.N), b(gl.N);
+			FI_CUDA(cudaMemcpy(a.data(), small_field, gs.N * sizeof(float), cudaMemcpyHostToDevice));
+			upscale_device(gs, gl, a.data(), b.data(), 1.0f, nullptr);
+			FI_CUDA(cudaMemcpy(large_field, b.data(), gl.N * sizeof(float), cudaMemcpyDeviceToHost));
+		}
+	});
+}
+
+int fi_sdf_solve_cascade(int32_t ndim, const int32_t* sizes, const fi_weights* w, int64_t num_points, const float* unit_positions,
+                         const float* normals, const float* point_weights, const fi_cascade_options* opt, float* solution,
+                         int32_t loc, fi_cascade_stats* stats)
+{
+	return guarded([&] {
+		FI_REQUIRE(1 <= ndim && ndim <= kMaxDim, FI_ERR_INVALID, "ndim must be 1..3");
+		FI_REQUIRE(sizes && opt && solution, FI_ERR_INVALID, "null argument");
+		FI_REQUIRE(unit_positions != nullptr || num_points == 0, FI_ERR_INVALID, "positions is null");
+		check_weights(w);
+		const int factor   = opt->factor;
+		const int coarsest = opt->coarsest_size > 0 ? opt->coarsest_size : 16;
+		// level 0 = finest
+		std::vector<std::vector<int32_t>> lv;
+		lv.emplace_back(sizes, sizes + ndim);
+		while (factor >= 2 && static_cast<int>(lv.size()) < 16 && (opt->max_levels <= 0 || static_cast<int>(lv.size()) < opt->max_levels)) {
+			std::vector<int32_t> next(ndim);
+			bool                 ok = true, shrunk = false;
+			for (int d = 0; d < ndim; ++d) {
+				next[d] = (lv.back()[d] + factor - 1) / factor;  // src/sdf_field.cpp:273
+				ok      = ok && next[d] >= coarsest;
+				shrunk  = shrunk || next[d] < lv.back()[d];
+			}
+			if (!ok || !shrunk) { break; }
+			lv.push_back(next);
+		}
+		const int L = static_cast<int>(lv.size());
+		if (stats) { std::memset(stats, 0, sizeof(*stats)); stats->levels = L; }
+
+		cudaStream_t s0 = nullptr;  // staging on the default stream, then per-level field streams
+		Staged<float> dunit(unit_positions, static_cast<size_t>(num_points) * ndim, loc, s0), dnrm(normals, static_cast<size_t>(num_points) * ndim, loc, s0);
+		Staged<float> dpw(point_weights, num_points, loc, s0);
+		FI_CUDA(cudaStreamSynchronize(s0));
+		DevBuf<float> pos(std::max<int64_t>(num_points * ndim, 1));
+		DevBuf<float> prev, cur;
+		std::vector<int32_t> prev_sizes;
+		cudaEvent_t e0, e1, t0;
+		FI_CUDA(cudaEventCreate(&e0));
+		FI_CUDA(cudaEventCreate(&e1));
+		FI_CUDA(cudaEventCreate(&t0));
+		FI_CUDA(cudaEventRecord(t0, s0));
+		for (int l = L - 1; l >= 0; --l) {
+			std::unique_ptr<fi_field> f(create_impl(ndim, lv[l].data()));
+			cudaStream_t s = f->stream;
+			FI_CUDA(cudaEventRecord(e0, s));
+			if (num_points > 0) {
+				const float sx = static_cast<float>(lv[l][0]) - 1.0f;
+				const float sy = ndim > 1 ? static_cast<float>(lv[l][1]) - 1.0f : 0.0f;
+				const float sz = ndim > 2 ? static_cast<float>(lv[l][2]) - 1.0f : 0.0f;
+				FI_LAUNCH(scale_positions_kernel, div_up(num_points * ndim, 256), 256, 0, s, ndim, num_points, dunit.ptr, pos.data(), sx, sy, sz);
+			}
+			add_model_impl(f.get(), w);
+			add_points_impl(f.get(), w->data_pos, w->value_kernel, w->data_gradient, w->gradient_kernel, num_points, pos.data(),
+			                dnrm.ptr, dpw.ptr, nullptr, FI_DEVICE, nullptr);
+			cur.resize(f->g.N);
+			const float* guess = nullptr;
+			if (l < L - 1) {
+				const Geom gs = make_geom(ndim, prev_sizes.data());
+				upscale_device(gs, f->g, prev.data(), cur.data(), static_cast<float>(factor), s);  // :284-288
+				guess = cur.data();
+			}
+			fi_solve_options o = opt->fine;
+			if (l > 0 && opt->coarse_tolerance > 0) { o.tolerance = opt->coarse_tolerance; }
+			fi_solve_stats st{};
+			solve_device(f.get(), o, guess, cur.data(), &st);
+			FI_CUDA(cudaEventRecord(e1, s));
+			FI_CUDA(cudaEventSynchronize(e1));
+			float ms = 0;
+			FI_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+			if (stats) {
+				stats->level_cells[l]            = f->g.N;
+				stats->level_iterations[l]       = st.iterations;
+				stats->level_ms[l]               = ms;
+				stats->level_initial_residual[l] = st.initial_residual;
+				stats->cell_iterations += f->g.N * st.iterations;
+				stats->total_ms += ms;
+				if (l == 0) { stats->finest = st; }
+			}
+			prev.swap(cur);
+			prev_sizes = lv[l];
+		}
+		cudaEventDestroy(e0);
+		cudaEventDestroy(e1);
+		cudaEventDestroy(t0);
+		const int64_t N = make_geom(ndim, sizes).N;
+		FI_CUDA(cudaMemcpy(solution, prev.data(), N * sizeof(float), loc == FI_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost));
+	});
+}
+
+int64_t fi_kernel_launches(void) { return g_launches; }
+void    fi_kernel_launches_reset(void) { g_launches = 0; }
+
+int fi_field_time_iterations(fi_field* f, const fi_solve_options* opt, int32_t iterations, double* ms, double* ms_stencil_only)
+{
+	return guarded([&] {
+		FI_REQUIRE(f && iterations > 0, FI_ERR_INVALID, "bad argument");
+		fi_solve_options o;
+		if (opt) { o = *opt; } else { fi_solve_options_default(&o); }
+		const int64_t N = f->g.N;
+		cudaStream_t  s = f->stream;
+		cudaEvent_t   e0, e1;
+		FI_CUDA(cudaEventCreate(&e0));
+		FI_CUDA(cudaEventCreate(&e1));
+		auto run = [&](auto& op, auto zero) {
+			using T = decltype(zero);
+			op.use_fast = o.use_fast_stencil != 0;
+			DevBuf<T> x(N);
+			x.zero(s);
+			// tolerance 0 is replaced by epsilon; a denormal-small positive tolerance is never met, so exactly
+			// `iterations` iterations run unless CG breaks down.
+			const PcgResult r = pcg_solve<T>(op, nullptr, x.data(), 1e-300, iterations, iterations, false, s);
+			if (ms) { *ms = r.loop_ms; }
+			if (ms_stencil_only) {
+				DevBuf<double> dot(1);
+				FI_CUDA(cudaEventRecord(e0, s));
+				for (int i = 0; i < iterations; ++i) { op.apply(op.work.p.data(), op.work.q.data(), dot.data(), nullptr, s); }
+				FI_CUDA(cudaEventRecord(e1, s));
+				FI_CUDA(cudaEventSynchronize(e1));
+				float t = 0;
+				FI_CUDA(cudaEventElapsedTime(&t, e0, e1));
+				*ms_stencil_only = t;
+			}
+		};
+		if (o.precision == FI_F64) { run(f->get64(), 0.0); } else { run(f->get32(), 0.0f); }
+		cudaEventDestroy(e0);
+		cudaEventDestroy(e1);
+	});
+}
+
+}  // extern "C"

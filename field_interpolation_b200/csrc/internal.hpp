@@ -1,0 +1,145 @@
+// Internal interfaces between the translation units of libfi_b200 (not installed).
+#pragma once
+
+#include <memory>
+
+#include "common.cuh"
+
+namespace fi {
+
+struct Geom  // LatticeField geometry, reference field_interpolation.hpp:97-114 (x fastest)
+{
+	int     ndim = 0;
+	int     size[kMaxDim]   = {1, 1, 1};
+	int64_t stride[kMaxDim] = {1, 1, 1};
+	int64_t N = 1;
+};
+
+inline Geom make_geom(int ndim, const int32_t* sizes)
+{
+	Geom g;
+	g.ndim    = ndim;
+	int64_t s = 1;
+	for (int d = 0; d < ndim; ++d) {
+		g.size[d]   = sizes[d];
+		g.stride[d] = s;
+		s *= sizes[d];
+	}
+	g.N = s;
+	return g;
+}
+
+// Canonical per-point records, appended by every add_points call (struct of arrays on the device).
+// kind: bit0 value kernel (0 nearest, 1 linear), bits1-2 gradient kernel, bit3 has-gradient.
+struct PointStore
+{
+	DevBuf<float>   pos, grad;        // D floats per point, interleaved
+	DevBuf<float>   value, vw, gw;    // f(pos), weight*value_weight, weight*gradient_weight (add_points :357-368)
+	DevBuf<uint8_t> kind;
+	int64_t         count = 0;
+};
+
+struct PointView
+{
+	const float *  pos, *grad, *value, *vw, *gw;
+	const uint8_t* kind;
+};
+
+inline PointView view(const PointStore& s)
+{
+	return PointView{s.pos.data(), s.grad.data(), s.value.data(), s.vw.data(), s.gw.data(), s.kind.data()};
+}
+
+// ---- sort_scan.cu ------------------------------------------------------------------------------------
+// Exclusive prefix sum over n uint64 values (in may alias out).  Returns nothing; total = out[n-1]+in[n-1]
+// is written to *total_dev (device, nullable).
+void exclusive_scan_u64(const uint64_t* in, uint64_t* out, int64_t n, uint64_t* total_dev, cudaStream_t s);
+// Stable LSD radix sort of (key, value) pairs on the low `bits` bits of the key.  Sorted data ends in
+// keys/vals (scratch buffers are swapped internally and results copied back if needed).
+void radix_sort_pairs(DevBuf<uint64_t>& keys, DevBuf<uint32_t>& vals, int64_t n, int bits, cudaStream_t s);
+
+// ---- assembly.cu (compiled with -fmad=false: bit-exact restatement of the reference's fp32 arithmetic) ----
+void canonicalise_points(const Geom& g, PointStore& store, float value_weight, int value_kernel, float gradient_weight,
+                         int gradient_kernel, int64_t n, const float* d_pos, const float* d_nrm, const float* d_pw,
+                         const float* d_val, cudaStream_t s);
+// rows / triplets contributed by points [p0,p1) (exclusive prefix per point into out_rows/out_trips, totals to host)
+void count_point_rows(const Geom& g, PointView pv, int64_t p0, int64_t p1, uint64_t* d_rowoff, uint64_t* d_tripoff,
+                      uint64_t* h_rows, uint64_t* h_trips, cudaStream_t s);
+void emit_point_rows(const Geom& g, PointView pv, int64_t p0, int64_t p1, const uint64_t* d_rowoff,
+                     const uint64_t* d_tripoff, int64_t row_base, int64_t trip_base, fi_triplet* d_trips, float* d_rhs,
+                     cudaStream_t s);
+void count_model_rows(const Geom& g, const fi_weights& w, uint64_t* d_rowoff, uint64_t* d_tripoff, uint64_t* h_rows,
+                      uint64_t* h_trips, cudaStream_t s);
+void emit_model_rows(const Geom& g, const fi_weights& w, const uint64_t* d_rowoff, const uint64_t* d_tripoff,
+                     int64_t row_base, int64_t trip_base, fi_triplet* d_trips, float* d_rhs, cudaStream_t s);
+void upscale_device(const Geom& small, const Geom& large, const float* d_small, float* d_large, float post_scale,
+                    cudaStream_t s);
+
+// Data term of the normal equations in compact form: per occupied cell a symmetric 2^D x 2^D block
+// (upper triangle, struct-of-arrays [tri][cell]) plus the rows that do not fit a cell (linear-interpolation
+// gradient rows) as CSR.
+template <typename T>
+struct DataTerm
+{
+	int64_t            nocc = 0;
+	DevBuf<uint64_t>   cell_key;  // per occupied cell: sum (base_d + 1) * kstride_d, sorted ascending
+	DevBuf<T>          blocks;    // [tri(2^D)][nocc]
+	int64_t            nrows = 0; // generic rows (derived + caller-appended)
+	DevBuf<uint64_t>   row_ptr;   // nrows + 1
+	DevBuf<int32_t>    col;
+	DevBuf<float>      val;
+	DevBuf<double>     partial;   // reduction scratch of the two apply kernels
+	DevBuf<unsigned>   ticket;
+};
+
+struct HostRows  // caller-appended rows (add_equation), already weighted
+{
+	std::vector<uint64_t> ptr{0};
+	std::vector<int32_t>  col;
+	std::vector<float>    val, rhs;
+	int64_t rows() const { return static_cast<int64_t>(rhs.size()); }
+};
+
+// Builds the data term, and accumulates Atb and diag(AtA) of all data rows into d_atb / d_diag (pre-zeroed or
+// pre-filled by the caller).
+template <typename T>
+void build_data_term(const Geom& g, const PointStore& pts, const HostRows& user_rows, DataTerm<T>& out, T* d_atb,
+                     T* d_diag, cudaStream_t s);
+
+// q += P p over the compact data term; p.(P p) is *added* to d_dot_accum[0] (nullable).
+template <typename T>
+void apply_data_term(const Geom& g, const DataTerm<T>& dt, const T* p, T* q, double* d_dot_accum, const int* d_done,
+                     cudaStream_t s);
+
+// ---- stencil.cu ------------------------------------------------------------------------------------------
+// Per-axis banded operator T_d = sum_k w_k^2 D_k^T D_k (rows that stick out dropped), 9 row classes x 9 taps,
+// plus the tri-diagonal D_1^T D_1 used by the gradient-smoothness cross terms.  See DESIGN.md §3.
+struct StencilTables
+{
+	double band[kMaxDim][9][9];  // [axis][row class][tap t = offset + 4]
+	double gs2;                  // 2 * sum of gradient_smoothness^2
+	int    radius;               // highest active order (taps beyond are zero)
+	bool   any;                  // any smoothness at all
+};
+
+struct ModelAccum  // sum over add_model calls of squared weights (add_model_constraint emits w_k rows iff w_k > 0)
+{
+	double wsq[5] = {0, 0, 0, 0, 0};
+	double gs_sq  = 0;
+};
+
+StencilTables make_tables(const Geom& g, const ModelAccum& m);
+
+template <typename T>
+void stencil_diagonal(const Geom& g, const StencilTables& t, T* d_diag /* += */, cudaStream_t s);
+
+// q = S p (overwrites q).  When d_dot_out is non-null, p.q is reduced deterministically (per-block partials in
+// d_partial, summed in block order by the last block to arrive) and *stored* to d_dot_out[0].  d_done
+// (nullable) is the solver's device-side convergence flag: the kernel returns at once when it is set.
+// use_fast selects the specialised 3D kernel when applicable.
+template <typename T>
+void stencil_apply(const Geom& g, const StencilTables& t, const T* p, T* q, double* d_dot_out, double* d_partial,
+                   unsigned* d_ticket, const int* d_done, bool use_fast, cudaStream_t s);
+int stencil_partial_slots(const Geom& g);  // upper bound of blocks any stencil launch uses (size of d_partial)
+
+}  // namespace fi

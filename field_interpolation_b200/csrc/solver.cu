@@ -1,0 +1,444 @@
+// Jacobi-preconditioned conjugate gradients on the normal equations — north-star item (c).
+//
+// Stands in for the reference's Eigen solves (sparse_linear.cpp:115-212, 392-443): same system A^T A x = A^T b,
+// same diagonal preconditioner (Eigen's default DiagonalPreconditioner: 1/diag, 1 where diag == 0), same
+// stopping rule |r| <= tol |A^T b|, same treatment of a zero right-hand side (x = 0) and of a failure to
+// converge (the last iterate is returned).  A^T A is symmetric positive (semi-)definite, so CG replaces
+// Eigen's BiCGSTAB at half the operator applications per iteration.
+//
+// Per iteration three kernels touch the lattice vectors:
+//   apply      q = (S+P) p, p.q                      read p, write q              8 B/cell (fp32)
+//   update     x += a p, r -= a q, r.Mr, r.r         read x,p,q,r,M, write x,r   28 B/cell
+//   direction  p = M r + b p                         read r,M,p, write p         16 B/cell
+// All scalars (alpha, beta, norms, the convergence flag, the iteration counter) live in a PcgState on the
+// device; dot products are reduced per block with warp shuffles and combined in a fixed order by the last
+// block to finish, so a run is bit-reproducible up to the data term's atomics.  `check_every` iterations are
+// captured into one CUDA graph; the host only polls the flag between graph launches.
+#include "solver.hpp"
+
+#include <algorithm>
+#include <cmath>
+
+namespace fi {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+int vec_grid(int64_t n)
+{
+	const int64_t want = (n + kThreads - 1) / kThreads;
+	return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, static_cast<int64_t>(sm_count()) * 8)));
+}
+
+template <typename T>
+struct Pack;
+template <>
+struct Pack<float>
+{
+	using type = float4;
+	static constexpr int V = 4;
+};
+template <>
+struct Pack<double>
+{
+	using type = double2;
+	static constexpr int V = 2;
+};
+
+// Applies f(i) to every element index, 16 bytes per thread per step where alignment allows.
+template <typename T, typename F>
+__device__ __forceinline__ void for_each_pack(int64_t n, F&& f)
+{
+	constexpr int V      = Pack<T>::V;
+	const int64_t npacks = n / V;
+	const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+	for (int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; k < npacks; k += stride) { f(k, true); }
+	if (blockIdx.x == 0) {
+		for (int64_t i = npacks * V + threadIdx.x; i < n; i += blockDim.x) { f(i, false); }
+	}
+}
+
+template <typename T>
+__global__ void inv_diag_kernel(int64_t n, const T* __restrict__ diag, T* __restrict__ minv)
+{
+	const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+	for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+		const T d = diag[i];
+		minv[i]   = d != T(0) ? T(1) / d : T(1);
+	}
+}
+
+// r = b - q, p = M r; rho = r.p, rr = r.r, bb = b.b
+template <typename T>
+__global__ void __launch_bounds__(kThreads) pcg_init_kernel(int64_t n, const T* __restrict__ b, const T* __restrict__ q,
+                                                            const T* __restrict__ minv, T* __restrict__ r, T* __restrict__ p,
+                                                            PcgState* st, double tol, long long max_iters, double* partial,
+                                                            unsigned* ticket)
+{
+	__shared__ double red[32];
+	double            acc[3] = {0, 0, 0};
+	const int64_t     stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+	for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+		const T bi = b[i], ri = bi - q[i], zi = minv[i] * ri;
+		r[i] = ri;
+		p[i] = zi;
+		acc[0] += static_cast<double>(ri) * static_cast<double>(zi);
+		acc[1] += static_cast<double>(ri) * static_cast<double>(ri);
+		acc[2] += static_cast<double>(bi) * static_cast<double>(bi);
+	}
+	acc[0] = block_sum(acc[0], red);
+	acc[1] = block_sum(acc[1], red);
+	acc[2] = block_sum(acc[2], red);
+	grid_sum<3>(acc, partial, ticket, red, [&](const double(&tot)[3]) {
+		st->rho[0]    = tot[0];
+		st->rho[1]    = 0;
+		st->pq        = 0;
+		st->rr        = tot[1];
+		st->rr0       = tot[1];
+		st->bb        = tot[2];
+		st->tol2bb    = tol * tol * tot[2];
+		st->iters     = 0;
+		st->max_iters = max_iters;
+		st->breakdown = 0;
+		st->done      = (tot[2] == 0.0 || tot[1] <= tol * tol * tot[2] || max_iters <= 0) ? 1 : 0;
+	});
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) pcg_update_kernel(int64_t n, T* __restrict__ x, T* __restrict__ r,
+                                                              const T* __restrict__ p, const T* __restrict__ q,
+                                                              const T* __restrict__ minv, PcgState* st, int par,
+                                                              double* partial, unsigned* ticket)
+{
+	__shared__ double red[32];
+	if (st->done) { return; }
+	const double pq = st->pq;
+	if (!(pq > 0.0)) {  // breakdown (singular direction or NaN): keep the last iterate
+		if (blockIdx.x == 0 && threadIdx.x == 0) {
+			st->breakdown = 1;
+			st->done      = 1;
+		}
+		return;
+	}
+	const T alpha = static_cast<T>(st->rho[par] / pq);
+	using P       = typename Pack<T>::type;
+	constexpr int V = Pack<T>::V;
+	double acc[2] = {0, 0};
+	for_each_pack<T>(n, [&](int64_t k, bool packed) {
+		if (packed) {
+			P        xv = reinterpret_cast<P*>(x)[k], rv = reinterpret_cast<P*>(r)[k];
+			const P  pv = reinterpret_cast<const P*>(p)[k], qv = reinterpret_cast<const P*>(q)[k];
+			const P  mv = reinterpret_cast<const P*>(minv)[k];
+			T*       xa = reinterpret_cast<T*>(&xv);
+			T*       ra = reinterpret_cast<T*>(&rv);
+			const T* pa = reinterpret_cast<const T*>(&pv);
+			const T* qa = reinterpret_cast<const T*>(&qv);
+			const T* ma = reinterpret_cast<const T*>(&mv);
+#pragma unroll
+			for (int j = 0; j < V; ++j) {
+				xa[j] += alpha * pa[j];
+				ra[j] -= alpha * qa[j];
+				const double rd = static_cast<double>(ra[j]);
+				acc[0] += rd * static_cast<double>(ma[j] * ra[j]);
+				acc[1] += rd * rd;
+			}
+			reinterpret_cast<P*>(x)[k] = xv;
+			reinterpret_cast<P*>(r)[k] = rv;
+		} else {
+			x[k] += alpha * p[k];
+			const T ri = r[k] - alpha * q[k];
+			r[k]       = ri;
+			acc[0] += static_cast<double>(ri) * static_cast<double>(minv[k] * ri);
+			acc[1] += static_cast<double>(ri) * static_cast<double>(ri);
+		}
+	});
+	acc[0] = block_sum(acc[0], red);
+	acc[1] = block_sum(acc[1], red);
+	grid_sum<2>(acc, partial, ticket, red, [&](const double(&tot)[2]) {
+		st->rho[par ^ 1] = tot[0];
+		st->rr           = tot[1];
+		st->iters += 1;
+		if (tot[1] <= st->tol2bb || st->iters >= st->max_iters || !(tot[0] > 0.0)) { st->done = 1; }
+	});
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) pcg_direction_kernel(int64_t n, const T* __restrict__ r, const T* __restrict__ minv,
+                                                                 T* __restrict__ p, const PcgState* st, int par)
+{
+	if (st->done) { return; }
+	const T beta  = static_cast<T>(st->rho[par ^ 1] / st->rho[par]);
+	using P       = typename Pack<T>::type;
+	constexpr int V = Pack<T>::V;
+	for_each_pack<T>(n, [&](int64_t k, bool packed) {
+		if (packed) {
+			const P  rv = reinterpret_cast<const P*>(r)[k], mv = reinterpret_cast<const P*>(minv)[k];
+			P        pv = reinterpret_cast<P*>(p)[k];
+			const T* ra = reinterpret_cast<const T*>(&rv);
+			const T* ma = reinterpret_cast<const T*>(&mv);
+			T*       pa = reinterpret_cast<T*>(&pv);
+#pragma unroll
+			for (int j = 0; j < V; ++j) { pa[j] = ma[j] * ra[j] + beta * pa[j]; }
+			reinterpret_cast<P*>(p)[k] = pv;
+		} else {
+			p[k] = minv[k] * r[k] + beta * p[k];
+		}
+	});
+}
+
+// r = b - q; rr = r.r, bb = b.b (out[0], out[1])
+template <typename T>
+__global__ void __launch_bounds__(kThreads) residual_kernel(int64_t n, const T* __restrict__ b, const T* __restrict__ q, T* __restrict__ r,
+                                                            double* out, double* partial, unsigned* ticket)
+{
+	__shared__ double red[32];
+	double            acc[2] = {0, 0};
+	const int64_t     stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+	for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+		const T bi = b[i], ri = bi - q[i];
+		if (r) { r[i] = ri; }
+		acc[0] += static_cast<double>(ri) * static_cast<double>(ri);
+		acc[1] += static_cast<double>(bi) * static_cast<double>(bi);
+	}
+	acc[0] = block_sum(acc[0], red);
+	acc[1] = block_sum(acc[1], red);
+	grid_sum<2>(acc, partial, ticket, red, [&](const double(&tot)[2]) {
+		out[0] = tot[0];
+		out[1] = tot[1];
+	});
+}
+
+// jacobi_iterations, reference sparse_linear.cpp:232-239: temp = Atb - R x with R = AtA - D, then
+// x = w*temp/D + (1-w)*x.  q holds AtA x.
+template <typename T>
+__global__ void jacobi_kernel(int64_t n, const T* __restrict__ atb, const T* __restrict__ q, const T* __restrict__ diag, T* __restrict__ x, T w)
+{
+	const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+	for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+		const T temp = atb[i] - (q[i] - diag[i] * x[i]);
+		x[i]         = w * temp / diag[i] + (T(1) - w) * x[i];
+	}
+}
+
+template <typename A, typename B>
+__global__ void convert_kernel(int64_t n, const A* __restrict__ a, B* __restrict__ b)
+{
+	const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+	for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) { b[i] = static_cast<B>(a[i]); }
+}
+
+__global__ void add_f32_f64_kernel(int64_t n, const float* __restrict__ e, double* __restrict__ x)
+{
+	const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+	for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) { x[i] += static_cast<double>(e[i]); }
+}
+
+template <typename T>
+void ensure_work(Operator<T>& op)
+{
+	PcgWork<T>& w = op.work;
+	const size_t n = static_cast<size_t>(op.g.N);
+	if (w.r.size() != n) {
+		w.r.resize(n);
+		w.p.resize(n);
+		w.q.resize(n);
+		w.partial.resize(static_cast<size_t>(3) * (static_cast<size_t>(sm_count()) * 8 + 8));
+		w.ticket.resize(1);
+		w.state.resize(1);
+		FI_CUDA(cudaMemset(w.ticket.data(), 0, sizeof(unsigned)));
+	}
+}
+
+}  // namespace
+
+void convert(const float* src, double* dst, int64_t n, cudaStream_t s)
+{
+	auto kern = convert_kernel<float, double>;
+	FI_LAUNCH(kern, vec_grid(n), kThreads, 0, s, n, src, dst);
+}
+void convert(const double* src, float* dst, int64_t n, cudaStream_t s)
+{
+	auto kern = convert_kernel<double, float>;
+	FI_LAUNCH(kern, vec_grid(n), kThreads, 0, s, n, src, dst);
+}
+void axpy_f32_into_f64(const float* e, double* x, int64_t n, cudaStream_t s)
+{
+	FI_LAUNCH(add_f32_f64_kernel, vec_grid(n), kThreads, 0, s, n, e, x);
+}
+
+template <typename T>
+std::unique_ptr<Operator<T>> build_operator(const Geom& g, const ModelAccum& m, const PointStore& pts, const HostRows& rows,
+                                            cudaStream_t s)
+{
+	cudaEvent_t e0, e1;
+	FI_CUDA(cudaEventCreate(&e0));
+	FI_CUDA(cudaEventCreate(&e1));
+	FI_CUDA(cudaEventRecord(e0, s));
+	auto op  = std::make_unique<Operator<T>>();
+	op->g    = g;
+	op->tabs = make_tables(g, m);
+	op->atb.resize(g.N);
+	op->diag.resize(g.N);
+	op->minv.resize(g.N);
+	op->atb.zero(s);
+	op->diag.zero(s);
+	build_data_term<T>(g, pts, rows, op->data, op->atb.data(), op->diag.data(), s);
+	stencil_diagonal<T>(g, op->tabs, op->diag.data(), s);
+	auto kern = inv_diag_kernel<T>;
+	FI_LAUNCH(kern, vec_grid(g.N), kThreads, 0, s, g.N, op->diag.data(), op->minv.data());
+	op->partial.resize(static_cast<size_t>(stencil_partial_slots(g)));
+	op->ticket.resize(1);
+	op->ticket.zero(s);
+	FI_CUDA(cudaEventRecord(e1, s));
+	FI_CUDA(cudaEventSynchronize(e1));
+	float ms = 0;
+	FI_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+	op->setup_ms = ms;
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	return op;
+}
+
+template <typename T>
+void residual(Operator<T>& op, const T* b, const T* x, T* r, double* rr, double* bb, cudaStream_t s)
+{
+	ensure_work(op);
+	PcgWork<T>& w = op.work;
+	op.apply(x, w.q.data(), nullptr, nullptr, s);
+	DevBuf<double> out(2);
+	auto kern = residual_kernel<T>;
+	FI_LAUNCH(kern, vec_grid(op.g.N), kThreads, 0, s, op.g.N, b ? b : op.atb.data(), w.q.data(), r, out.data(), w.partial.data(),
+	          w.ticket.data());
+	double h[2];
+	FI_CUDA(cudaMemcpyAsync(h, out.data(), sizeof(h), cudaMemcpyDeviceToHost, s));
+	FI_CUDA(cudaStreamSynchronize(s));
+	*rr = h[0];
+	*bb = h[1];
+}
+
+template <typename T>
+PcgResult pcg_solve(Operator<T>& op, const T* b, T* x, double tol, long long max_iter, int check_every, bool want_true_residual,
+                    cudaStream_t s)
+{
+	ensure_work(op);
+	PcgWork<T>&   w = op.work;
+	const int64_t n = op.g.N;
+	const T*      rhs = b ? b : op.atb.data();
+	if (max_iter <= 0) { max_iter = 2 * n; }  // Eigen: maxIterations() = 2 * cols by default
+	if (!(tol > 0)) { tol = std::is_same<T, float>::value ? 1.1920929e-07 : 2.220446049250313e-16; }
+	check_every = std::max(2, check_every <= 0 ? 32 : check_every);
+	check_every += check_every & 1;  // whole parity pairs per graph
+
+	cudaEvent_t e0, e1;
+	FI_CUDA(cudaEventCreate(&e0));
+	FI_CUDA(cudaEventCreate(&e1));
+	FI_CUDA(cudaEventRecord(e0, s));
+
+	const int grid = vec_grid(n);
+	op.apply(x, w.q.data(), nullptr, nullptr, s);
+	{
+		auto kern = pcg_init_kernel<T>;
+		FI_LAUNCH(kern, grid, kThreads, 0, s, n, rhs, w.q.data(), op.minv.data(), w.r.data(), w.p.data(), w.state.data(), tol,
+		          max_iter, w.partial.data(), w.ticket.data());
+	}
+	PcgState h;
+	FI_CUDA(cudaMemcpyAsync(&h, w.state.data(), sizeof(h), cudaMemcpyDeviceToHost, s));
+	FI_CUDA(cudaStreamSynchronize(s));
+
+	PcgResult res;
+	res.zero_rhs         = (h.bb == 0.0);
+	res.initial_residual = h.bb > 0 ? std::sqrt(h.rr0 / h.bb) : 0.0;
+	if (res.zero_rhs) {
+		FI_CUDA(cudaMemsetAsync(x, 0, n * sizeof(T), s));  // Eigen: rhs == 0 => x = 0
+	} else if (!h.done) {
+		const int* d_done = &w.state.data()->done;
+		double*    d_pq   = &w.state.data()->pq;
+		// one graph = check_every iterations
+		cudaGraph_t     graph = nullptr;
+		cudaGraphExec_t exec  = nullptr;
+		const int64_t   before = g_launches;
+		FI_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+		try {
+			for (int it = 0; it < check_every; ++it) {
+				const int par = it & 1;
+				op.apply(w.p.data(), w.q.data(), d_pq, d_done, s);
+				auto ku = pcg_update_kernel<T>;
+				FI_LAUNCH(ku, grid, kThreads, 0, s, n, x, w.r.data(), w.p.data(), w.q.data(), op.minv.data(), w.state.data(), par,
+				          w.partial.data(), w.ticket.data());
+				auto kd = pcg_direction_kernel<T>;
+				FI_LAUNCH(kd, grid, kThreads, 0, s, n, w.r.data(), op.minv.data(), w.p.data(), w.state.data(), par);
+			}
+		} catch (...) {
+			cudaStreamEndCapture(s, &graph);
+			if (graph) { cudaGraphDestroy(graph); }
+			throw;
+		}
+		FI_CUDA(cudaStreamEndCapture(s, &graph));
+		const int64_t per_graph = g_launches - before;
+		g_launches              = before;
+		FI_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+		cudaEvent_t l0, l1;
+		FI_CUDA(cudaEventCreate(&l0));
+		FI_CUDA(cudaEventCreate(&l1));
+		FI_CUDA(cudaEventRecord(l0, s));
+		while (true) {
+			FI_CUDA(cudaGraphLaunch(exec, s));
+			count_launch(static_cast<int>(per_graph));
+			FI_CUDA(cudaMemcpyAsync(&h, w.state.data(), sizeof(h), cudaMemcpyDeviceToHost, s));
+			FI_CUDA(cudaStreamSynchronize(s));
+			if (h.done) { break; }
+		}
+		FI_CUDA(cudaEventRecord(l1, s));
+		FI_CUDA(cudaEventSynchronize(l1));
+		float lms = 0;
+		FI_CUDA(cudaEventElapsedTime(&lms, l0, l1));
+		res.loop_ms = lms;
+		cudaEventDestroy(l0);
+		cudaEventDestroy(l1);
+		cudaGraphExecDestroy(exec);
+		cudaGraphDestroy(graph);
+	}
+	FI_CUDA(cudaEventRecord(e1, s));
+	FI_CUDA(cudaEventSynchronize(e1));
+	float ms = 0;
+	FI_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+
+	res.solve_ms     = ms;
+	res.iterations   = h.iters;
+	res.rel_residual = h.bb > 0 ? std::sqrt(h.rr / h.bb) : 0.0;
+	res.converged    = res.zero_rhs || (h.rr <= h.tol2bb);
+	res.true_residual = res.rel_residual;
+	if (want_true_residual && !res.zero_rhs) {
+		double rr = 0, bb = 0;
+		residual<T>(op, rhs, x, nullptr, &rr, &bb, s);
+		res.true_residual = bb > 0 ? std::sqrt(rr / bb) : 0.0;
+	}
+	return res;
+}
+
+template <typename T>
+void jacobi_sweeps(Operator<T>& op, T* x, int iterations, T weight, cudaStream_t s)
+{
+	ensure_work(op);
+	PcgWork<T>& w = op.work;
+	for (int it = 0; it < iterations; ++it) {
+		op.apply(x, w.q.data(), nullptr, nullptr, s);
+		auto kern = jacobi_kernel<T>;
+		FI_LAUNCH(kern, vec_grid(op.g.N), kThreads, 0, s, op.g.N, op.atb.data(), w.q.data(), op.diag.data(), x, weight);
+	}
+	FI_CUDA(cudaStreamSynchronize(s));
+}
+
+template std::unique_ptr<Operator<float>> build_operator<float>(const Geom&, const ModelAccum&, const PointStore&, const HostRows&, cudaStream_t);
+template std::unique_ptr<Operator<double>> build_operator<double>(const Geom&, const ModelAccum&, const PointStore&, const HostRows&, cudaStream_t);
+template PcgResult pcg_solve<float>(Operator<float>&, const float*, float*, double, long long, int, bool, cudaStream_t);
+template PcgResult pcg_solve<double>(Operator<double>&, const double*, double*, double, long long, int, bool, cudaStream_t);
+template void jacobi_sweeps<float>(Operator<float>&, float*, int, float, cudaStream_t);
+template void jacobi_sweeps<double>(Operator<double>&, double*, int, double, cudaStream_t);
+template void residual<float>(Operator<float>&, const float*, const float*, float*, double*, double*, cudaStream_t);
+template void residual<double>(Operator<double>&, const double*, const double*, double*, double*, double*, cudaStream_t);
+
+}  // namespace fi

@@ -1,0 +1,84 @@
+// Normal-equation operator and the preconditioned conjugate-gradient driver (solver.cu).
+#pragma once
+
+#include "internal.hpp"
+
+namespace fi {
+
+// Device-resident scalars of one PCG run; nothing here is read by the host inside the iteration loop except
+// at convergence polls.
+struct PcgState
+{
+	double rho[2];  // r.z, ping-pong by iteration parity
+	double pq;      // p.(A p)
+	double rr;      // r.r (recurrence residual)
+	double bb;      // b.b
+	double tol2bb;  // tolerance^2 * b.b  (Eigen's stopping rule: |r|^2 <= tol^2 |b|^2)
+	double rr0;     // r.r of the initial guess
+	int    done;
+	int    breakdown;
+	long long iters;
+	long long max_iters;
+};
+
+template <typename T>
+struct PcgWork
+{
+	DevBuf<T>        r, p, q;
+	DevBuf<double>   partial;
+	DevBuf<unsigned> ticket;
+	DevBuf<PcgState> state;
+};
+
+// A^T A = S (matrix-free stencil) + P (cell blocks + generic rows), with A^T b and the Jacobi preconditioner.
+template <typename T>
+struct Operator
+{
+	Geom             g;
+	StencilTables    tabs;
+	DataTerm<T>      data;
+	DevBuf<T>        atb, diag, minv;
+	DevBuf<double>   partial;  // stencil reduction scratch
+	DevBuf<unsigned> ticket;
+	bool             use_fast = true;
+	double           setup_ms = 0;
+	PcgWork<T>       work;
+
+	// q = (S + P) p; when d_dot is non-null it receives p.q (deterministic apart from the order of the data
+	// term's atomics into q).
+	void apply(const T* p, T* q, double* d_dot, const int* d_done, cudaStream_t s)
+	{
+		stencil_apply<T>(g, tabs, p, q, d_dot, partial.data(), ticket.data(), d_done, use_fast, s);
+		apply_data_term<T>(g, data, p, q, d_dot, d_done, s);
+	}
+};
+
+template <typename T>
+std::unique_ptr<Operator<T>> build_operator(const Geom& g, const ModelAccum& m, const PointStore& pts, const HostRows& rows,
+                                            cudaStream_t s);
+
+struct PcgResult
+{
+	long long iterations = 0;
+	double    rel_residual = 0, initial_residual = 0, true_residual = 0, solve_ms = 0;
+	double    loop_ms = 0;  // graph launches only (no init, capture or instantiation)
+	bool      converged = false, zero_rhs = false;
+};
+
+// Solves A x = b from the guess in x (device, N elements of T).  b == nullptr: the operator's own A^T b.
+template <typename T>
+PcgResult pcg_solve(Operator<T>& op, const T* b, T* x, double tol, long long max_iter, int check_every, bool want_true_residual,
+                    cudaStream_t s);
+
+template <typename T>
+void jacobi_sweeps(Operator<T>& op, T* x, int iterations, T weight, cudaStream_t s);
+
+// r = b - A x (device), returns |r|^2 and |b|^2.
+template <typename T>
+void residual(Operator<T>& op, const T* b, const T* x, T* r, double* rr, double* bb, cudaStream_t s);
+
+void convert(const float* src, double* dst, int64_t n, cudaStream_t s);
+void convert(const double* src, float* dst, int64_t n, cudaStream_t s);
+void axpy_f32_into_f64(const float* e, double* x, int64_t n, cudaStream_t s);  // x += e
+
+}  // namespace fi

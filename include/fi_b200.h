@@ -1,0 +1,202 @@
+/* fi_b200.h — C ABI of libfi_b200.so, the B200 (sm_100a) implementation of the hot path of
+ * emilk/field_interpolation: assembling and solving the sparse least-squares system that fits a
+ * LatticeField to value / gradient data under the finite-difference smoothness model.
+ *
+ * The reference has no FFI layer; its drop-in surface is the C++ API of
+ *   field_interpolation/field_interpolation.hpp:44-183  and  field_interpolation/sparse_linear.hpp:8-80
+ * (paths relative to the reference tree).  The C++ mirror of those two headers shipped in
+ * include/field_interpolation/ is a thin host layer over the entry points below; each entry point cites
+ * the reference interface it stands in for.  Plain pointers and sizes only, 64-bit counts, every function
+ * returns an int status and never throws.  There is no CPU fallback: without a CUDA device every compute
+ * entry point returns FI_ERR_CUDA.
+ *
+ * Conventions
+ *   - lattice: x fastest, index = sum coord[d]*stride[d], stride[0] = 1 (field_interpolation.hpp:104-111)
+ *   - positions / normals: interleaved fp32, D floats per point (field_interpolation.hpp:160)
+ *   - `loc` arguments say where caller buffers live: FI_HOST (borrowed for the call) or FI_DEVICE
+ *   - rows are numbered in call order exactly as the reference numbers them (running eq.rhs.size())
+ */
+#ifndef FI_B200_H
+#define FI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FI_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define FI_API __attribute__((visibility("default")))
+#else
+#define FI_API
+#endif
+
+enum fi_status {
+	FI_OK              = 0,
+	FI_ERR_INVALID     = 1, /* bad argument (null pointer, ndim outside 1..3, size < 1, unknown kernel enum) */
+	FI_ERR_CUDA        = 2, /* CUDA runtime failure or no device; fi_last_error() has the text */
+	FI_ERR_RANGE       = 3, /* result does not fit the reference's int32 Triplet view (sparse_linear.hpp:10) */
+	FI_ERR_UNSUPPORTED = 4, /* feature outside the built scope */
+	FI_ERR_COMM        = 5  /* multi-GPU communicator failure */
+};
+
+enum fi_location { FI_HOST = 0, FI_DEVICE = 1 };
+
+/* ValueKernel / GradientKernel, field_interpolation.hpp:47-59 (same numeric values) */
+enum fi_value_kernel { FI_VALUE_NEAREST_NEIGHBOR = 0, FI_VALUE_LINEAR_INTERPOLATION = 1 };
+enum fi_gradient_kernel { FI_GRADIENT_NEAREST_NEIGHBOR = 0, FI_GRADIENT_CELL_EDGES = 1, FI_GRADIENT_LINEAR_INTERPOLATION = 2 };
+
+/* Arithmetic of the solve.  FI_F32 mirrors the reference's float path (sparse_linear.cpp:186-212,392-443),
+ * FI_F64 its double path (:154-184).  FI_MIXED = fp32 PCG inside fp64 iterative refinement. */
+enum fi_precision { FI_F32 = 0, FI_F64 = 1, FI_MIXED = 2 };
+
+/* Weights, field_interpolation.hpp:75-95 (same field order and defaults; see fi_weights_default) */
+typedef struct fi_weights {
+	float   data_pos, data_gradient;
+	float   model_0, model_1, model_2, model_3, model_4;
+	float   gradient_smoothness;
+	int32_t value_kernel, gradient_kernel;
+} fi_weights;
+
+/* Triplet, sparse_linear.hpp:8-15: 12 bytes, layout-identical */
+typedef struct fi_triplet {
+	int32_t row, col;
+	float   value;
+} fi_triplet;
+
+/* SolveOptions (sparse_linear.hpp:66-73) plus what the iterative GPU path needs. */
+typedef struct fi_solve_options {
+	int32_t precision;      /* fi_precision */
+	int32_t max_iterations; /* <= 0: 2*N, Eigen's default for its iterative solvers */
+	double  tolerance;      /* stop when |r| <= tolerance*|Atb| (Eigen's rule); <= 0: epsilon of the precision */
+	int32_t check_every;    /* iterations per CUDA-graph launch between convergence polls; <= 0: 32 */
+	int32_t use_fast_stencil; /* 0: generic kernel only (debug / parity), 1: specialised kernels when applicable */
+	int32_t refine_max_outer; /* FI_MIXED: max fp64 refinement sweeps; <= 0: 20 */
+	double  refine_inner_tolerance; /* FI_MIXED: relative tolerance of each inner fp32 solve; <= 0: 1e-3 */
+} fi_solve_options;
+
+typedef struct fi_solve_stats {
+	int64_t iterations;        /* CG iterations at this lattice (all refinement sweeps summed) */
+	double  relative_residual; /* recurrence |r|/|Atb| at exit (what Eigen reports as error()) */
+	double  true_residual;     /* |Atb - AtA x|/|Atb| recomputed from x at exit */
+	double  initial_residual;  /* |Atb - AtA guess|/|Atb| */
+	double  setup_ms;          /* operator build: sort, scatter, diagonal (device time) */
+	double  solve_ms;          /* iteration loop (device time) */
+	int32_t converged;         /* 1 if the stopping rule was met */
+	int32_t outer_sweeps;      /* FI_MIXED only */
+	int64_t occupied_cells;    /* cells holding at least one data row */
+	int64_t generic_rows;      /* rows applied through the COO fallback */
+} fi_solve_stats;
+
+typedef struct fi_field fi_field; /* opaque: one LatticeField (field_interpolation.hpp:97-114) on one GPU */
+
+/* ---- library -------------------------------------------------------------------------------- */
+FI_API int         fi_abi_version(void);
+FI_API const char* fi_last_error(void);        /* thread-local text of the last failure */
+FI_API int         fi_device_count(int32_t* count);
+FI_API int         fi_set_device(int32_t device);
+FI_API void        fi_weights_default(fi_weights* w); /* data_pos=1, data_gradient=1, model_2=0.5, linear value, cell edges */
+FI_API void        fi_solve_options_default(fi_solve_options* o);
+
+/* ---- LatticeField lifetime ------------------------------------------------------------------ */
+/* LatticeField{sizes}, field_interpolation.hpp:104-111.  1 <= ndim <= 3 (MAX_DIM, :44). */
+FI_API int fi_field_create(int32_t ndim, const int32_t* sizes, fi_field** out);
+FI_API int fi_field_destroy(fi_field* f);
+
+/* ---- builders (each call appends rows after all earlier ones, like the reference) ---------- */
+/* add_field_constraints, field_interpolation.cpp:326-341 (+ add_model_constraint :243-316). */
+FI_API int fi_field_add_model(fi_field* f, const fi_weights* w);
+
+/* add_points, field_interpolation.cpp:343-371.  `values` (nullable) is the per-point f(pos) of
+ * add_value_constraint (:57-80); add_points itself always uses 0.  normals / point_weights / values may be
+ * null.  rows_added (nullable) receives the number of equations appended.  A single-point batch is
+ * add_value_constraint / add_value_constraint_nearest_neighbor (:82-107) / add_gradient_constraint
+ * (:123-240): pass value_weight or gradient_weight = 0 to leave that part out. */
+FI_API int fi_field_add_points(fi_field* f, float value_weight, int32_t value_kernel, float gradient_weight,
+                        int32_t gradient_kernel, int64_t num_points, const float* positions, const float* normals,
+                        const float* point_weights, const float* values, int32_t loc, int64_t* rows_added);
+
+/* Rows appended by the caller with add_equation (sparse_linear.cpp:34-50), already weighted, as COO:
+ * trip_row in [0,num_rows) non-decreasing, trip_col in [0,N).  Host buffers. */
+FI_API int fi_field_add_rows(fi_field* f, int64_t num_rows, int64_t num_triplets, const int32_t* trip_row,
+                      const int32_t* trip_col, const float* trip_val, const float* rhs);
+
+/* sdf_from_points, field_interpolation.cpp:373-400 = create + add_model + add_points. */
+FI_API int fi_sdf_from_points(int32_t ndim, const int32_t* sizes, const fi_weights* w, int64_t num_points,
+                       const float* positions, const float* normals, const float* point_weights, int32_t loc,
+                       fi_field** out);
+
+/* ---- the triplet view (LinearEquation, sparse_linear.hpp:18-22) ------------------------------ */
+FI_API int fi_field_counts(fi_field* f, int64_t* num_rows, int64_t* num_triplets);
+/* Writes eq.triplets / eq.rhs bit-identical to the reference's.  Host buffers sized by fi_field_counts.
+ * FI_ERR_RANGE when rows or triplets exceed INT32_MAX (the reference's int row overflows there). */
+FI_API int fi_field_export(fi_field* f, fi_triplet* triplets, float* rhs);
+
+/* ---- normal equations, matrix-free ----------------------------------------------------------- */
+/* y = (AtA) x, Atb and diag(AtA) of everything added so far; make_square / Atb, sparse_linear.cpp:105-113,
+ * :120.  x, y: N elements of float (FI_F32) or double (FI_F64), host buffers. */
+FI_API int fi_field_apply(fi_field* f, int32_t precision, const void* x, void* y);
+FI_API int fi_field_rhs(fi_field* f, int32_t precision, void* atb);
+FI_API int fi_field_diagonal(fi_field* f, int32_t precision, void* diag);
+
+/* ---- solvers ---------------------------------------------------------------------------------- */
+/* Jacobi-preconditioned CG on the normal equations with Eigen's stopping rule.  Stands in for
+ * solve_sparse_linear_exact / _fast (sparse_linear.cpp:115-184: pass FI_F64 and a tight tolerance),
+ * solve_sparse_linear_with_guess (:186-212) and the CG phase of solve_tiled_with_guess (:392-443).
+ * guess: N floats or null (zeros).  solution: N floats.  Non-convergence is not an error (Eigen returns the
+ * last iterate too); stats->converged says which. */
+FI_API int fi_field_solve(fi_field* f, const fi_solve_options* opt, const float* guess, float* solution, int32_t loc,
+                   fi_solve_stats* stats);
+
+/* jacobi_iterations, sparse_linear.cpp:214-241: x <- w*(Atb - R x)/D + (1-w)*x, fp32. Host buffers. */
+FI_API int fi_field_jacobi(fi_field* f, const float* guess, int32_t num_iterations, float weight, float* solution);
+
+/* upscale_field, field_interpolation.cpp:431-485 (bit-identical fp32 arithmetic). */
+FI_API int fi_upscale_field(int32_t ndim, const int32_t* small_sizes, const int32_t* large_sizes, const float* small_field,
+                     float* large_field, int32_t loc);
+
+/* Coarse-to-fine solve mirroring the demo's recipe (src/sdf_field.cpp:251-304) applied recursively:
+ * positions are in UNIT coordinates and are scaled per level by (size-1) as on_lattice does (:198-210);
+ * each level re-assembles sdf_from_points with the same weights and unscaled normals, the coarser solution
+ * is upscaled (upscale_field) and multiplied by the size ratio (:284-288), then refined by PCG.
+ * Levels: sizes, ceil(sizes/factor), ... while every axis stays >= coarsest_size. */
+typedef struct fi_cascade_options {
+	fi_solve_options fine;     /* solve options of the finest level */
+	int32_t factor;            /* downscale_factor between levels (>= 2); 0/1: no cascade (zero guess) */
+	int32_t coarsest_size;     /* stop coarsening below this size; <= 0: 16 */
+	double  coarse_tolerance;  /* tolerance of every level but the finest; <= 0: same as fine.tolerance */
+	int32_t max_levels;        /* <= 0: unlimited */
+} fi_cascade_options;
+
+typedef struct fi_cascade_stats {
+	int32_t levels;
+	int64_t level_cells[16];
+	int64_t level_iterations[16];
+	double  level_ms[16];           /* assemble + solve per level (device time) */
+	double  level_initial_residual[16];
+	double  total_ms;
+	int64_t cell_iterations;        /* sum over levels of cells * iterations */
+	fi_solve_stats finest;
+} fi_cascade_stats;
+
+FI_API int fi_sdf_solve_cascade(int32_t ndim, const int32_t* sizes, const fi_weights* w, int64_t num_points,
+                         const float* unit_positions, const float* normals, const float* point_weights,
+                         const fi_cascade_options* opt, float* solution, int32_t loc, fi_cascade_stats* stats);
+
+/* ---- instrumentation -------------------------------------------------------------------------- */
+/* Number of kernels this library has launched on the calling thread's device since load (bench.py's
+ * gpu_launches), and a reset. */
+FI_API int64_t fi_kernel_launches(void);
+FI_API void    fi_kernel_launches_reset(void);
+
+/* Times `iterations` PCG iterations (no convergence test) of the already-built operator, for the roofline
+ * of the CG kernels: returns device milliseconds measured with CUDA events on the solver stream. */
+FI_API int fi_field_time_iterations(fi_field* f, const fi_solve_options* opt, int32_t iterations, double* ms,
+                             double* ms_stencil_only);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FI_B200_H */

@@ -1,0 +1,190 @@
+"""GPU: the matrix-free normal equations and the PCG solves against the oracle.
+
+Tolerances (BASELINE.json north_star): relative L2 error of the solved field vs the reference's exact solve
+<= 1e-5 in fp64 and <= 1e-3 in fp32.  The "exact solve" is the fp64 sparse direct solve of the
+reference-assembled rows (golden fixtures / oracle), see oracle/fi_oracle.cpp header for why not Eigen."""
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden, weights_kwargs
+from field_interpolation_b200 import workloads as W
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL_F64, TOL_F32 = 1e-5, 1e-3
+
+
+def rel(a, b):
+    return float(np.linalg.norm(np.asarray(a, np.float64) - b) / max(np.linalg.norm(b), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def fi():
+    import field_interpolation_b200 as m
+    return m
+
+
+ALL_ON = dict(model_0=0.1, model_1=0.2, model_2=0.5, model_3=0.3, model_4=0.25, gradient_smoothness=0.15)
+
+
+@pytest.mark.parametrize("sizes", [[1], [2], [5], [9], [10], [37], [7, 6], [1, 9], [12, 3], [7, 6, 9], [3, 2, 4], [13, 11, 10], [10, 1, 10]])
+@pytest.mark.parametrize("fast", [False, True])
+def test_operator_matches_reference_normal_equations(fi, port, sizes, fast):
+    """y = AtA x, Atb and diag(AtA) vs the oracle's explicit normal equations; every weight on, every kernel."""
+    D, n = len(sizes), int(np.prod(sizes))
+    rng = np.random.default_rng(n)
+    for vk, gk in ((1, 1), (0, 0), (1, 2)):
+        pos, nrm = W.random_cloud(D, 150, sizes, seed=n + gk)
+        kw = dict(ALL_ON, value_kernel=vk, gradient_kernel=gk)
+        f = fi.sdf_from_points(sizes, fi.Weights(**kw), pos, nrm)
+        fi.add_equation(f, 0.7, 1.5, [(0, 1.0), (n - 1, -2.0), (0, 0.5)])  # duplicate column inside one row
+        ref = port.sdf_from_points(sizes, O.make_weights(**kw), pos, nrm)
+        ref.add_equation(0.7, 1.5, [0, n - 1, 0], [1.0, -2.0, 0.5])
+        M, atb = O.normal_equations_f64(ref.system(), n)
+        x = rng.normal(size=n)
+        scale = abs(M).max() * np.abs(x).max()
+        np.testing.assert_allclose(f.rhs(fi.FI_F64), atb, rtol=0, atol=1e-12 * max(1, np.abs(atb).max()))
+        np.testing.assert_allclose(f.diagonal(fi.FI_F64), M.diagonal(), rtol=1e-12, atol=1e-13)
+        # the fast flag only matters inside solve(); apply() always uses the operator's current setting
+        np.testing.assert_allclose(f.apply(x, fi.FI_F64), M @ x, rtol=0, atol=1e-12 * scale * 30)
+        np.testing.assert_allclose(f.apply(x.astype(np.float32), fi.FI_F32), M @ x, rtol=0, atol=2e-6 * scale * 30)
+        np.testing.assert_allclose(f.rhs(fi.FI_F32), atb, rtol=0, atol=1e-6 * max(1, np.abs(atb).max()))
+
+
+@pytest.mark.parametrize("name", ["kat1_readme_1d", "kat2_field_1d_res12", "kat2_field_1d_res100"])
+def test_1d_known_answers(fi, name):
+    g = load_golden(name)
+    if name.startswith("kat1"):
+        f = fi.LatticeField([6])
+        fi.add_value_constraint(f, [0.0], 4.0, 1.0)
+        fi.add_value_constraint(f, [5.0], 2.0, 1.0)
+        fi.add_gradient_constraint(f, [0.0], [1.0], 1.0, 0)
+        fi.add_gradient_constraint(f, [5.0], [-1.0], 1.0, 0)
+        fi.add_field_constraints(f, fi.Weights(model_2=1.0))
+    else:
+        res = int(name.split("res")[1])
+        c, w = W.field_1d(res), fi.Weights()
+        f = fi.LatticeField(c["sizes"])
+        for p, v, gr in zip(c["pos"], c["value"], c["gradient"]):
+            fi.add_value_constraint(f, p, float(v), w.data_pos)
+            fi.add_gradient_constraint(f, p, gr, w.data_gradient, w.gradient_kernel)
+        fi.add_field_constraints(f, w)
+    x = fi.solve_sparse_linear_exact(f)
+    assert rel(x, g["solution"]) <= TOL_F64
+    x32 = fi.solve_sparse_linear_fast(f)
+    assert rel(x32, g["solution"]) <= TOL_F32
+
+
+@pytest.mark.parametrize("name", golden_names("rand_"))
+def test_randomised_golden_solutions(fi, name):
+    g = load_golden(name)
+    f = fi.sdf_from_points(g["sizes"], fi.Weights(**weights_kwargs(g["weights"])), g["positions"], g["normals"],
+                           g["point_weights"])
+    x, st = f.solve(fi.solve_options(fi.FI_F64, 0, 1e-13))
+    assert rel(x, g["solution"]) <= TOL_F64, st
+    x, st = f.solve(fi.solve_options(fi.FI_MIXED, 0, 1e-9))
+    assert rel(x, g["solution"]) <= TOL_F32, st
+    x, st = f.solve(fi.solve_options(fi.FI_F32, 0, 1e-6))
+    assert rel(x, g["solution"]) <= TOL_F32, st
+
+
+@pytest.mark.parametrize("sizes,npts", [([40, 37], 400), ([24, 20, 22], 1500)])
+def test_sdf_solve_vs_exact_and_same_algorithm(fi, port, sizes, npts):
+    cloud = W.circles_2d(npts, seed=2) if len(sizes) == 2 else W.sphere_torus_3d(npts, seed=2)
+    pos = W.to_lattice(cloud["unit_pos"], sizes)
+    f = fi.sdf_from_points(sizes, fi.Weights(), pos, cloud["normals"])
+    sys_ = port.sdf_from_points(sizes, O.make_weights(), pos, cloud["normals"]).system()
+    n = int(np.prod(sizes))
+    exact = O.exact_solve(sys_, n)
+    x64, st = f.solve(fi.solve_options(fi.FI_F64, 0, 1e-12))
+    assert st["converged"] and rel(x64, exact) <= TOL_F64
+    # like for like: CPU PCG (same algorithm, same stopping rule) at the same tolerance
+    N64 = port.normal(sys_, n, "f64")
+    for tol in (1e-4, 1e-8):
+        xg, sg = f.solve(fi.solve_options(fi.FI_F64, 0, tol))
+        xc, itc, errc = N64.pcg(tol=tol)
+        assert abs(sg["iterations"] - itc) <= max(2, 0.02 * itc), (sg["iterations"], itc)
+        assert rel(xg, xc) <= 1e-5
+    x32, st32 = f.solve(fi.solve_options(fi.FI_F32, 0, 1e-6))
+    assert rel(x32, exact) <= TOL_F32, st32
+    xm, stm = f.solve(fi.solve_options(fi.FI_MIXED, 0, 1e-10))
+    assert stm["converged"] and rel(xm, exact) <= TOL_F64, stm
+
+
+def test_with_guess_and_iteration_cap(fi, port):
+    sizes = [30, 28]
+    cloud = W.circles_2d(300, seed=4)
+    pos = W.to_lattice(cloud["unit_pos"], sizes)
+    f = fi.sdf_from_points(sizes, fi.Weights(), pos, cloud["normals"])
+    n = 30 * 28
+    exact = O.exact_solve(port.sdf_from_points(sizes, O.make_weights(), pos, cloud["normals"]).system(), n)
+    x, st = f.solve(fi.solve_options(fi.FI_F32, 0, 1e-6), guess=exact.astype(np.float32))
+    assert st["iterations"] <= 3 and st["initial_residual"] < 1e-4
+    x5, st5 = f.solve(fi.solve_options(fi.FI_F32, 5, 1e-12, check_every=2))
+    assert st5["iterations"] == 5 and not st5["converged"]           # last iterate returned, not an error
+    g = np.zeros(n, np.float32)
+    assert fi.solve_tiled_with_guess(f, g[:-1]).size == 0              # incomplete guess => {} (:402-405)
+    xt = fi.solve_tiled_with_guess(f, g, sizes, fi.SolveOptions(error_tolerance=1e-6))
+    assert rel(xt, exact) <= TOL_F32
+    xw = fi.solve_sparse_linear_with_guess(f, g, 0, 1e-6)
+    assert rel(xw, exact) <= TOL_F32
+
+
+def test_jacobi_iterations_vs_port(fi, port):
+    sizes = [14, 12]
+    pos, nrm = W.random_cloud(2, 120, sizes, 8)
+    f = fi.sdf_from_points(sizes, fi.Weights(), pos, nrm)
+    N32 = port.normal(port.sdf_from_points(sizes, O.make_weights(), pos, nrm).system(), 14 * 12, "f32")
+    g = np.random.default_rng(0).normal(size=14 * 12).astype(np.float32)
+    assert np.array_equal(fi.jacobi_iterations(f, g, 0, 0.5), g)
+    for its, w in ((1, 0.5), (25, 2.0 / 3.0)):
+        got, want = fi.jacobi_iterations(f, g, its, w), N32.jacobi(g, its, w)
+        np.testing.assert_allclose(got, want, rtol=0, atol=2e-4 * max(1.0, np.abs(want).max()))
+
+
+def test_generic_rows_only_system(fi, port):
+    """A bare LinearEquation (no lattice structure, the line_2d / bipolar pattern): rows appended by hand."""
+    rng = np.random.default_rng(12)
+    n, m = 40, 160
+    f, ref = fi.LatticeField([n]), port.field([n])
+    for _ in range(m):
+        k = int(rng.integers(1, 5))
+        cols = rng.integers(0, n, k).tolist()
+        vals = rng.normal(size=k).astype(np.float32).tolist()
+        w, b = float(rng.uniform(0.2, 2)), float(rng.normal())
+        fi.add_equation(f, w, b, list(zip(cols, vals)))
+        ref.add_equation(w, b, cols, vals)
+    s = ref.system()
+    e = f.eq
+    assert np.array_equal(e.rows, s.rows) and np.array_equal(e.cols, s.cols) and np.array_equal(e.vals, s.vals)
+    exact = O.exact_solve(s, n)
+    x, st = f.solve(fi.solve_options(fi.FI_F64, 0, 1e-13))
+    assert rel(x, exact) <= TOL_F64, st
+
+
+def test_cascade_matches_manual_recipe(fi, port):
+    """fi_sdf_solve_cascade == the reference recipe (src/sdf_field.cpp:272-288) done by hand with the oracle."""
+    sizes, factor = [48, 48], 2
+    cloud = W.circles_2d(500, seed=6)
+    w = fi.Weights()
+    x, st = fi.sdf_solve_cascade(sizes, w, cloud["unit_pos"], cloud["normals"], options=fi.solve_options(fi.FI_F64, 0, 1e-12),
+                                 factor=factor, coarsest_size=20, coarse_tolerance=1e-12)
+    assert st["levels"] == 2 and st["level_cells"] == [48 * 48, 24 * 24]
+    # by hand: coarse exact solve -> upscale -> x2 -> that is the fine level's initial guess
+    small = [24, 24]
+    ps = W.to_lattice(cloud["unit_pos"], small)
+    coarse = O.exact_solve(port.sdf_from_points(small, O.make_weights(), ps, cloud["normals"]).system(), 24 * 24)
+    guess = port.upscale_field(coarse.astype(np.float32), small, sizes) * np.float32(factor)
+    pl = W.to_lattice(cloud["unit_pos"], sizes)
+    sys_l = port.sdf_from_points(sizes, O.make_weights(), pl, cloud["normals"]).system()
+    M, atb = O.normal_equations_f64(sys_l, 48 * 48)
+    want_r0 = np.linalg.norm(atb - M @ guess.astype(np.float64)) / np.linalg.norm(atb)
+    assert abs(st["level_initial_residual"][0] - want_r0) <= 1e-3 * want_r0
+    assert rel(x, O.exact_solve(sys_l, 48 * 48)) <= TOL_F64
+    # and the guess pays: far fewer iterations than from zero
+    f = fi.sdf_from_points(sizes, w, pl, cloud["normals"])
+    _, st0 = f.solve(fi.solve_options(fi.FI_F64, 0, 1e-6))
+    _, stc = fi.sdf_solve_cascade(sizes, w, cloud["unit_pos"], cloud["normals"], options=fi.solve_options(fi.FI_F64, 0, 1e-6),
+                                  factor=factor, coarsest_size=20)
+    assert stc["level_iterations"][0] < st0["iterations"]
