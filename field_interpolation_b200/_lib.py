@@ -83,6 +83,7 @@ SIGNATURES = {
     "fi_field_counts": (C.c_int, [_vp, _pi64, _pi64]),
     "fi_field_export": (C.c_int, [_vp, _vp, _vp]),
     "fi_field_apply": (C.c_int, [_vp, _i32, _vp, _vp]),
+    "fi_field_use_fast_stencil": (C.c_int, [_vp, _i32]),
     "fi_field_rhs": (C.c_int, [_vp, _i32, _vp]),
     "fi_field_diagonal": (C.c_int, [_vp, _i32, _vp]),
     "fi_field_solve": (C.c_int, [_vp, _p(fi_solve_options), _vp, _vp, _i32, _p(fi_solve_stats)]),
@@ -92,7 +93,7 @@ SIGNATURES = {
                                        _p(fi_cascade_stats)]),
     "fi_kernel_launches": (_i64, []),
     "fi_kernel_launches_reset": (None, []),
-    "fi_field_time_iterations": (C.c_int, [_vp, _p(fi_solve_options), _i32, _pd, _pd]),
+    "fi_field_time_iterations": (C.c_int, [_vp, _p(fi_solve_options), _i32, _pd]),
 }
 
 _dll = None

@@ -168,6 +168,9 @@ class LatticeField:
     def diagonal(self, precision=FI_F64):
         return self._vec(L.lib().fi_field_diagonal, precision)
 
+    def use_fast_stencil(self, enable: bool):
+        L.check(L.lib().fi_field_use_fast_stencil(self._h, 1 if enable else 0))
+
     def apply(self, x, precision=FI_F64):
         dt = np.float32 if precision == FI_F32 else np.float64
         xi = np.ascontiguousarray(x, dtype=dt)
@@ -195,10 +198,11 @@ class LatticeField:
         return (out if _is_device(out) else o.keep), st.as_dict()
 
     def time_iterations(self, iterations: int, options: Optional[L.fi_solve_options] = None):
+        """Device ms (totals over `iterations` launches): whole iterations, apply kernels, update, direction; fused?"""
         opt = options if options is not None else solve_options()
-        ms, ms_apply = C.c_double(0), C.c_double(0)
-        L.check(L.lib().fi_field_time_iterations(self._h, C.byref(opt), int(iterations), C.byref(ms), C.byref(ms_apply)))
-        return ms.value, ms_apply.value
+        ms = (C.c_double * 5)()
+        L.check(L.lib().fi_field_time_iterations(self._h, C.byref(opt), int(iterations), ms))
+        return {"iteration_ms": ms[0], "apply_ms": ms[1], "update_ms": ms[2], "direction_ms": ms[3], "fused": bool(ms[4])}
 
 
 # ---- builders (field_interpolation.hpp:116-173) ------------------------------------------------------
@@ -327,8 +331,10 @@ def solve_sparse_linear_exact(field: LatticeField, num_columns: Optional[int] = 
 
 
 def solve_sparse_linear_fast(field: LatticeField, num_columns: Optional[int] = None):
-    """sparse_linear.cpp:115-152 (float Cholesky) -> fp32 PCG inside fp64 refinement."""
-    return _solve(field, solve_options(FI_MIXED, 0, 1e-7))[0]
+    """sparse_linear.cpp:115-152 (float Cholesky).  A direct float factorisation has no iterative analogue that
+    is both cheaper and as robust on these ill-conditioned systems (cond ~ n^4), so this is the fp64 PCG at a
+    float-level tolerance."""
+    return _solve(field, solve_options(FI_F64, 0, 1e-9))[0]
 
 
 def solve_sparse_linear_with_guess(field: LatticeField, guess, max_iterations: int = 0, error_tolerance: float = 0.0):

@@ -67,6 +67,7 @@ struct fi_field
 	fi::ModelAccum                         model;
 	std::unique_ptr<fi::Operator<float>>   op32;
 	std::unique_ptr<fi::Operator<double>>  op64;
+	bool                                   fast = true;  // kernel choice of fi_field_apply
 
 	void invalidate()
 	{
@@ -172,8 +173,16 @@ void add_model_impl(fi_field* f, const fi_weights* w)
 	sg.w    = *w;
 	f->segs.push_back(sg);
 	const float wk[5] = {w->model_0, w->model_1, w->model_2, w->model_3, w->model_4};
+	static const float binom[5][5] = {{1, 0, 0, 0, 0}, {-1, 1, 0, 0, 0}, {1, -2, 1, 0, 0}, {1, -3, 3, -1, 0}, {1, -4, 6, -4, 1}};
 	for (int k = 0; k <= 4; ++k) {
-		if (wk[k] > 0) { f->model.wsq[k] += static_cast<double>(wk[k]) * static_cast<double>(wk[k]); }
+		if (!(wk[k] > 0)) { continue; }  // add_model_constraint emits order-k rows only for w_k > 0 (:257-292)
+		f->model.on[k] = true;
+		for (int a = 0; a <= k; ++a) {
+			for (int b = 0; b <= k; ++b) {
+				const volatile float ca = binom[k][a] * wk[k], cb = binom[k][b] * wk[k];  // fp32, as stored in the triplets
+				f->model.cc[k][a][b] += static_cast<double>(ca) * static_cast<double>(cb);
+			}
+		}
 	}
 	if (w->gradient_smoothness > 0) {
 		f->model.gs_sq += static_cast<double>(w->gradient_smoothness) * static_cast<double>(w->gradient_smoothness);
@@ -536,6 +545,14 @@ int fi_field_export(fi_field* f, fi_triplet* triplets, float* rhs)
 	});
 }
 
+int fi_field_use_fast_stencil(fi_field* f, int32_t enable)
+{
+	return guarded([&] {
+		FI_REQUIRE(f != nullptr, FI_ERR_INVALID, "field is null");
+		f->fast = enable != 0;
+	});
+}
+
 int fi_field_apply(fi_field* f, int32_t precision, const void* x, void* y)
 {
 	return guarded([&] {
@@ -544,12 +561,14 @@ int fi_field_apply(fi_field* f, int32_t precision, const void* x, void* y)
 		cudaStream_t  s = f->stream;
 		if (precision == FI_F32) {
 			Operator<float>& op = f->get32();
+			op.use_fast = f->fast;
 			DevBuf<float>    dx(N), dy(N);
 			FI_CUDA(cudaMemcpyAsync(dx.data(), x, N * sizeof(float), cudaMemcpyHostToDevice, s));
 			op.apply(dx.data(), dy.data(), nullptr, nullptr, s);
 			FI_CUDA(cudaMemcpyAsync(y, dy.data(), N * sizeof(float), cudaMemcpyDeviceToHost, s));
 		} else if (precision == FI_F64) {
 			Operator<double>& op = f->get64();
+			op.use_fast = f->fast;
 			DevBuf<double>    dx(N), dy(N);
 			FI_CUDA(cudaMemcpyAsync(dx.data(), x, N * sizeof(double), cudaMemcpyHostToDevice, s));
 			op.apply(dx.data(), dy.data(), nullptr, nullptr, s);
@@ -729,40 +748,21 @@ int fi_sdf_solve_cascade(int32_t ndim, const int32_t* sizes, const fi_weights* w
 int64_t fi_kernel_launches(void) { return g_launches; }
 void    fi_kernel_launches_reset(void) { g_launches = 0; }
 
-int fi_field_time_iterations(fi_field* f, const fi_solve_options* opt, int32_t iterations, double* ms, double* ms_stencil_only)
+int fi_field_time_iterations(fi_field* f, const fi_solve_options* opt, int32_t iterations, double* ms)
 {
 	return guarded([&] {
-		FI_REQUIRE(f && iterations > 0, FI_ERR_INVALID, "bad argument");
+		FI_REQUIRE(f && ms && iterations > 0, FI_ERR_INVALID, "bad argument");
 		fi_solve_options o;
 		if (opt) { o = *opt; } else { fi_solve_options_default(&o); }
-		const int64_t N = f->g.N;
-		cudaStream_t  s = f->stream;
-		cudaEvent_t   e0, e1;
-		FI_CUDA(cudaEventCreate(&e0));
-		FI_CUDA(cudaEventCreate(&e1));
-		auto run = [&](auto& op, auto zero) {
-			using T = decltype(zero);
+		if (o.precision == FI_F64) {
+			Operator<double>& op = f->get64();
 			op.use_fast = o.use_fast_stencil != 0;
-			DevBuf<T> x(N);
-			x.zero(s);
-			// tolerance 0 is replaced by epsilon; a denormal-small positive tolerance is never met, so exactly
-			// `iterations` iterations run unless CG breaks down.
-			const PcgResult r = pcg_solve<T>(op, nullptr, x.data(), 1e-300, iterations, iterations, false, s);
-			if (ms) { *ms = r.loop_ms; }
-			if (ms_stencil_only) {
-				DevBuf<double> dot(1);
-				FI_CUDA(cudaEventRecord(e0, s));
-				for (int i = 0; i < iterations; ++i) { op.apply(op.work.p.data(), op.work.q.data(), dot.data(), nullptr, s); }
-				FI_CUDA(cudaEventRecord(e1, s));
-				FI_CUDA(cudaEventSynchronize(e1));
-				float t = 0;
-				FI_CUDA(cudaEventElapsedTime(&t, e0, e1));
-				*ms_stencil_only = t;
-			}
-		};
-		if (o.precision == FI_F64) { run(f->get64(), 0.0); } else { run(f->get32(), 0.0f); }
-		cudaEventDestroy(e0);
-		cudaEventDestroy(e1);
+			time_kernels<double>(op, iterations, o.check_every, ms, f->stream);
+		} else {
+			Operator<float>& op = f->get32();
+			op.use_fast = o.use_fast_stencil != 0;
+			time_kernels<float>(op, iterations, o.check_every, ms, f->stream);
+		}
 	});
 }
 

@@ -122,10 +122,14 @@ struct StencilTables
 	bool   any;                  // any smoothness at all
 };
 
-struct ModelAccum  // sum over add_model calls of squared weights (add_model_constraint emits w_k rows iff w_k > 0)
+// Sum over add_model calls of the products of row coefficients.  The reference stores each coefficient as the
+// fp32 product binomial * w_k (add_equation, sparse_linear.cpp:43) before anything is squared, so the products
+// are formed from those rounded values: cc[k][a][b] = sum_calls double(c_ka) * double(c_kb).
+struct ModelAccum
 {
-	double wsq[5] = {0, 0, 0, 0, 0};
-	double gs_sq  = 0;
+	double cc[5][5][5] = {};
+	bool   on[5]       = {false, false, false, false, false};
+	double gs_sq       = 0;  // sum of double(1.0f * w_gs)^2
 };
 
 StencilTables make_tables(const Geom& g, const ModelAccum& m);

@@ -243,6 +243,7 @@ void ensure_work(Operator<T>& op)
 		w.r.resize(n);
 		w.p.resize(n);
 		w.q.resize(n);
+		w.p2.resize(n);
 		w.partial.resize(static_cast<size_t>(3) * (static_cast<size_t>(sm_count()) * 8 + 8));
 		w.ticket.resize(1);
 		w.state.resize(1);
@@ -360,14 +361,26 @@ PcgResult pcg_solve(Operator<T>& op, const T* b, T* x, double tol, long long max
 		const int64_t   before = g_launches;
 		FI_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
 		try {
+			T* pp[2] = {w.p.data(), w.p2.data()};
 			for (int it = 0; it < check_every; ++it) {
 				const int par = it & 1;
-				op.apply(w.p.data(), w.q.data(), d_pq, d_done, s);
-				auto ku = pcg_update_kernel<T>;
-				FI_LAUNCH(ku, grid, kThreads, 0, s, n, x, w.r.data(), w.p.data(), w.q.data(), op.minv.data(), w.state.data(), par,
-				          w.partial.data(), w.ticket.data());
-				auto kd = pcg_direction_kernel<T>;
-				FI_LAUNCH(kd, grid, kThreads, 0, s, n, w.r.data(), op.minv.data(), w.p.data(), w.state.data(), par);
+				// fused form: direction update folded into the stencil's load stage (p ping-pongs between two buffers)
+				const bool fused = op.use_fast &&
+				                   stencil_fast_3d_fused<T>(op.g, op.tabs, w.r.data(), op.minv.data(), pp[par], pp[par ^ 1], w.q.data(),
+				                                            w.state.data(), par, d_pq, op.partial.data(), op.ticket.data(), d_done, s);
+				if (fused) {
+					apply_data_term<T>(op.g, op.data, pp[par ^ 1], w.q.data(), d_pq, d_done, s);
+					auto ku = pcg_update_kernel<T>;
+					FI_LAUNCH(ku, grid, kThreads, 0, s, n, x, w.r.data(), pp[par ^ 1], w.q.data(), op.minv.data(), w.state.data(), par,
+					          w.partial.data(), w.ticket.data());
+				} else {
+					op.apply(w.p.data(), w.q.data(), d_pq, d_done, s);
+					auto ku = pcg_update_kernel<T>;
+					FI_LAUNCH(ku, grid, kThreads, 0, s, n, x, w.r.data(), w.p.data(), w.q.data(), op.minv.data(), w.state.data(), par,
+					          w.partial.data(), w.ticket.data());
+					auto kd = pcg_direction_kernel<T>;
+					FI_LAUNCH(kd, grid, kThreads, 0, s, n, w.r.data(), op.minv.data(), w.p.data(), w.state.data(), par);
+				}
 			}
 		} catch (...) {
 			cudaStreamEndCapture(s, &graph);
@@ -432,6 +445,76 @@ void jacobi_sweeps(Operator<T>& op, T* x, int iterations, T weight, cudaStream_t
 	FI_CUDA(cudaStreamSynchronize(s));
 }
 
+// Per-kernel device times for the roofline figures (fi_field_time_iterations).
+template <typename T>
+void time_kernels(Operator<T>& op, int iterations, int check_every, double* out, cudaStream_t s)
+{
+	ensure_work(op);
+	PcgWork<T>&   w = op.work;
+	const int64_t n = op.g.N;
+	DevBuf<T>     x(n);
+	x.zero(s);
+	// a tolerance far below anything reachable: exactly `iterations` iterations run unless CG breaks down
+	const PcgResult r = pcg_solve<T>(op, nullptr, x.data(), 1e-300, iterations, check_every, false, s);
+	out[0] = r.loop_ms;
+	// re-arm the state so the kernels do real work when launched on their own
+	PcgState h;
+	FI_CUDA(cudaMemcpy(&h, w.state.data(), sizeof(h), cudaMemcpyDeviceToHost));
+	h.done      = 0;
+	h.max_iters = 1ll << 60;
+	h.tol2bb    = 0;
+	h.iters     = 1;
+	if (!(h.rho[0] > 0)) { h.rho[0] = 1; }
+	if (!(h.rho[1] > 0)) { h.rho[1] = 1; }
+	if (!(h.pq > 0)) { h.pq = 1; }
+	FI_CUDA(cudaMemcpy(w.state.data(), &h, sizeof(h), cudaMemcpyHostToDevice));
+	cudaEvent_t e0, e1;
+	FI_CUDA(cudaEventCreate(&e0));
+	FI_CUDA(cudaEventCreate(&e1));
+	auto timed = [&](auto&& body) {
+		FI_CUDA(cudaEventRecord(e0, s));
+		for (int i = 0; i < iterations; ++i) { body(i); }
+		FI_CUDA(cudaEventRecord(e1, s));
+		FI_CUDA(cudaEventSynchronize(e1));
+		float ms = 0;
+		FI_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+		return static_cast<double>(ms);
+	};
+	DevBuf<double> dot(1);
+	T*             pp[2] = {w.p.data(), w.p2.data()};
+	bool           fused = false;
+	out[1] = timed([&](int i) {
+		const int par = i & 1;
+		fused = op.use_fast && stencil_fast_3d_fused<T>(op.g, op.tabs, w.r.data(), op.minv.data(), pp[par], pp[par ^ 1], w.q.data(),
+		                                              w.state.data(), par, dot.data(), op.partial.data(), op.ticket.data(), nullptr, s);
+		if (fused) {
+			apply_data_term<T>(op.g, op.data, pp[par ^ 1], w.q.data(), dot.data(), nullptr, s);
+		} else {
+			op.apply(w.p.data(), w.q.data(), dot.data(), nullptr, s);
+		}
+	});
+	// alpha = rho/pq is recomputed from the (frozen) state each launch; a tiny alpha keeps the vectors finite
+	h.pq = 1e30;
+	FI_CUDA(cudaMemcpy(w.state.data(), &h, sizeof(h), cudaMemcpyHostToDevice));
+	out[2] = timed([&](int i) {
+		auto ku = pcg_update_kernel<T>;
+		FI_LAUNCH(ku, vec_grid(n), kThreads, 0, s, n, x.data(), w.r.data(), w.p.data(), w.q.data(), op.minv.data(), w.state.data(), 0,
+		          w.partial.data(), w.ticket.data());  // reads rho[0], pq (frozen); writes rho[1], rr, iters
+	});
+	out[3] = 0.0;
+	if (!fused) {
+		out[3] = timed([&](int) {
+			auto kd = pcg_direction_kernel<T>;
+			FI_LAUNCH(kd, vec_grid(n), kThreads, 0, s, n, w.r.data(), op.minv.data(), w.p.data(), w.state.data(), 0);
+		});
+	}
+	out[4] = fused ? 1.0 : 0.0;
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+}
+
+template void time_kernels<float>(Operator<float>&, int, int, double*, cudaStream_t);
+template void time_kernels<double>(Operator<double>&, int, int, double*, cudaStream_t);
 template std::unique_ptr<Operator<float>> build_operator<float>(const Geom&, const ModelAccum&, const PointStore&, const HostRows&, cudaStream_t);
 template std::unique_ptr<Operator<double>> build_operator<double>(const Geom&, const ModelAccum&, const PointStore&, const HostRows&, cudaStream_t);
 template PcgResult pcg_solve<float>(Operator<float>&, const float*, float*, double, long long, int, bool, cudaStream_t);

@@ -25,6 +25,7 @@ template <typename T>
 struct PcgWork
 {
 	DevBuf<T>        r, p, q;
+	DevBuf<T>        p2;  // ping-pong partner of p for the fused direction+stencil kernel
 	DevBuf<double>   partial;
 	DevBuf<unsigned> ticket;
 	DevBuf<PcgState> state;
@@ -70,8 +71,18 @@ template <typename T>
 PcgResult pcg_solve(Operator<T>& op, const T* b, T* x, double tol, long long max_iter, int check_every, bool want_true_residual,
                     cudaStream_t s);
 
+// stencil_fast.cu: p_new = M r + beta p_old, q = S p_new, dot = p_new.q in one pass.  false: not applicable.
+template <typename T>
+bool stencil_fast_3d_fused(const Geom& g, const StencilTables& t, const T* r, const T* minv, const T* p_old, T* p_new, T* q,
+                           const PcgState* st, int par, double* d_dot_out, double* d_partial, unsigned* d_ticket, const int* d_done,
+                           cudaStream_t s);
+
 template <typename T>
 void jacobi_sweeps(Operator<T>& op, T* x, int iterations, T weight, cudaStream_t s);
+
+// out[0..4]: see fi_field_time_iterations in include/fi_b200.h.
+template <typename T>
+void time_kernels(Operator<T>& op, int iterations, int check_every, double* out, cudaStream_t s);
 
 // r = b - A x (device), returns |r|^2 and |b|^2.
 template <typename T>

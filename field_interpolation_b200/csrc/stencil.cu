@@ -131,16 +131,15 @@ __global__ void __launch_bounds__(kThreads) stencil_generic_kernel(Geom g, DevTa
 
 StencilTables make_tables(const Geom& g, const ModelAccum& m)
 {
-	static const double binom[5][5] = {{1, 0, 0, 0, 0}, {-1, 1, 0, 0, 0}, {1, -2, 1, 0, 0}, {1, -3, 3, -1, 0}, {1, -4, 6, -4, 1}};
 	StencilTables t;
 	std::memset(&t, 0, sizeof(t));
 	t.gs2    = 2.0 * m.gs_sq;
 	t.radius = 0;
 	for (int k = 0; k <= 4; ++k) {
-		if (m.wsq[k] > 0) { t.radius = k; }
+		if (m.on[k]) { t.radius = k; }
 	}
 	t.any = t.gs2 > 0;
-	for (int k = 0; k <= 4; ++k) { t.any = t.any || m.wsq[k] > 0; }
+	for (int k = 0; k <= 4; ++k) { t.any = t.any || m.on[k]; }
 	for (int d = 0; d < g.ndim; ++d) {
 		const int n = g.size[d];
 		for (int cls = 0; cls < 9; ++cls) {
@@ -152,12 +151,12 @@ StencilTables make_tables(const Geom& g, const ModelAccum& m)
 				i = cls < 4 ? cls : (cls == 4 ? 4 : n - 9 + cls);
 			}
 			for (int k = 0; k <= 4; ++k) {
-				if (!(m.wsq[k] > 0)) { continue; }
+				if (!m.on[k]) { continue; }
 				// rows j of D_k exist for 0 <= j <= n-k-1 and touch nodes j..j+k
 				for (int j = std::max(0, i - k); j <= std::min(i, n - k - 1); ++j) {
 					for (int mm = 0; mm <= k; ++mm) {
 						const int o = j + mm - i;  // neighbour offset
-						t.band[d][cls][o + 4] += m.wsq[k] * binom[k][i - j] * binom[k][mm];
+						t.band[d][cls][o + 4] += m.cc[k][i - j][mm];
 					}
 				}
 			}

@@ -138,6 +138,9 @@ FI_API int fi_field_export(fi_field* f, fi_triplet* triplets, float* rhs);
 /* y = (AtA) x, Atb and diag(AtA) of everything added so far; make_square / Atb, sparse_linear.cpp:105-113,
  * :120.  x, y: N elements of float (FI_F32) or double (FI_F64), host buffers. */
 FI_API int fi_field_apply(fi_field* f, int32_t precision, const void* x, void* y);
+/* Selects the kernel fi_field_apply uses for the smoothness part: 1 (default) specialised kernels where
+ * applicable, 0 the generic reference-shaped kernel.  fi_field_solve takes the same switch in its options. */
+FI_API int fi_field_use_fast_stencil(fi_field* f, int32_t enable);
 FI_API int fi_field_rhs(fi_field* f, int32_t precision, void* atb);
 FI_API int fi_field_diagonal(fi_field* f, int32_t precision, void* diag);
 
@@ -191,10 +194,15 @@ FI_API int fi_sdf_solve_cascade(int32_t ndim, const int32_t* sizes, const fi_wei
 FI_API int64_t fi_kernel_launches(void);
 FI_API void    fi_kernel_launches_reset(void);
 
-/* Times `iterations` PCG iterations (no convergence test) of the already-built operator, for the roofline
- * of the CG kernels: returns device milliseconds measured with CUDA events on the solver stream. */
-FI_API int fi_field_time_iterations(fi_field* f, const fi_solve_options* opt, int32_t iterations, double* ms,
-                             double* ms_stencil_only);
+/* Times the CG kernels of the already-built operator with CUDA events on the solver stream (device
+ * milliseconds, totals over `iterations` launches), for the roofline figures:
+ *   ms[0] `iterations` whole PCG iterations as fi_field_solve runs them (CUDA graph, no convergence stop)
+ *   ms[1] the operator-apply kernels alone, back to back: the fused direction+stencil kernel when the solve
+ *         uses it, else the stencil kernel (plus the data-term kernels)
+ *   ms[2] the update kernel alone (x += a p, r -= a q, r.Mr, r.r)
+ *   ms[3] the direction kernel alone (0 when it is fused into the stencil)
+ *   ms[4] 1 if the fused kernel is in use, else 0 */
+FI_API int fi_field_time_iterations(fi_field* f, const fi_solve_options* opt, int32_t iterations, double* ms);
 
 #ifdef __cplusplus
 }
