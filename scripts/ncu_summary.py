@@ -1,0 +1,104 @@
+"""Turns ncu output brought back in gpurun_out/ into the small text summaries kept under profiles/.
+
+    python scripts/ncu_summary.py launches gpurun_out/launches.csv          > profiles/rNN_launches.md
+    python scripts/ncu_summary.py full gpurun_out/prof.ncu-rep [regex]       > profiles/rNN_full.md
+"""
+import collections
+import csv
+import io
+import re
+import subprocess
+import sys
+
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__t_sector_hit_rate.pct", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__maximum_warps_per_active_cycle_pct",
+        "launch__registers_per_thread", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+        "launch__shared_mem_per_block_static", "launch__shared_mem_per_block_dynamic", "launch__grid_size",
+        "launch__block_size", "launch__waves_per_multiprocessor", "smsp__inst_executed.sum",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
+
+
+def short(name):
+    name = re.sub(r"\(.*", "", name)
+    return name.replace("void ", "").replace("fi::<unnamed>::", "").replace("unnamed>::", "").strip()
+
+
+def launches(path):
+    lines = [l for l in open(path) if not l.startswith("==")]
+    agg = collections.OrderedDict()
+    for row in csv.DictReader(lines):
+        if row.get("Metric Name") != "gpu__time_duration.sum":
+            continue
+        v = float(row["Metric Value"].replace(",", ""))
+        v = {"ns": v / 1e3, "us": v, "ms": v * 1e3, "s": v * 1e6}.get(row["Metric Unit"], v)
+        key = (short(row["Kernel Name"]), row["Grid Size"], row["Block Size"])
+        a = agg.setdefault(key, [0, 0.0])
+        a[0] += 1
+        a[1] += v
+    tot = sum(v[1] for v in agg.values())
+    print(f"| kernel | grid | block | launches | total us | share | avg us |\n|---|---|---|---:|---:|---:|---:|")
+    for (k, g, b), v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"| `{k}` | {g} | {b} | {v[0]} | {v[1]:.1f} | {100 * v[1] / tot:.1f}% | {v[1] / v[0]:.1f} |")
+    print(f"\ntotal {tot:.1f} us over {sum(v[0] for v in agg.values())} launches (ncu per-launch times: cold-cache, serialised)")
+
+
+def full(path, pattern=None):
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    ix = {h: i for i, h in enumerate(hdr)}
+    seen = set()
+    for r in rows[2:]:
+        name = short(r[ix["Kernel Name"]])
+        if pattern and not re.search(pattern, name):
+            continue
+        if name in seen:
+            continue
+        seen.add(name)
+        print(f"\n### `{name}`  grid {r[ix['Grid Size']]} block {r[ix['Block Size']]}\n")
+        print("| metric | value | unit |\n|---|---:|---|")
+        for k in KEYS:
+            if k in ix:
+                print(f"| {k} | {r[ix[k]]} | {units[ix[k]]} |")
+    src = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    secs, cur = [], None
+    for r in csv.reader(io.StringIO(src)):
+        if r and r[0] == "Kernel Name":
+            cur = {"name": short(r[1]), "hdr": None, "rows": []}
+            secs.append(cur)
+        elif cur is not None and cur["hdr"] is None:
+            cur["hdr"] = r
+        elif cur is not None:
+            cur["rows"].append(r)
+    seen = set()
+    for s in secs:
+        if (pattern and not re.search(pattern, s["name"])) or s["name"] in seen or not s["hdr"]:
+            continue
+        seen.add(s["name"])
+        h = s["hdr"]
+        ix = {k: i for i, k in enumerate(h)}
+        stalls = [k for k in h if k.startswith("stall_") and "Not Issued" not in k]
+        tot = {k: 0 for k in stalls}
+        ns = 0
+        good = [r for r in s["rows"] if len(r) >= len(h)]
+        for r in good:
+            for k in stalls:
+                tot[k] += int(r[ix[k]] or 0)
+            ns += int(r[ix["# Samples"]] or 0)
+        print(f"\n### warp-stall samples, `{s['name']}` ({ns} samples)\n")
+        print(", ".join(f"{k[6:]} {100 * v / max(ns, 1):.1f}%" for k, v in sorted(tot.items(), key=lambda kv: -kv[1])[:8]))
+        print("\n| samples | SASS | dominant stall |\n|---:|---|---|")
+        for r in sorted(good, key=lambda r: -int(r[ix["# Samples"]] or 0))[:12]:
+            st = {k: int(r[ix[k]] or 0) for k in stalls}
+            m = max(st, key=st.get)
+            print(f"| {r[ix['# Samples']]} | `{r[ix['Source']].strip()[:80]}` | {m[6:]} |")
+
+
+if __name__ == "__main__":
+    if sys.argv[1] == "launches":
+        launches(sys.argv[2])
+    else:
+        full(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None)
