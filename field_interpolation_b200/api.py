@@ -106,7 +106,7 @@ def _common_loc(bufs):
 def solve_options(precision=FI_F32, max_iterations=0, tolerance=1e-3, check_every=32, use_fast_stencil=True,
                   refine_max_outer=20, refine_inner_tolerance=1e-3) -> L.fi_solve_options:
     return L.fi_solve_options(int(precision), int(max_iterations), float(tolerance), int(check_every),
-                              1 if use_fast_stencil else 0, int(refine_max_outer), float(refine_inner_tolerance))
+                              int(use_fast_stencil), int(refine_max_outer), float(refine_inner_tolerance))
 
 
 class LatticeField:
@@ -168,8 +168,9 @@ class LatticeField:
     def diagonal(self, precision=FI_F64):
         return self._vec(L.lib().fi_field_diagonal, precision)
 
-    def use_fast_stencil(self, enable: bool):
-        L.check(L.lib().fi_field_use_fast_stencil(self._h, 1 if enable else 0))
+    def use_fast_stencil(self, mode):
+        """0/False generic kernel, 1/True best specialised kernel (TMA-staged), 2 tiled kernel without TMA."""
+        L.check(L.lib().fi_field_use_fast_stencil(self._h, int(mode)))
 
     def apply(self, x, precision=FI_F64):
         dt = np.float32 if precision == FI_F32 else np.float64

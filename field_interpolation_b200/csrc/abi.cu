@@ -67,7 +67,7 @@ struct fi_field
 	fi::ModelAccum                         model;
 	std::unique_ptr<fi::Operator<float>>   op32;
 	std::unique_ptr<fi::Operator<double>>  op64;
-	bool                                   fast = true;  // kernel choice of fi_field_apply
+	int                                    fast = fi::kStencilAuto;  // kernel choice of fi_field_apply
 
 	void invalidate()
 	{
@@ -261,7 +261,7 @@ void solve_device(fi_field* f, const fi_solve_options& o, const float* d_guess, 
 {
 	const int64_t N = f->g.N;
 	cudaStream_t  s = f->stream;
-	const bool    fast = o.use_fast_stencil != 0;
+	const int     fast = o.use_fast_stencil;
 	if (o.precision == FI_F32) {
 		const bool fresh = !f->op32;
 		Operator<float>& op = f->get32();
@@ -549,7 +549,7 @@ int fi_field_use_fast_stencil(fi_field* f, int32_t enable)
 {
 	return guarded([&] {
 		FI_REQUIRE(f != nullptr, FI_ERR_INVALID, "field is null");
-		f->fast = enable != 0;
+		f->fast = enable;
 	});
 }
 
@@ -756,11 +756,11 @@ int fi_field_time_iterations(fi_field* f, const fi_solve_options* opt, int32_t i
 		if (opt) { o = *opt; } else { fi_solve_options_default(&o); }
 		if (o.precision == FI_F64) {
 			Operator<double>& op = f->get64();
-			op.use_fast = o.use_fast_stencil != 0;
+			op.use_fast = o.use_fast_stencil;
 			time_kernels<double>(op, iterations, o.check_every, ms, f->stream);
 		} else {
 			Operator<float>& op = f->get32();
-			op.use_fast = o.use_fast_stencil != 0;
+			op.use_fast = o.use_fast_stencil;
 			time_kernels<float>(op, iterations, o.check_every, ms, f->stream);
 		}
 	});

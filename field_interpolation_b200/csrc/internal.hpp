@@ -140,10 +140,12 @@ void stencil_diagonal(const Geom& g, const StencilTables& t, T* d_diag /* += */,
 // q = S p (overwrites q).  When d_dot_out is non-null, p.q is reduced deterministically (per-block partials in
 // d_partial, summed in block order by the last block to arrive) and *stored* to d_dot_out[0].  d_done
 // (nullable) is the solver's device-side convergence flag: the kernel returns at once when it is set.
-// use_fast selects the specialised 3D kernel when applicable.
+// mode selects the kernel: generic (reference-shaped, any dimension / weights), auto (TMA-staged 3D kernel when
+// applicable, else the tiled one, else generic), tiled (register-pipeline 3D kernel without TMA, else generic).
+enum StencilMode { kStencilGeneric = 0, kStencilAuto = 1, kStencilTiled = 2 };
 template <typename T>
 void stencil_apply(const Geom& g, const StencilTables& t, const T* p, T* q, double* d_dot_out, double* d_partial,
-                   unsigned* d_ticket, const int* d_done, bool use_fast, cudaStream_t s);
+                   unsigned* d_ticket, const int* d_done, int mode, cudaStream_t s);
 int stencil_partial_slots(const Geom& g);  // upper bound of blocks any stencil launch uses (size of d_partial)
 
 }  // namespace fi

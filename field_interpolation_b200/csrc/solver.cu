@@ -365,9 +365,8 @@ PcgResult pcg_solve(Operator<T>& op, const T* b, T* x, double tol, long long max
 			for (int it = 0; it < check_every; ++it) {
 				const int par = it & 1;
 				// fused form: direction update folded into the stencil's load stage (p ping-pongs between two buffers)
-				const bool fused = op.use_fast &&
-				                   stencil_fast_3d_fused<T>(op.g, op.tabs, w.r.data(), op.minv.data(), pp[par], pp[par ^ 1], w.q.data(),
-				                                            w.state.data(), par, d_pq, op.partial.data(), op.ticket.data(), d_done, s);
+				const bool fused = stencil_fused_step<T>(op.use_fast, op.g, op.tabs, w.r.data(), op.minv.data(), pp[par], pp[par ^ 1], w.q.data(),
+				                                         w.state.data(), par, d_pq, op.partial.data(), op.ticket.data(), d_done, s);
 				if (fused) {
 					apply_data_term<T>(op.g, op.data, pp[par ^ 1], w.q.data(), d_pq, d_done, s);
 					auto ku = pcg_update_kernel<T>;
@@ -485,8 +484,8 @@ void time_kernels(Operator<T>& op, int iterations, int check_every, double* out,
 	bool           fused = false;
 	out[1] = timed([&](int i) {
 		const int par = i & 1;
-		fused = op.use_fast && stencil_fast_3d_fused<T>(op.g, op.tabs, w.r.data(), op.minv.data(), pp[par], pp[par ^ 1], w.q.data(),
-		                                              w.state.data(), par, dot.data(), op.partial.data(), op.ticket.data(), nullptr, s);
+		fused = stencil_fused_step<T>(op.use_fast, op.g, op.tabs, w.r.data(), op.minv.data(), pp[par], pp[par ^ 1], w.q.data(),
+		                              w.state.data(), par, dot.data(), op.partial.data(), op.ticket.data(), nullptr, s);
 		if (fused) {
 			apply_data_term<T>(op.g, op.data, pp[par ^ 1], w.q.data(), dot.data(), nullptr, s);
 		} else {

@@ -41,7 +41,7 @@ struct Operator
 	DevBuf<T>        atb, diag, minv;
 	DevBuf<double>   partial;  // stencil reduction scratch
 	DevBuf<unsigned> ticket;
-	bool             use_fast = true;
+	int              use_fast = kStencilAuto;  // StencilMode
 	double           setup_ms = 0;
 	PcgWork<T>       work;
 
@@ -76,6 +76,23 @@ template <typename T>
 bool stencil_fast_3d_fused(const Geom& g, const StencilTables& t, const T* r, const T* minv, const T* p_old, T* p_new, T* q,
                            const PcgState* st, int par, double* d_dot_out, double* d_partial, unsigned* d_ticket, const int* d_done,
                            cudaStream_t s);
+
+// stencil_tma.cu: the same fused step with TMA-staged loads.  false: not applicable.
+template <typename T>
+bool stencil_tma_3d_fused(const Geom& g, const StencilTables& t, const T* r, const T* minv, const T* p_old, T* p_new, T* q,
+                          const PcgState* st, int par, double* d_dot_out, double* d_partial, unsigned* d_ticket, const int* d_done,
+                          cudaStream_t s);
+
+// The fused direction+stencil step in the given StencilMode; false when no fused kernel applies.
+template <typename T>
+inline bool stencil_fused_step(int mode, const Geom& g, const StencilTables& t, const T* r, const T* minv, const T* p_old, T* p_new,
+                               T* q, const PcgState* st, int par, double* d_dot_out, double* d_partial, unsigned* d_ticket,
+                               const int* d_done, cudaStream_t s)
+{
+	if (mode == kStencilAuto && stencil_tma_3d_fused<T>(g, t, r, minv, p_old, p_new, q, st, par, d_dot_out, d_partial, d_ticket, d_done, s)) { return true; }
+	if (mode != kStencilGeneric && stencil_fast_3d_fused<T>(g, t, r, minv, p_old, p_new, q, st, par, d_dot_out, d_partial, d_ticket, d_done, s)) { return true; }
+	return false;
+}
 
 template <typename T>
 void jacobi_sweeps(Operator<T>& op, T* x, int iterations, T weight, cudaStream_t s);

@@ -179,19 +179,23 @@ int stencil_partial_slots(const Geom& g) { return div_up(g.N, kThreads) + 8; }
 template <typename T>
 bool stencil_fast_3d(const Geom& g, const StencilTables& t, const T* p, T* q, double* d_dot_out, double* d_partial,
                      unsigned* d_ticket, const int* d_done, cudaStream_t s);  // stencil_fast.cu
+template <typename T>
+bool stencil_tma_3d(const Geom& g, const StencilTables& t, const T* p, T* q, double* d_dot_out, double* d_partial,
+                    unsigned* d_ticket, const int* d_done, cudaStream_t s);  // stencil_tma.cu
 
 template <typename T>
 void stencil_apply(const Geom& g, const StencilTables& t, const T* p, T* q, double* d_dot_out, double* d_partial,
-                   unsigned* d_ticket, const int* d_done, bool use_fast, cudaStream_t s)
+                   unsigned* d_ticket, const int* d_done, int mode, cudaStream_t s)
 {
-	if (use_fast && stencil_fast_3d<T>(g, t, p, q, d_dot_out, d_partial, d_ticket, d_done, s)) { return; }
+	if (mode == kStencilAuto && stencil_tma_3d<T>(g, t, p, q, d_dot_out, d_partial, d_ticket, d_done, s)) { return; }
+	if (mode != kStencilGeneric && stencil_fast_3d<T>(g, t, p, q, d_dot_out, d_partial, d_ticket, d_done, s)) { return; }
 	auto kern = stencil_generic_kernel<T>;
 	FI_LAUNCH(kern, div_up(g.N, kThreads), kThreads, 0, s, g, to_dev<T>(t), p, q, d_dot_out, d_partial, d_ticket, d_done);
 }
 
 template void stencil_diagonal<float>(const Geom&, const StencilTables&, float*, cudaStream_t);
 template void stencil_diagonal<double>(const Geom&, const StencilTables&, double*, cudaStream_t);
-template void stencil_apply<float>(const Geom&, const StencilTables&, const float*, float*, double*, double*, unsigned*, const int*, bool, cudaStream_t);
-template void stencil_apply<double>(const Geom&, const StencilTables&, const double*, double*, double*, double*, unsigned*, const int*, bool, cudaStream_t);
+template void stencil_apply<float>(const Geom&, const StencilTables&, const float*, float*, double*, double*, unsigned*, const int*, int, cudaStream_t);
+template void stencil_apply<double>(const Geom&, const StencilTables&, const double*, double*, double*, double*, unsigned*, const int*, int, cudaStream_t);
 
 }  // namespace fi

@@ -1,0 +1,421 @@
+// TMA-staged 3D smoothness kernel for sm_100a: q = S p (+ p.q), optionally with the CG direction update
+// p = M r + beta p_old folded into the load stage — north-star item (b), the roofline kernel of the solve.
+//
+// Same mathematics as stencil_fast.cu (2.5-D blocking of the star-shaped operator built from the reference's
+// model rows, field_interpolation/field_interpolation.cpp:243-316), different data movement:
+//   * one elected thread issues cp.async.bulk.tensor (TMA) loads of whole xy boxes — tile plus halo, one z
+//     plane per stage, for each of the 1 (plain) or 3 (fused: r, M^-1, p_old) input arrays — into a ring of
+//     S shared-memory stages guarded by mbarriers, S planes ahead of use.  Loads cost no registers and no
+//     address arithmetic in the compute warps, and lattice boundaries need no branches: the tensor map's
+//     out-of-bounds fill supplies the zeros that the dropped difference rows imply;
+//   * the 256 compute threads turn a landed stage into the new direction p (tile and halo) in a second
+//     shared-memory ring of R+2 planes, keep their own z column in a register pipeline of 2R+1 packs (the
+//     plane loop is unrolled 2R+1 times so the pipeline rotates by renaming, not by moves), and evaluate the
+//     2R+1 taps per axis with per-thread coefficient rows that already contain the boundary truncation;
+//   * q and p are written with 128-bit coalesced stores straight from registers.
+// One __syncthreads and one mbarrier wait per plane.
+#include <cuda.h>
+
+#include <mutex>
+
+#include "internal.hpp"
+#include "solver.hpp"
+
+namespace fi {
+
+namespace {
+
+__host__ __device__ __forceinline__ int row_class(int i, int n)
+{
+	return n <= 9 ? i : (i < 4 ? i : (i >= n - 4 ? i - n + 9 : 4));
+}
+
+template <typename T>
+struct PackOf;
+template <>
+struct PackOf<float>
+{
+	using type = float4;
+};
+template <>
+struct PackOf<double>
+{
+	using type = double2;
+};
+
+template <typename T, int V>
+union PackU
+{
+	typename PackOf<T>::type v;
+	T                        a[V];
+};
+
+template <typename T>
+struct TmaTables
+{
+	T band[kMaxDim][9][9];
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+	asm volatile(
+	    "{\n"
+	    ".reg .pred p;\n"
+	    "FI_WAIT:\n"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+	    "@p bra FI_DONE;\n"
+	    "bra FI_WAIT;\n"
+	    "FI_DONE:\n"
+	    "}\n" ::"r"(smem_u32(bar)),
+	    "r"(parity)
+	    : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int z)
+{
+	asm volatile(
+	    "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+	        smem_u32(dst)),
+	    "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
+	    : "memory");
+}
+
+// ---- geometry of one block -----------------------------------------------------------------------------------
+template <typename T, int R>
+struct Tile
+{
+	static constexpr int V    = 16 / sizeof(T);       // elements per 16-byte pack
+	static constexpr int NP   = (R + V - 1) / V;      // halo packs per side in x
+	static constexpr int TXP  = 32;                   // packs per tile row (one per lane)
+	static constexpr int TY   = 8;                    // tile rows (one per warp)
+	static constexpr int BXP  = TXP + 2 * NP;         // box row in packs
+	static constexpr int BY   = TY + 2 * R;           // box rows
+	static constexpr int RING = R + 2;                // planes of the new direction kept in shared memory
+	static constexpr int TILE_BYTES = ((BXP * BY * 16 + 127) / 128) * 128;
+	static constexpr int BOX_BYTES  = BXP * BY * 16;  // what one TMA load delivers
+};
+
+template <typename T, int R, int S, bool Fused>
+constexpr size_t smem_bytes()
+{
+	using G = Tile<T, R>;
+	return 128 /* alignment slack */ + static_cast<size_t>(S) * (Fused ? 3 : 1) * G::TILE_BYTES + static_cast<size_t>(G::RING) * G::TILE_BYTES +
+	       S * sizeof(uint64_t) + 9 * (2 * R + 1) * sizeof(T) + 32 * sizeof(double) + 64;
+}
+
+template <typename T, int R, int S, bool Fused, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+    stencil3d_tma_kernel(const __grid_constant__ CUtensorMap map_a,  // p (plain) or r (fused)
+                         const __grid_constant__ CUtensorMap map_b,  // M^-1 (fused)
+                         const __grid_constant__ CUtensorMap map_c,  // p_old (fused)
+                         int nx, int ny, int nz, int zchunk, TmaTables<T> tab, T* __restrict__ q, T* __restrict__ p_new,
+                         const PcgState* st, int par, double* dot_out, double* partial, unsigned* ticket, const int* done)
+{
+	using G           = Tile<T, R>;
+	constexpr int V   = G::V;
+	constexpr int NP  = G::NP;
+	constexpr int NA  = Fused ? 3 : 1;
+	constexpr int W   = 2 * R + 1;
+	using Pack        = typename PackOf<T>::type;
+	using PU          = PackU<T, V>;
+
+	if (done && *done) { return; }
+
+	extern __shared__ unsigned char smem_raw[];
+	unsigned char* base = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+	auto stage_ptr = [&](int s, int a) { return reinterpret_cast<Pack*>(base + (static_cast<size_t>(s) * NA + a) * G::TILE_BYTES); };
+	unsigned char* ring_base = base + static_cast<size_t>(S) * NA * G::TILE_BYTES;
+	auto ring_ptr = [&](int slot) { return reinterpret_cast<Pack*>(ring_base + static_cast<size_t>(slot) * G::TILE_BYTES); };
+	uint64_t* full  = reinterpret_cast<uint64_t*>(ring_base + static_cast<size_t>(G::RING) * G::TILE_BYTES);
+	T*        zband = reinterpret_cast<T*>(full + S);                                      // [9][W]
+	double*   red   = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(zband + 9 * W) + 7) & ~uintptr_t(7));
+
+	const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+	const int x0t = blockIdx.x * (G::TXP * V);  // first element column of the tile
+	const int y0t = blockIdx.y * G::TY;
+	const int x0  = x0t + tx * V;
+	const int y   = y0t + ty;
+	const int zb  = blockIdx.z * zchunk;
+	const int ze  = min(nz, zb + zchunk);
+	const bool   in_xy = (x0 < nx) && (y < ny);
+	const size_t plane = static_cast<size_t>(nx) * ny;
+
+	if (tid == 0) {
+#pragma unroll
+		for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); }
+		fence_barrier_init();
+	}
+	for (int k = tid; k < 9 * W; k += 256) { zband[k] = tab.band[2][k / W][k % W + 4 - R]; }
+
+	T beta = 0;
+	if (Fused) { beta = st->iters == 0 ? T(0) : static_cast<T>(st->rho[par] / st->rho[par ^ 1]); }
+
+	// per-thread x / y coefficient rows (boundary truncation included)
+	T cx[V][W], cy[W];
+#pragma unroll
+	for (int j = 0; j < V; ++j) {
+		const int cls = row_class(min(x0 + j, nx - 1), nx);
+#pragma unroll
+		for (int t = 0; t < W; ++t) { cx[j][t] = tab.band[0][cls][t + 4 - R]; }
+	}
+	{
+		const int cls = row_class(min(y, ny - 1), ny);
+#pragma unroll
+		for (int t = 0; t < W; ++t) { cy[t] = tab.band[1][cls][t + 4 - R]; }
+	}
+
+	const int lp0    = zb - R;             // first plane loaded
+	const int n_iter = ze + R - lp0;       // planes loaded by this block
+	auto issue = [&](int i) {              // thread 0 only: plane lp0 + i into stage i % S
+		const int s = i % S;
+		mbar_expect_tx(&full[s], NA * G::BOX_BYTES);
+		tma_load_3d(stage_ptr(s, 0), &map_a, &full[s], x0t - NP * V, y0t - R, lp0 + i);
+		if (Fused) {
+			tma_load_3d(stage_ptr(s, 1), &map_b, &full[s], x0t - NP * V, y0t - R, lp0 + i);
+			tma_load_3d(stage_ptr(s, 2), &map_c, &full[s], x0t - NP * V, y0t - R, lp0 + i);
+		}
+	};
+	__syncthreads();  // barriers initialised, zband visible
+	if (tid == 0) {
+		for (int i = 0; i < S && i < n_iter; ++i) { issue(i); }
+	}
+
+	// halo duties: one y-halo pack (warps 0..2R-1) and one x-halo pack (first 2*NP*TY threads) per plane
+	const bool has_yh = ty < 2 * R;
+	const int  yh_row = ty < R ? ty : G::TY + ty;
+	const bool has_xh = tid < 2 * NP * G::TY;
+	const int  xh_r   = (tid / (2 * NP)) + R;
+	const int  xh_k   = tid % (2 * NP);
+	const int  xh_col = xh_k < NP ? xh_k : G::TXP + xh_k;
+	const int  own_at = (ty + R) * G::BXP + tx + NP;
+	const int  yh_at  = yh_row * G::BXP + tx + NP;
+	const int  xh_at  = xh_r * G::BXP + xh_col;
+
+	auto direction = [&](const Pack* sa, const Pack* sb, const Pack* sc, int at) -> Pack {
+		if (!Fused) { return sa[at]; }
+		PU rr, mm, pp, out;
+		rr.v = sa[at];
+		mm.v = sb[at];
+		pp.v = sc[at];
+#pragma unroll
+		for (int j = 0; j < V; ++j) { out.a[j] = mm.a[j] * rr.a[j] + beta * pp.a[j]; }
+		return out.v;
+	};
+
+	PU     pipe[W];
+	double acc = 0.0;
+	T*       qout = q + static_cast<size_t>(y) * nx + x0;
+	T*       pout = Fused ? p_new + static_cast<size_t>(y) * nx + x0 : nullptr;
+
+	int stage = 0, slot = 0;
+	uint32_t phase = 0;
+	for (int i0 = 0; i0 < n_iter; i0 += W) {
+#pragma unroll
+		for (int k = 0; k < W; ++k) {
+			const int i = i0 + k;
+			if (i >= n_iter) { break; }
+			const int lp = lp0 + i;
+			mbar_wait(&full[stage], phase);
+			const Pack* sa = stage_ptr(stage, 0);
+			const Pack* sb = Fused ? stage_ptr(stage, 1) : nullptr;
+			const Pack* sc = Fused ? stage_ptr(stage, 2) : nullptr;
+			Pack*       rg = ring_ptr(slot);
+			// newest plane of the own column -> pipe[k]; plane lp - 2R + t sits in pipe[(k + 1 + t) % W]
+			pipe[k].v  = direction(sa, sb, sc, own_at);
+			rg[own_at] = pipe[k].v;
+			if (has_yh) { rg[yh_at] = direction(sa, sb, sc, yh_at); }
+			if (has_xh) { rg[xh_at] = direction(sa, sb, sc, xh_at); }
+			if (Fused && in_xy && lp >= zb && lp < ze) { *reinterpret_cast<Pack*>(pout + static_cast<size_t>(lp) * plane) = pipe[k].v; }
+			__syncthreads();
+			if (tid == 0 && i + S < n_iter) { issue(i + S); }
+
+			const int z = lp - R;
+			if (z >= zb && in_xy) {
+				int zslot = slot - R;
+				if (zslot < 0) { zslot += G::RING; }
+				const Pack* pz = ring_ptr(zslot);
+				const T*    cz = zband + row_class(z, nz) * W;
+				const PU&   ctr = pipe[(k + 1 + R) % W];
+				PU          out;
+#pragma unroll
+				for (int j = 0; j < V; ++j) {
+					T s = T(0);
+#pragma unroll
+					for (int t = 0; t < W; ++t) { s += cz[t] * pipe[(k + 1 + t) % W].a[j]; }
+					out.a[j] = s;
+				}
+#pragma unroll
+				for (int t = 0; t < W; ++t) {
+					if (t == R) {
+#pragma unroll
+						for (int j = 0; j < V; ++j) { out.a[j] += cy[t] * ctr.a[j]; }
+					} else {
+						PU nb;
+						nb.v = pz[(ty + t) * G::BXP + tx + NP];
+#pragma unroll
+						for (int j = 0; j < V; ++j) { out.a[j] += cy[t] * nb.a[j]; }
+					}
+				}
+				T xs[(2 * NP + 1) * V];
+#pragma unroll
+				for (int kk = 0; kk < 2 * NP + 1; ++kk) {
+					PU nb;
+					if (kk == NP) { nb = ctr; } else { nb.v = pz[(ty + R) * G::BXP + tx + kk]; }
+#pragma unroll
+					for (int j = 0; j < V; ++j) { xs[kk * V + j] = nb.a[j]; }
+				}
+#pragma unroll
+				for (int j = 0; j < V; ++j) {
+#pragma unroll
+					for (int t = 0; t < W; ++t) { out.a[j] += cx[j][t] * xs[NP * V + j + t - R]; }
+				}
+				*reinterpret_cast<Pack*>(qout + static_cast<size_t>(z) * plane) = out.v;
+				T d = T(0);
+#pragma unroll
+				for (int j = 0; j < V; ++j) { d += out.a[j] * ctr.a[j]; }
+				acc += static_cast<double>(d);
+			}
+			if (++stage == S) { stage = 0; phase ^= 1u; }
+			if (++slot == G::RING) { slot = 0; }
+		}
+	}
+
+	if (dot_out) {
+		double mine[1] = {block_sum(acc, red)};
+		grid_sum<1>(mine, partial, ticket, red, [&](const double(&tot)[1]) { *dot_out = tot[0]; });
+	}
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn encode_fn()
+{
+	static EncodeFn   fn = nullptr;
+	static std::once_flag once;
+	std::call_once(once, [] {
+		void*                            p = nullptr;
+		cudaDriverEntryPointQueryResult  qr;
+		if (cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &p, 12000, cudaEnableDefault, &qr) == cudaSuccess &&
+		    qr == cudaDriverEntryPointSuccess) {
+			fn = reinterpret_cast<EncodeFn>(p);
+		}
+	});
+	return fn;
+}
+
+template <typename T, int R>
+CUtensorMap make_map(const Geom& g, const T* ptr)
+{
+	using G = Tile<T, R>;
+	CUtensorMap m;
+	std::memset(&m, 0, sizeof(m));
+	EncodeFn fn = encode_fn();
+	FI_REQUIRE(fn != nullptr, FI_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+	const cuuint64_t dims[3]    = {static_cast<cuuint64_t>(g.size[0]), static_cast<cuuint64_t>(g.size[1]), static_cast<cuuint64_t>(g.size[2])};
+	const cuuint64_t strides[2] = {static_cast<cuuint64_t>(g.size[0]) * sizeof(T), static_cast<cuuint64_t>(g.size[0]) * g.size[1] * sizeof(T)};
+	const cuuint32_t box[3]     = {static_cast<cuuint32_t>(G::BXP * G::V), static_cast<cuuint32_t>(G::BY), 1u};
+	const cuuint32_t estr[3]    = {1u, 1u, 1u};
+	const CUresult   r = fn(&m, sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3,
+	                        const_cast<T*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+	                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	FI_REQUIRE(r == CUDA_SUCCESS, FI_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)));
+	return m;
+}
+
+template <typename T, int R, int S, bool Fused, int MINB>
+void launch(const Geom& g, const StencilTables& t, const T* a, const T* b, const T* c, T* q, T* p_new, const PcgState* st, int par,
+            double* d_dot_out, double* d_partial, unsigned* d_ticket, const int* d_done, cudaStream_t s)
+{
+	using G = Tile<T, R>;
+	TmaTables<T> tab;
+	for (int ax = 0; ax < kMaxDim; ++ax) {
+		for (int cl = 0; cl < 9; ++cl) {
+			for (int k = 0; k < 9; ++k) { tab.band[ax][cl][k] = static_cast<T>(t.band[ax][cl][k]); }
+		}
+	}
+	const CUtensorMap ma = make_map<T, R>(g, a);
+	const CUtensorMap mb = Fused ? make_map<T, R>(g, b) : ma;
+	const CUtensorMap mc = Fused ? make_map<T, R>(g, c) : ma;
+	const int tiles_x = div_up(g.size[0], G::TXP * G::V), tiles_y = div_up(g.size[1], G::TY);
+	// z chunking: enough blocks for ~8 waves of MINB resident blocks per SM, chunks of at least 16 planes
+	const int64_t resident    = static_cast<int64_t>(sm_count()) * MINB;
+	const int64_t want_blocks = resident * 8;
+	int           chunks      = static_cast<int>(std::max<int64_t>(1, want_blocks / (static_cast<int64_t>(tiles_x) * tiles_y)));
+	chunks                    = std::min(chunks, std::max(1, g.size[2] / 16));
+	const int zchunk          = div_up(g.size[2], chunks);
+	chunks                    = div_up(g.size[2], zchunk);
+	dim3 grid(tiles_x, tiles_y, chunks);
+	auto kern = stencil3d_tma_kernel<T, R, S, Fused, MINB>;
+	constexpr size_t smem = smem_bytes<T, R, S, Fused>();
+	static bool configured = false;  // per instantiation
+	if (!configured) {
+		FI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+		configured = true;
+	}
+	FI_LAUNCH(kern, grid, 256, smem, s, ma, mb, mc, g.size[0], g.size[1], g.size[2], zchunk, tab, q, p_new, st, par, d_dot_out,
+	          d_partial, d_ticket, d_done);
+}
+
+template <typename T>
+bool eligible(const Geom& g, const StencilTables& t)
+{
+	constexpr int V = 16 / sizeof(T);
+	return g.ndim == 3 && t.gs2 == 0.0 && t.radius >= 1 && g.size[0] % V == 0 && g.size[0] >= 32 && g.size[1] >= 8 && g.size[2] >= 8 &&
+	       encode_fn() != nullptr;
+}
+
+template <typename T, bool Fused>
+void dispatch(const Geom& g, const StencilTables& t, const T* a, const T* b, const T* c, T* q, T* p_new, const PcgState* st, int par,
+              double* d_dot_out, double* d_partial, unsigned* d_ticket, const int* d_done, cudaStream_t s)
+{
+	if (t.radius <= 1) {
+		launch<T, 1, 3, Fused, 2>(g, t, a, b, c, q, p_new, st, par, d_dot_out, d_partial, d_ticket, d_done, s);
+	} else if (t.radius == 2) {
+		launch<T, 2, 3, Fused, 2>(g, t, a, b, c, q, p_new, st, par, d_dot_out, d_partial, d_ticket, d_done, s);
+	} else {
+		launch<T, 4, 2, Fused, 1>(g, t, a, b, c, q, p_new, st, par, d_dot_out, d_partial, d_ticket, d_done, s);
+	}
+}
+
+}  // namespace
+
+template <typename T>
+bool stencil_tma_3d(const Geom& g, const StencilTables& t, const T* p, T* q, double* d_dot_out, double* d_partial, unsigned* d_ticket,
+                    const int* d_done, cudaStream_t s)
+{
+	if (!eligible<T>(g, t)) { return false; }
+	dispatch<T, false>(g, t, p, nullptr, nullptr, q, nullptr, nullptr, 0, d_dot_out, d_partial, d_ticket, d_done, s);
+	return true;
+}
+
+template <typename T>
+bool stencil_tma_3d_fused(const Geom& g, const StencilTables& t, const T* r, const T* minv, const T* p_old, T* p_new, T* q,
+                          const PcgState* st, int par, double* d_dot_out, double* d_partial, unsigned* d_ticket, const int* d_done,
+                          cudaStream_t s)
+{
+	if (!eligible<T>(g, t)) { return false; }
+	dispatch<T, true>(g, t, r, minv, p_old, q, p_new, st, par, d_dot_out, d_partial, d_ticket, d_done, s);
+	return true;
+}
+
+template bool stencil_tma_3d<float>(const Geom&, const StencilTables&, const float*, float*, double*, double*, unsigned*, const int*, cudaStream_t);
+template bool stencil_tma_3d<double>(const Geom&, const StencilTables&, const double*, double*, double*, double*, unsigned*, const int*, cudaStream_t);
+template bool stencil_tma_3d_fused<float>(const Geom&, const StencilTables&, const float*, const float*, const float*, float*, float*, const PcgState*, int, double*, double*, unsigned*, const int*, cudaStream_t);
+template bool stencil_tma_3d_fused<double>(const Geom&, const StencilTables&, const double*, const double*, const double*, double*, double*, const PcgState*, int, double*, double*, unsigned*, const int*, cudaStream_t);
+
+}  // namespace fi

@@ -72,7 +72,8 @@ typedef struct fi_solve_options {
 	int32_t max_iterations; /* <= 0: 2*N, Eigen's default for its iterative solvers */
 	double  tolerance;      /* stop when |r| <= tolerance*|Atb| (Eigen's rule); <= 0: epsilon of the precision */
 	int32_t check_every;    /* iterations per CUDA-graph launch between convergence polls; <= 0: 32 */
-	int32_t use_fast_stencil; /* 0: generic kernel only (debug / parity), 1: specialised kernels when applicable */
+	int32_t use_fast_stencil; /* 0: generic kernel only (debug / parity), 1: best specialised kernel (TMA-staged 3D kernel
+	                           * when applicable, else the tiled one), 2: tiled 3D kernel without TMA */
 	int32_t refine_max_outer; /* FI_MIXED: max fp64 refinement sweeps; <= 0: 20 */
 	double  refine_inner_tolerance; /* FI_MIXED: relative tolerance of each inner fp32 solve; <= 0: 1e-3 */
 } fi_solve_options;
@@ -138,8 +139,9 @@ FI_API int fi_field_export(fi_field* f, fi_triplet* triplets, float* rhs);
 /* y = (AtA) x, Atb and diag(AtA) of everything added so far; make_square / Atb, sparse_linear.cpp:105-113,
  * :120.  x, y: N elements of float (FI_F32) or double (FI_F64), host buffers. */
 FI_API int fi_field_apply(fi_field* f, int32_t precision, const void* x, void* y);
-/* Selects the kernel fi_field_apply uses for the smoothness part: 1 (default) specialised kernels where
- * applicable, 0 the generic reference-shaped kernel.  fi_field_solve takes the same switch in its options. */
+/* Selects the kernel fi_field_apply uses for the smoothness part: 1 (default) best specialised kernel where
+ * applicable (TMA-staged), 2 the tiled kernel without TMA, 0 the generic reference-shaped kernel.
+ * fi_field_solve takes the same switch in its options. */
 FI_API int fi_field_use_fast_stencil(fi_field* f, int32_t enable);
 FI_API int fi_field_rhs(fi_field* f, int32_t precision, void* atb);
 FI_API int fi_field_diagonal(fi_field* f, int32_t precision, void* diag);

@@ -56,8 +56,8 @@ def test_operator_matches_reference_normal_equations(fi, port, sizes, fast):
 @pytest.mark.parametrize("orders", [dict(model_1=0.7), dict(model_2=0.5), dict(model_0=0.2, model_1=0.3, model_2=0.5),
                                     dict(model_3=0.4), dict(model_0=0.1, model_1=0.2, model_2=0.5, model_3=0.3, model_4=0.25)])
 def test_fast_stencil_matches_generic_and_oracle(fi, port, sizes, orders):
-    """The tiled 3D kernel (smem tile + z register pipeline) against the generic kernel and the explicit AtA,
-    fp32 and fp64, radius 1 / 2 / 4, lattices with ragged tiles and short z chunks."""
+    """The TMA-staged 3D kernel (mode 1) and the tiled one without TMA (mode 2) against the generic kernel (mode 0)
+    and the explicit AtA, fp32 and fp64, radius 1 / 2 / 4, lattices with ragged tiles and short z chunks."""
     n = int(np.prod(sizes))
     rng = np.random.default_rng(n)
     kw = dict(model_2=0.0)
@@ -68,26 +68,28 @@ def test_fast_stencil_matches_generic_and_oracle(fi, port, sizes, orders):
     x = rng.normal(size=n)
     want = M @ x
     scale = abs(M).max() * np.abs(x).max() * 30
-    for enable in (True, False):
+    for enable in (1, 2, 0):
         f.use_fast_stencil(enable)
         np.testing.assert_allclose(f.apply(x, fi.FI_F64), want, rtol=0, atol=1e-12 * scale)
         np.testing.assert_allclose(f.apply(x.astype(np.float32), fi.FI_F32), want, rtol=0, atol=2e-6 * scale)
 
 
+@pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("prec", ["f32", "f64"])
-def test_fused_pcg_matches_unfused(fi, prec):
-    """Fused direction+stencil iteration (p ping-pong) vs the three-kernel iteration: same iterates."""
+def test_fused_pcg_matches_unfused(fi, prec, mode):
+    """Fused direction+stencil iteration (p ping-pong; mode 1 TMA-staged, mode 2 tiled) vs the three-kernel
+    iteration: same iterates."""
     sizes = [64, 40, 24]
     cloud = W.sphere_torus_3d(3000, seed=9)
     pos = W.to_lattice(cloud["unit_pos"], sizes)
     f = fi.sdf_from_points(sizes, fi.Weights(), pos, cloud["normals"])
     P = fi.FI_F32 if prec == "f32" else fi.FI_F64
     for its in (1, 2, 7, 40):
-        xa, sa = f.solve(fi.solve_options(P, its, 1e-30, check_every=4, use_fast_stencil=True))
+        xa, sa = f.solve(fi.solve_options(P, its, 1e-30, check_every=4, use_fast_stencil=mode))
         xb, sb = f.solve(fi.solve_options(P, its, 1e-30, check_every=4, use_fast_stencil=False))
         assert sa["iterations"] == sb["iterations"] == its
         assert rel(xa, xb.astype(np.float64)) <= (2e-4 if prec == "f32" else 1e-10)
-    xa, sa = f.solve(fi.solve_options(P, 0, 1e-5, use_fast_stencil=True))
+    xa, sa = f.solve(fi.solve_options(P, 0, 1e-5, use_fast_stencil=mode))
     xb, sb = f.solve(fi.solve_options(P, 0, 1e-5, use_fast_stencil=False))
     assert sa["converged"] and sb["converged"] and abs(sa["iterations"] - sb["iterations"]) <= max(3, 0.03 * sb["iterations"])
     assert rel(xa, xb.astype(np.float64)) <= 1e-3
