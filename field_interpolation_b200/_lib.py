@@ -82,6 +82,7 @@ SIGNATURES = {
     "fi_sdf_from_points": (C.c_int, [_i32, _pi32, _p(fi_weights), _i64, _vp, _vp, _vp, _i32, _p(_vp)]),
     "fi_field_counts": (C.c_int, [_vp, _pi64, _pi64]),
     "fi_field_export": (C.c_int, [_vp, _vp, _vp]),
+    "fi_field_export_rows": (C.c_int, [_vp, _i64, _vp, _vp]),
     "fi_field_apply": (C.c_int, [_vp, _i32, _vp, _vp]),
     "fi_field_use_fast_stencil": (C.c_int, [_vp, _i32]),
     "fi_field_rhs": (C.c_int, [_vp, _i32, _vp]),
@@ -89,6 +90,7 @@ SIGNATURES = {
     "fi_field_solve": (C.c_int, [_vp, _p(fi_solve_options), _vp, _vp, _i32, _p(fi_solve_stats)]),
     "fi_field_jacobi": (C.c_int, [_vp, _pf, _i32, _f, _pf]),
     "fi_upscale_field": (C.c_int, [_i32, _pi32, _pi32, _vp, _vp, _i32]),
+    "fi_error_map": (C.c_int, [_i64, _vp, _i64, _pf, _i64, _pf, _pf]),
     "fi_sdf_solve_cascade": (C.c_int, [_i32, _pi32, _p(fi_weights), _i64, _vp, _vp, _vp, _p(fi_cascade_options), _vp, _i32,
                                        _p(fi_cascade_stats)]),
     "fi_kernel_launches": (_i64, []),

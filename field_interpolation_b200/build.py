@@ -17,7 +17,7 @@ COMMON = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-l
           "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-I", os.path.join(HERE, "..", "include")]
 # assembly.cu restates the reference's scalar fp32 arithmetic bit for bit: no FMA contraction there.
 PER_FILE = {"assembly.cu": ["-fmad=false"]}
-SOURCES = ["abi.cu", "assembly.cu", "sort_scan.cu", "stencil.cu", "stencil_fast.cu", "stencil_tma.cu", "solver.cu", "dist.cu"]
+SOURCES = ["abi.cu", "assembly.cu", "sort_scan.cu", "stencil.cu", "stencil_fast.cu", "stencil_tma.cu", "solver.cu", "errormap.cu", "dist.cu"]
 
 
 def _stale(src, obj):
@@ -58,7 +58,43 @@ def build(verbose: bool = False, force: bool = False) -> str:
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("link failed")
+    build_host()
     return OUT
+
+
+HOST_SRC = [os.path.join(HERE, "host", f) for f in ("field_interpolation.cpp", "sparse_linear.cpp")]
+HOST_OUT = os.path.join(HERE, "libfield_interpolation.so")
+CXX = os.environ.get("CXX", "g++")
+
+
+def build_host(force: bool = False) -> str:
+    """The C++ drop-in API (include/field_interpolation/*.hpp): host C++14 over the C ABI, linked to libfi_b200.so."""
+    deps = HOST_SRC + [os.path.join(HERE, "host", "structured.hpp"), OUT,
+                       os.path.join(HERE, "..", "include", "fi_b200.h"),
+                       os.path.join(HERE, "..", "include", "field_interpolation", "field_interpolation.hpp"),
+                       os.path.join(HERE, "..", "include", "field_interpolation", "sparse_linear.hpp")]
+    if not force and os.path.exists(HOST_OUT) and all(os.path.getmtime(d) <= os.path.getmtime(HOST_OUT) for d in deps):
+        return HOST_OUT
+    cmd = [CXX, "-std=c++14", "-O2", "-fPIC", "-shared", "-Wall", "-Wextra", "-o", HOST_OUT, *HOST_SRC,
+           "-L", HERE, "-lfi_b200", "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("host library build failed")
+    return HOST_OUT
+
+
+def build_cpp_driver(src: str, out: str) -> str:
+    """Compiles a C++ program against the drop-in headers (what a user of the reference would do)."""
+    if os.path.exists(out) and os.path.getmtime(out) >= max(os.path.getmtime(src), os.path.getmtime(HOST_OUT)):
+        return out
+    cmd = [CXX, "-std=c++14", "-O2", "-Wall", "-o", out, src, "-I", os.path.join(HERE, "..", "include"), "-L", HERE,
+           "-lfield_interpolation", "-lfi_b200", f"-Wl,-rpath,{HERE}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("driver build failed")
+    return out
 
 
 if __name__ == "__main__":

@@ -485,64 +485,88 @@ int fi_field_counts(fi_field* f, int64_t* num_rows, int64_t* num_triplets)
 	});
 }
 
+// Exports the rows numbered >= row_begin (which must be where one builder call ended and the next began).
+static void export_impl(fi_field* f, int64_t row_begin, fi_triplet* triplets, float* rhs)
+{
+	FI_REQUIRE(f != nullptr, FI_ERR_INVALID, "field is null");
+	FI_REQUIRE(row_begin >= 0, FI_ERR_INVALID, "negative row_begin");
+	int64_t R = 0, T = 0;
+	for (Segment& sg : f->segs) {
+		segment_counts(f, sg);
+		R += sg.rows;
+		T += sg.trips;
+	}
+	FI_REQUIRE(R <= INT32_MAX && T <= INT32_MAX && f->g.N <= INT32_MAX, FI_ERR_RANGE,
+	           "system does not fit the reference's int32 triplet view");
+	// first segment to export
+	size_t  first = 0;
+	int64_t row_base = 0, trip_base = 0;
+	while (first < f->segs.size() && row_base < row_begin) {
+		row_base += f->segs[first].rows;
+		trip_base += f->segs[first].trips;
+		++first;
+	}
+	// builder calls that appended nothing leave empty segments at the boundary: skipping them is harmless
+	FI_REQUIRE(row_base == row_begin || (first == f->segs.size() && row_begin == R), FI_ERR_INVALID,
+	           "row_begin is not a boundary between builder calls");
+	const int64_t outR = R - row_base, outT = T - trip_base;
+	if (outR == 0 && outT == 0) { return; }
+	FI_REQUIRE((triplets || outT == 0) && (rhs || outR == 0), FI_ERR_INVALID, "output buffers are null");
+	cudaStream_t       s = f->stream;
+	DevBuf<fi_triplet> d_trips(std::max<int64_t>(outT, 1));
+	DevBuf<float>      d_rhs(std::max<int64_t>(outR, 1));
+	const int64_t      row0 = row_base, trip0 = trip_base;
+	fi_triplet*        dt = d_trips.data() - trip0;  // indexed by absolute triplet number below
+	float*             dr = d_rhs.data() - row0;
+	for (size_t k = first; k < f->segs.size(); ++k) {
+		Segment& sg = f->segs[k];
+		if (sg.kind == Segment::kModel) {
+			DevBuf<uint64_t> ro(f->g.N), to(f->g.N);
+			uint64_t         hr = 0, ht = 0;
+			count_model_rows(f->g, sg.w, ro.data(), to.data(), &hr, &ht, s);
+			FI_REQUIRE(static_cast<int64_t>(hr) == sg.rows && static_cast<int64_t>(ht) == sg.trips, FI_ERR_INVALID,
+			           "internal: model row count mismatch");
+			emit_model_rows(f->g, sg.w, ro.data(), to.data(), row_base, trip_base, dt, dr, s);
+			FI_CUDA(cudaStreamSynchronize(s));
+		} else if (sg.kind == Segment::kPoints) {
+			const int64_t    n = sg.p1 - sg.p0;
+			DevBuf<uint64_t> ro(std::max<int64_t>(n, 1)), to(std::max<int64_t>(n, 1));
+			uint64_t         hr = 0, ht = 0;
+			count_point_rows(f->g, view(f->pts), sg.p0, sg.p1, ro.data(), to.data(), &hr, &ht, s);
+			emit_point_rows(f->g, view(f->pts), sg.p0, sg.p1, ro.data(), to.data(), row_base, trip_base, dt, dr, s);
+			FI_CUDA(cudaStreamSynchronize(s));
+		} else {
+			std::vector<fi_triplet> ht(static_cast<size_t>(sg.trips));
+			size_t                  at = 0;
+			for (int64_t r = sg.r0; r < sg.r1; ++r) {
+				for (uint64_t kk = f->rows.ptr[r]; kk < f->rows.ptr[r + 1]; ++kk) {
+					ht[at++] = fi_triplet{static_cast<int32_t>(row_base + (r - sg.r0)), f->rows.col[kk], f->rows.val[kk]};
+				}
+			}
+			if (!ht.empty()) {
+				FI_CUDA(cudaMemcpyAsync(dt + trip_base, ht.data(), ht.size() * sizeof(fi_triplet), cudaMemcpyHostToDevice, s));
+			}
+			if (sg.rows > 0) {
+				FI_CUDA(cudaMemcpyAsync(dr + row_base, f->rows.rhs.data() + sg.r0, sg.rows * sizeof(float), cudaMemcpyHostToDevice, s));
+			}
+			FI_CUDA(cudaStreamSynchronize(s));
+		}
+		row_base += sg.rows;
+		trip_base += sg.trips;
+	}
+	if (outT > 0) { FI_CUDA(cudaMemcpyAsync(triplets, d_trips.data(), outT * sizeof(fi_triplet), cudaMemcpyDeviceToHost, s)); }
+	if (outR > 0) { FI_CUDA(cudaMemcpyAsync(rhs, d_rhs.data(), outR * sizeof(float), cudaMemcpyDeviceToHost, s)); }
+	FI_CUDA(cudaStreamSynchronize(s));
+}
+
 int fi_field_export(fi_field* f, fi_triplet* triplets, float* rhs)
 {
-	return guarded([&] {
-		FI_REQUIRE(f != nullptr, FI_ERR_INVALID, "field is null");
-		int64_t R = 0, T = 0;
-		for (Segment& sg : f->segs) {
-			segment_counts(f, sg);
-			R += sg.rows;
-			T += sg.trips;
-		}
-		FI_REQUIRE(R <= INT32_MAX && T <= INT32_MAX && f->g.N <= INT32_MAX, FI_ERR_RANGE,
-		           "system does not fit the reference's int32 triplet view");
-		if (R == 0 && T == 0) { return; }
-		FI_REQUIRE((triplets || T == 0) && (rhs || R == 0), FI_ERR_INVALID, "output buffers are null");
-		cudaStream_t       s = f->stream;
-		DevBuf<fi_triplet> d_trips(std::max<int64_t>(T, 1));
-		DevBuf<float>      d_rhs(std::max<int64_t>(R, 1));
-		int64_t            row_base = 0, trip_base = 0;
-		for (Segment& sg : f->segs) {
-			if (sg.kind == Segment::kModel) {
-				DevBuf<uint64_t> ro(f->g.N), to(f->g.N);
-				uint64_t         hr = 0, ht = 0;
-				count_model_rows(f->g, sg.w, ro.data(), to.data(), &hr, &ht, s);
-				FI_REQUIRE(static_cast<int64_t>(hr) == sg.rows && static_cast<int64_t>(ht) == sg.trips, FI_ERR_INVALID,
-				           "internal: model row count mismatch");
-				emit_model_rows(f->g, sg.w, ro.data(), to.data(), row_base, trip_base, d_trips.data(), d_rhs.data(), s);
-				FI_CUDA(cudaStreamSynchronize(s));
-			} else if (sg.kind == Segment::kPoints) {
-				const int64_t    n = sg.p1 - sg.p0;
-				DevBuf<uint64_t> ro(std::max<int64_t>(n, 1)), to(std::max<int64_t>(n, 1));
-				uint64_t         hr = 0, ht = 0;
-				count_point_rows(f->g, view(f->pts), sg.p0, sg.p1, ro.data(), to.data(), &hr, &ht, s);
-				emit_point_rows(f->g, view(f->pts), sg.p0, sg.p1, ro.data(), to.data(), row_base, trip_base, d_trips.data(),
-				                d_rhs.data(), s);
-				FI_CUDA(cudaStreamSynchronize(s));
-			} else {
-				std::vector<fi_triplet> ht(static_cast<size_t>(sg.trips));
-				size_t                  at = 0;
-				for (int64_t r = sg.r0; r < sg.r1; ++r) {
-					for (uint64_t k = f->rows.ptr[r]; k < f->rows.ptr[r + 1]; ++k) {
-						ht[at++] = fi_triplet{static_cast<int32_t>(row_base + (r - sg.r0)), f->rows.col[k], f->rows.val[k]};
-					}
-				}
-				if (!ht.empty()) {
-					FI_CUDA(cudaMemcpyAsync(d_trips.data() + trip_base, ht.data(), ht.size() * sizeof(fi_triplet), cudaMemcpyHostToDevice, s));
-				}
-				if (sg.rows > 0) {
-					FI_CUDA(cudaMemcpyAsync(d_rhs.data() + row_base, f->rows.rhs.data() + sg.r0, sg.rows * sizeof(float), cudaMemcpyHostToDevice, s));
-				}
-				FI_CUDA(cudaStreamSynchronize(s));
-			}
-			row_base += sg.rows;
-			trip_base += sg.trips;
-		}
-		if (T > 0) { FI_CUDA(cudaMemcpyAsync(triplets, d_trips.data(), T * sizeof(fi_triplet), cudaMemcpyDeviceToHost, s)); }
-		if (R > 0) { FI_CUDA(cudaMemcpyAsync(rhs, d_rhs.data(), R * sizeof(float), cudaMemcpyDeviceToHost, s)); }
-		FI_CUDA(cudaStreamSynchronize(s));
-	});
+	return guarded([&] { export_impl(f, 0, triplets, rhs); });
+}
+
+int fi_field_export_rows(fi_field* f, int64_t row_begin, fi_triplet* triplets, float* rhs)
+{
+	return guarded([&] { export_impl(f, row_begin, triplets, rhs); });
 }
 
 int fi_field_use_fast_stencil(fi_field* f, int32_t enable)
@@ -654,6 +678,17 @@ int fi_upscale_field(int32_t ndim, const int32_t* small_sizes, const int32_t* la
 			upscale_device(gs, gl, a.data(), b.data(), 1.0f, nullptr);
 			FI_CUDA(cudaMemcpy(large_field, b.data(), gl.N * sizeof(float), cudaMemcpyDeviceToHost));
 		}
+	});
+}
+
+int fi_error_map(int64_t num_triplets, const fi_triplet* triplets, int64_t num_columns, const float* solution, int64_t num_rows,
+                 const float* rhs, float* heatmap)
+{
+	return guarded([&] {
+		FI_REQUIRE(num_triplets >= 0 && num_columns >= 0 && num_rows >= 0, FI_ERR_INVALID, "negative count");
+		FI_REQUIRE((triplets || num_triplets == 0) && (solution || num_columns == 0) && (rhs || num_rows == 0) && (heatmap || num_columns == 0),
+		           FI_ERR_INVALID, "null argument");
+		error_map(num_triplets, triplets, num_columns, solution, num_rows, rhs, heatmap);
 	});
 }
 

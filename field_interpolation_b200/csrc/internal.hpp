@@ -111,6 +111,9 @@ template <typename T>
 void apply_data_term(const Geom& g, const DataTerm<T>& dt, const T* p, T* q, double* d_dot_accum, const int* d_done,
                      cudaStream_t s);
 
+// ---- errormap.cu ------------------------------------------------------------------------------------------
+void error_map(int64_t nt, const fi_triplet* h_trips, int64_t n, const float* h_x, int64_t nrows, const float* h_rhs, float* h_out);
+
 // ---- stencil.cu ------------------------------------------------------------------------------------------
 // Per-axis banded operator T_d = sum_k w_k^2 D_k^T D_k (rows that stick out dropped), 9 row classes x 9 taps,
 // plus the tri-diagonal D_1^T D_1 used by the gradient-smoothness cross terms.  See DESIGN.md §3.

@@ -134,6 +134,10 @@ FI_API int fi_field_counts(fi_field* f, int64_t* num_rows, int64_t* num_triplets
 /* Writes eq.triplets / eq.rhs bit-identical to the reference's.  Host buffers sized by fi_field_counts.
  * FI_ERR_RANGE when rows or triplets exceed INT32_MAX (the reference's int row overflows there). */
 FI_API int fi_field_export(fi_field* f, fi_triplet* triplets, float* rhs);
+/* The same for the rows numbered >= row_begin only (row numbers stay absolute), so that a host mirror of
+ * LatticeField::eq can append what one builder call added.  row_begin must be the row count before some
+ * builder call.  Buffers sized by the difference of two fi_field_counts results. */
+FI_API int fi_field_export_rows(fi_field* f, int64_t row_begin, fi_triplet* triplets, float* rhs);
 
 /* ---- normal equations, matrix-free ----------------------------------------------------------- */
 /* y = (AtA) x, Atb and diag(AtA) of everything added so far; make_square / Atb, sparse_linear.cpp:105-113,
@@ -161,6 +165,11 @@ FI_API int fi_field_jacobi(fi_field* f, const float* guess, int32_t num_iteratio
 /* upscale_field, field_interpolation.cpp:431-485 (bit-identical fp32 arithmetic). */
 FI_API int fi_upscale_field(int32_t ndim, const int32_t* small_sizes, const int32_t* large_sizes, const float* small_field,
                      float* large_field, int32_t loc);
+
+/* generate_error_map, field_interpolation.cpp:402-429: (A x - b)^2 per row, distributed over the row's columns
+ * by squared coefficient.  Any triplet list (rows need not be grouped).  Host buffers; heatmap: num_columns floats. */
+FI_API int fi_error_map(int64_t num_triplets, const fi_triplet* triplets, int64_t num_columns, const float* solution,
+                 int64_t num_rows, const float* rhs, float* heatmap);
 
 /* Coarse-to-fine solve mirroring the demo's recipe (src/sdf_field.cpp:251-304) applied recursively:
  * positions are in UNIT coordinates and are scaled per level by (size-1) as on_lattice does (:198-210);

@@ -36,7 +36,4 @@ for n in sizes_list:
     f = fi.sdf_from_points(sizes, fi.Weights(), pos, nr)
     x, st = f.solve(fi.solve_options(fi.FI_F32, 60000, 1e-6, check_every=64), guess=None, out=torch.empty(n**3, device="cuda"))
     print(json.dumps({"n": n, "zero_guess_f32": st}), flush=True)
-    ms, ms_apply = f.time_iterations(200)
-    print(json.dumps({"n": n, "ms_per_iter": ms / 200, "ms_per_apply": ms_apply / 200,
-                      "GBs_iter_52B": 52 * n**3 / (ms / 200 * 1e-3) / 1e9, "GBs_apply_8B": 8 * n**3 / (ms_apply / 200 * 1e-3) / 1e9}), flush=True)
     del f

@@ -1,0 +1,262 @@
+// Test driver for the C++ drop-in API (include/field_interpolation/*.hpp).  Each scenario is written the way
+// the reference's own callers use the library (cited per scenario) and dumps the resulting system and
+// solution to a binary file that tests/test_cpp_api.py compares with the CPU oracle.
+//
+//   api_driver <scenario> <out.bin> [in.bin]
+//
+// File format (little endian): repeated records { char name[16]; int64 count; int32 dtype (0 f32, 1 i32);
+// payload }.
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include <field_interpolation/field_interpolation.hpp>
+
+namespace fi = field_interpolation;
+
+static FILE* g_out = nullptr;
+
+static void put(const char* name, const void* data, int64_t count, int32_t dtype)
+{
+	char n[16] = {0};
+	std::strncpy(n, name, 15);
+	std::fwrite(n, 1, 16, g_out);
+	std::fwrite(&count, sizeof(count), 1, g_out);
+	std::fwrite(&dtype, sizeof(dtype), 1, g_out);
+	std::fwrite(data, 4, static_cast<size_t>(count), g_out);
+}
+static void put_f(const char* name, const std::vector<float>& v) { put(name, v.data(), static_cast<int64_t>(v.size()), 0); }
+static void put_i(const char* name, const std::vector<int>& v) { put(name, v.data(), static_cast<int64_t>(v.size()), 1); }
+
+static void put_system(const fi::LinearEquation& eq)
+{
+	std::vector<int>   rows, cols;
+	std::vector<float> vals;
+	for (const fi::Triplet& t : eq.triplets) {
+		rows.push_back(t.row);
+		cols.push_back(t.col);
+		vals.push_back(t.value);
+	}
+	put_i("rows", rows);
+	put_i("cols", cols);
+	put_f("vals", vals);
+	put_f("rhs", eq.rhs);
+}
+
+static std::vector<float> read_floats(FILE* f)
+{
+	int64_t n = 0;
+	if (std::fread(&n, sizeof(n), 1, f) != 1) { return {}; }
+	std::vector<float> v(static_cast<size_t>(n));
+	if (n && std::fread(v.data(), 4, v.size(), f) != v.size()) { return {}; }
+	return v;
+}
+
+// reference src/field_1d.cpp:98-110 — data rows first, then the model, exact solve
+static int scenario_field_1d(int resolution)
+{
+	struct Point { float pos, value, gradient; };
+	const Point points[] = {{0.2f, 0.0f, +1.0f}, {0.8f, 0.0f, -1.0f}};  // src/field_1d.cpp:20-29
+	fi::Weights weights;
+	fi::LatticeField field{{resolution}};
+	std::vector<int> accepted;
+	for (const Point& point : points) {
+		float pos_lattice      = point.pos * (resolution - 1);
+		float gradient_lattice = point.gradient / (resolution - 1);
+		accepted.push_back(add_value_constraint(&field, &pos_lattice, point.value, weights.data_pos));
+		accepted.push_back(add_gradient_constraint(&field, &pos_lattice, &gradient_lattice, weights.data_gradient, weights.gradient_kernel));
+	}
+	add_field_constraints(&field, weights);
+	const size_t num_unknowns = resolution;
+	auto interpolated = solve_sparse_linear_exact(field.eq, num_unknowns);
+	put_system(field.eq);
+	put_i("accepted", accepted);
+	put_f("solution", interpolated);
+	std::ostringstream os;
+	os << field.eq;  // src/field_1d.cpp:83-90 prints the system
+	std::vector<int> printed{static_cast<int>(os.str().size())};
+	put_i("printed", printed);
+	return interpolated.size() == num_unknowns ? 0 : 2;
+}
+
+// README.md:11-40 on the real library
+static int scenario_readme()
+{
+	fi::LatticeField field{{6}};
+	std::vector<int> accepted;
+	const float p0 = 0.0f, p5 = 5.0f, gp = 1.0f, gm = -1.0f;
+	accepted.push_back(add_value_constraint(&field, &p0, 4.0f, 1.0f));
+	accepted.push_back(add_value_constraint(&field, &p5, 2.0f, 1.0f));
+	accepted.push_back(add_gradient_constraint(&field, &p0, &gp, 1.0f, fi::GradientKernel::kNearestNeighbor));
+	accepted.push_back(add_gradient_constraint(&field, &p5, &gm, 1.0f, fi::GradientKernel::kNearestNeighbor));
+	fi::Weights w;
+	w.model_2 = 1.0f;
+	add_field_constraints(&field, w);
+	put_system(field.eq);
+	put_i("accepted", accepted);
+	put_f("solution", solve_sparse_linear_exact(field.eq, 6));
+	return 0;
+}
+
+// reference src/interpolate_2d.cpp:31-47 — model rows first, 4x4 value grid with zero-gradient constraints
+static int scenario_interpolate_2d(int resolution)
+{
+	const float values[16] = {5, 4, 2, 3, 4, 2, 1, 5, 6, 3, 5, 2, 1, 2, 4, 1};
+	fi::Weights weights;
+	fi::LatticeField field{{resolution, resolution}};
+	add_field_constraints(&field, weights);
+	for (int y = 0; y < 4; ++y) {
+		for (int x = 0; x < 4; ++x) {
+			const float pos[2]  = {x / 3.0f * (resolution - 1.0f), y / 3.0f * (resolution - 1.0f)};
+			add_value_constraint(&field, pos, values[y * 4 + x], weights.data_pos);
+			const float zero[2] = {0, 0};
+			add_gradient_constraint(&field, pos, zero, weights.data_gradient, weights.gradient_kernel);
+		}
+	}
+	put_system(field.eq);
+	put_f("solution", solve_sparse_linear_exact(field.eq, resolution * resolution));
+	return 0;
+}
+
+// reference src/sdf_field.cpp:212-249 + :251-304 — sdf_from_points, border-distance rows appended by hand with
+// add_equation, exact solve; then the approximate path: coarse solve -> upscale_field -> * factor ->
+// solve_tiled_with_guess; and the error heat map (:350).
+static int scenario_sdf_2d(const char* in_path)
+{
+	FILE* in = std::fopen(in_path, "rb");
+	if (!in) { return 3; }
+	const std::vector<float> dims = read_floats(in);  // width, height, boundary_weight, downscale_factor
+	const std::vector<float> unit = read_floats(in);  // unit positions xyxy..
+	const std::vector<float> nrm  = read_floats(in);
+	std::fclose(in);
+	const int   width = static_cast<int>(dims[0]), height = static_cast<int>(dims[1]);
+	const float boundary_weight = dims[2];
+	const int   factor = static_cast<int>(dims[3]);
+	const int   npts = static_cast<int>(unit.size() / 2);
+	fi::Weights weights;
+
+	auto generate_sdf_field = [&](int w, int h, const std::vector<float>& pos) {
+		auto field = fi::sdf_from_points({w, h}, weights, npts, pos.data(), nrm.data(), nullptr);
+		if (boundary_weight > 0) {
+			for (int y = 0; y < h; ++y) {
+				for (int x = 0; x < w; ++x) {
+					if (!(x == 0 || x == w - 1 || y == 0 || y == h - 1)) { continue; }
+					float closest = std::numeric_limits<float>::infinity();
+					for (int i = 0; i < npts; ++i) {
+						const float dx = pos[2 * i] - x, dy = pos[2 * i + 1] - y;
+						closest = std::min(closest, dx * dx + dy * dy);
+					}
+					add_equation(&field.eq, fi::Weight{boundary_weight}, {std::sqrt(closest)}, {{y * w + x, 1.0f}});
+				}
+			}
+		}
+		return field;
+	};
+	auto on_lattice = [&](int w, int h) {
+		std::vector<float> p(unit.size());
+		for (int i = 0; i < npts; ++i) {
+			p[2 * i]     = unit[2 * i] * (w - 1.0f);
+			p[2 * i + 1] = unit[2 * i + 1] * (h - 1.0f);
+		}
+		return p;
+	};
+
+	const auto pos   = on_lattice(width, height);
+	auto       field = generate_sdf_field(width, height, pos);
+	put_system(field.eq);
+	const auto exact = solve_sparse_linear_exact(field.eq, width * height);
+	put_f("exact", exact);
+
+	const int  ws = (width + factor - 1) / factor, hs = (height + factor - 1) / factor;
+	auto       field_small = generate_sdf_field(ws, hs, on_lattice(ws, hs));
+	const auto small       = solve_sparse_linear_exact(field_small.eq, ws * hs);
+	put_f("small", small);
+	auto sdf = fi::upscale_field(small.data(), {ws, hs}, {width, height});
+	put_f("upscaled", sdf);
+	for (float& v : sdf) { v *= factor; }
+	fi::SolveOptions so;
+	so.error_tolerance = 1e-4f;
+	const auto approx = solve_tiled_with_guess(field.eq, sdf, {width, height}, so);
+	put_f("approx", approx);
+	put_f("bad_guess", solve_tiled_with_guess(field.eq, small, {width, height}, so));  // wrong size -> {}
+	put_f("heatmap", generate_error_map(field.eq.triplets, exact, field.eq.rhs));
+	put_f("jacobi", jacobi_iterations(field.eq, sdf, 5, 0.5f));
+	return 0;
+}
+
+// a system written entirely by hand (reference src/line_2d.cpp / src/bipolar_2d.cpp style): no lattice at all
+static int scenario_hand_rows()
+{
+	fi::LinearEquation eq;
+	const int n = 9;
+	for (int i = 0; i + 1 < n; ++i) { add_equation(&eq, fi::Weight{0.5f}, fi::Rhs{1.0f}, {{i, -1.0f}, {i + 1, 1.0f}}); }
+	add_equation(&eq, fi::Weight{2.0f}, fi::Rhs{3.0f}, {{0, 1.0f}});
+	add_equation(&eq, fi::Weight{0.0f}, fi::Rhs{3.0f}, {{0, 1.0f}});           // dropped: zero weight
+	add_equation(&eq, fi::Weight{1.0f}, fi::Rhs{3.0f}, {{4, 0.0f}});           // dropped: all-zero row
+	add_equation(&eq, fi::Weight{1.0f}, fi::Rhs{1.0f}, {{3, 1.0f}, {3, 0.5f}, {5, 0.0f}});  // duplicate column
+	put_system(eq);
+	put_f("exact", solve_sparse_linear_exact(eq, n));
+	put_f("fast", solve_sparse_linear_fast(eq, n));
+	put_f("guess", solve_sparse_linear_with_guess(eq, std::vector<float>(n, 0.0f), 0, 1e-6f));
+	return 0;
+}
+
+// deferred mode: nothing of size O(rows) on the host; counts still observable; materialize on demand
+static int scenario_deferred_3d()
+{
+	const int n = 20;
+	fi::LatticeField field{{n, n, n}};
+	fi::b200::defer_triplets(&field, true);
+	std::vector<float> pos, nrm;
+	for (int i = 0; i < 500; ++i) {
+		const float a = 0.37f * i, b = 0.11f * i;
+		const float d[3] = {std::cos(a) * std::sin(b), std::sin(a) * std::sin(b), std::cos(b)};
+		for (int k = 0; k < 3; ++k) {
+			pos.push_back((0.5f + 0.3f * d[k]) * (n - 1.0f));
+			nrm.push_back(d[k]);
+		}
+	}
+	fi::Weights w;
+	add_field_constraints(&field, w);
+	add_points(&field, w.data_pos, w.value_kernel, w.data_gradient, w.gradient_kernel, 500, pos.data(), nrm.data(), nullptr);
+	long long rows = 0, trips = 0;
+	fi::b200::counts(field, &rows, &trips);
+	std::vector<int> c{static_cast<int>(rows), static_cast<int>(trips), static_cast<int>(field.eq.rhs.size())};
+	put_i("counts", c);
+	fi::b200::SolveStats st;
+	put_f("solution", fi::b200::solve(field.eq, n * n * n, fi::b200::Precision::kDouble, nullptr, 0, 1e-11, &st));
+	fi::b200::materialize(&field);
+	put_system(field.eq);
+	put_f("points", pos);
+	put_f("normals", nrm);
+	std::vector<int> s{static_cast<int>(st.iterations), st.converged ? 1 : 0};
+	put_i("stats", s);
+	return 0;
+}
+
+int main(int argc, char** argv)
+{
+	if (argc < 3) {
+		std::fprintf(stderr, "usage: api_driver <scenario> <out.bin> [in.bin]\n");
+		return 64;
+	}
+	const std::string sc = argv[1];
+	g_out = std::fopen(argv[2], "wb");
+	if (!g_out) { return 65; }
+	int rc = 66;
+	if (sc == "field_1d_100") { rc = scenario_field_1d(100); }
+	else if (sc == "field_1d_12") { rc = scenario_field_1d(12); }
+	else if (sc == "readme") { rc = scenario_readme(); }
+	else if (sc == "interpolate_2d") { rc = scenario_interpolate_2d(24); }
+	else if (sc == "sdf_2d" && argc > 3) { rc = scenario_sdf_2d(argv[3]); }
+	else if (sc == "hand_rows") { rc = scenario_hand_rows(); }
+	else if (sc == "deferred_3d") { rc = scenario_deferred_3d(); }
+	std::fclose(g_out);
+	if (rc != 0) { std::fprintf(stderr, "scenario %s failed (%d): %s\n", sc.c_str(), rc, fi::b200::last_error()); }
+	return rc;
+}
