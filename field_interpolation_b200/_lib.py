@@ -93,6 +93,12 @@ SIGNATURES = {
     "fi_error_map": (C.c_int, [_i64, _vp, _i64, _pf, _i64, _pf, _pf]),
     "fi_sdf_solve_cascade": (C.c_int, [_i32, _pi32, _p(fi_weights), _i64, _vp, _vp, _vp, _p(fi_cascade_options), _vp, _i32,
                                        _p(fi_cascade_stats)]),
+    "fi_comm_unique_id": (C.c_int, [_vp, _i64]),
+    "fi_comm_create": (C.c_int, [_i32, _i32, _vp, _p(_vp)]),
+    "fi_comm_destroy": (C.c_int, [_vp]),
+    "fi_slab_range": (C.c_int, [_i32, _i32, _i32, _pi32, _pi32]),
+    "fi_slab_sdf_solve": (C.c_int, [_vp, _pi32, _p(fi_weights), _i64, _vp, _vp, _vp, _i32, _p(fi_solve_options), _vp, _vp, _i32,
+                                    _p(fi_solve_stats)]),
     "fi_kernel_launches": (_i64, []),
     "fi_kernel_launches_reset": (None, []),
     "fi_field_time_iterations": (C.c_int, [_vp, _p(fi_solve_options), _i32, _pd]),

@@ -165,6 +165,30 @@ void check_weights(const fi_weights* w)
 	FI_REQUIRE(w->gradient_kernel >= 0 && w->gradient_kernel <= 2, FI_ERR_INVALID, "unknown gradient kernel");
 }
 
+}  // namespace
+
+// Adds one add_field_constraints call to the accumulated smoothness operator (also used by dist.cu).
+void accumulate_model(const fi_weights& w, ModelAccum& m)
+{
+	const float wk[5] = {w.model_0, w.model_1, w.model_2, w.model_3, w.model_4};
+	static const float binom[5][5] = {{1, 0, 0, 0, 0}, {-1, 1, 0, 0, 0}, {1, -2, 1, 0, 0}, {1, -3, 3, -1, 0}, {1, -4, 6, -4, 1}};
+	for (int k = 0; k <= 4; ++k) {
+		if (!(wk[k] > 0)) { continue; }  // add_model_constraint emits order-k rows only for w_k > 0 (:257-292)
+		m.on[k] = true;
+		for (int a = 0; a <= k; ++a) {
+			for (int b = 0; b <= k; ++b) {
+				const volatile float ca = binom[k][a] * wk[k], cb = binom[k][b] * wk[k];  // fp32, as stored in the triplets
+				m.cc[k][a][b] += static_cast<double>(ca) * static_cast<double>(cb);
+			}
+		}
+	}
+	if (w.gradient_smoothness > 0) {
+		m.gs_sq += static_cast<double>(w.gradient_smoothness) * static_cast<double>(w.gradient_smoothness);
+	}
+}
+
+namespace {
+
 void add_model_impl(fi_field* f, const fi_weights* w)
 {
 	check_weights(w);
@@ -172,21 +196,7 @@ void add_model_impl(fi_field* f, const fi_weights* w)
 	sg.kind = Segment::kModel;
 	sg.w    = *w;
 	f->segs.push_back(sg);
-	const float wk[5] = {w->model_0, w->model_1, w->model_2, w->model_3, w->model_4};
-	static const float binom[5][5] = {{1, 0, 0, 0, 0}, {-1, 1, 0, 0, 0}, {1, -2, 1, 0, 0}, {1, -3, 3, -1, 0}, {1, -4, 6, -4, 1}};
-	for (int k = 0; k <= 4; ++k) {
-		if (!(wk[k] > 0)) { continue; }  // add_model_constraint emits order-k rows only for w_k > 0 (:257-292)
-		f->model.on[k] = true;
-		for (int a = 0; a <= k; ++a) {
-			for (int b = 0; b <= k; ++b) {
-				const volatile float ca = binom[k][a] * wk[k], cb = binom[k][b] * wk[k];  // fp32, as stored in the triplets
-				f->model.cc[k][a][b] += static_cast<double>(ca) * static_cast<double>(cb);
-			}
-		}
-	}
-	if (w->gradient_smoothness > 0) {
-		f->model.gs_sq += static_cast<double>(w->gradient_smoothness) * static_cast<double>(w->gradient_smoothness);
-	}
+	accumulate_model(*w, f->model);
 	f->invalidate();
 }
 
@@ -777,6 +787,51 @@ int fi_sdf_solve_cascade(int32_t ndim, const int32_t* sizes, const fi_weights* w
 		cudaEventDestroy(t0);
 		const int64_t N = make_geom(ndim, sizes).N;
 		FI_CUDA(cudaMemcpy(solution, prev.data(), N * sizeof(float), loc == FI_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost));
+	});
+}
+
+int fi_comm_unique_id(void* id, int64_t capacity)
+{
+	return guarded([&] { comm_unique_id(id, capacity); });
+}
+
+int fi_comm_create(int32_t rank, int32_t world, const void* id, fi_comm** out)
+{
+	return guarded([&] {
+		FI_REQUIRE(out != nullptr, FI_ERR_INVALID, "out is null");
+		*out = nullptr;
+		*out = comm_create(rank, world, id);
+	});
+}
+
+int fi_comm_destroy(fi_comm* c)
+{
+	return guarded([&] { comm_destroy(c); });
+}
+
+int fi_slab_range(int32_t nz, int32_t world, int32_t rank, int32_t* z0, int32_t* z1)
+{
+	return guarded([&] {
+		FI_REQUIRE(nz >= 1 && world >= 1 && rank >= 0 && rank < world && z0 && z1, FI_ERR_INVALID, "bad argument");
+		int a = 0, b = 0;
+		slab_range(nz, world, rank, &a, &b);
+		*z0 = a;
+		*z1 = b;
+	});
+}
+
+int fi_slab_sdf_solve(fi_comm* c, const int32_t* sizes, const fi_weights* w, int64_t num_points, const float* positions, const float* normals,
+                      const float* point_weights, int32_t loc, const fi_solve_options* opt, const float* guess_own, float* solution_own,
+                      int32_t solution_loc, fi_solve_stats* stats)
+{
+	return guarded([&] {
+		FI_REQUIRE(c && sizes && solution_own, FI_ERR_INVALID, "null argument");
+		FI_REQUIRE(positions != nullptr || num_points == 0, FI_ERR_INVALID, "positions is null");
+		check_weights(w);
+		for (int d = 0; d < 3; ++d) { FI_REQUIRE(sizes[d] >= 1, FI_ERR_INVALID, "lattice size must be >= 1"); }
+		fi_solve_options o;
+		if (opt) { o = *opt; } else { fi_solve_options_default(&o); }
+		slab_sdf_solve(c, sizes, *w, num_points, positions, normals, point_weights, loc, o, guess_own, solution_own, solution_loc, stats);
 	});
 }
 

@@ -44,7 +44,7 @@ __device__ __forceinline__ int corner_weights(const Geom& g, const float* pos, i
 	}
 	int kept = 0;
 	for (int corner = 0; corner < (1 << g.ndim); ++corner) {
-		int64_t index = 0;
+		int64_t index = g.shift;
 		float   wt    = 1.0f;
 		bool    ok    = true;
 		for (int d = 0; d < g.ndim; ++d) {
@@ -116,7 +116,7 @@ __device__ __forceinline__ void analyse_point(const Geom& g, const PointView& pv
 			r.vrhs = sum * value;
 		}
 	} else {  // nearest neighbour, :82-107 (the row goes through add_equation: dropped when the weight is 0)
-		int64_t node = 0;
+		int64_t node = g.shift;
 		float   along = 0.0f;
 		int     corner = 0;
 		bool    inside = true;
@@ -139,7 +139,7 @@ __device__ __forceinline__ void analyse_point(const Geom& g, const PointView& pv
 	if ((kind & 8) && gw != 0) {  // :123-240
 		const int gk = (kind >> 1) & 3;
 		if (gk == 0 || gk == 1) {
-			int64_t cell = 0;
+			int64_t cell = g.shift;
 			bool    ok   = true;
 			for (int d = 0; d < D; ++d) {
 				ok = ok && (0 <= r.base[d]) && (r.base[d] + 1 < g.size[d]);
@@ -355,7 +355,9 @@ __global__ void cell_keys_kernel(Geom g, PointView pv, int64_t n, uint64_t no_ce
 	PointPlan r;
 	analyse_point(g, pv, i, r);
 	uint64_t key = no_cell;
-	if (r.nv > 0 || r.gkind == 0 || r.gkind == 1) {
+	// a slab keeps the cells that touch a plane it owns: floor(pos_z) in [first owned - 1, last owned]
+	const bool in_window = !g.sharded() || (r.base[2] - g.zoff >= g.zown0 - 1 && r.base[2] - g.zoff <= g.zown1 - 1);
+	if (in_window && (r.nv > 0 || r.gkind == 0 || r.gkind == 1)) {
 		key            = 0;
 		uint64_t kstr  = 1;
 		for (int d = 0; d < g.ndim; ++d) {
@@ -477,7 +479,7 @@ __global__ void __launch_bounds__(kThreads) scatter_points_kernel(Geom g, PointV
 			if (head && v != T(0)) { atomic_add(&blocks[static_cast<size_t>(tri) * nocc + my_slot], v); }
 			if (ci == cj) {
 				bool    inside = true;
-				int64_t node   = 0;
+				int64_t node   = g.shift;
 #pragma unroll
 				for (int d = 0; d < D; ++d) {
 					const int c = base[d] + ((ci >> d) & 1);
@@ -593,7 +595,8 @@ __global__ void __launch_bounds__(kThreads) apply_blocks_kernel(Geom g, int64_t 
 	if (cell < nocc) {
 		uint64_t key = cell_key[cell];
 		int64_t  node[C];
-		bool     ok[C];
+		bool     ok[C];    // the corner is a lattice node: p is read there
+		bool     own[C];   // ... whose row this process computes (always, unless the lattice is slab-sharded)
 		int      base[D];
 #pragma unroll
 		for (int d = 0; d < D; ++d) {
@@ -605,12 +608,17 @@ __global__ void __launch_bounds__(kThreads) apply_blocks_kernel(Geom g, int64_t 
 #pragma unroll
 		for (int c = 0; c < C; ++c) {
 			ok[c]   = true;
-			node[c] = 0;
+			node[c] = g.shift;
 #pragma unroll
 			for (int d = 0; d < D; ++d) {
 				const int x = base[d] + ((c >> d) & 1);
 				ok[c]       = ok[c] && (0 <= x) && (x < g.size[d]);
 				node[c] += g.stride[d] * x;
+			}
+			own[c] = ok[c];
+			if (D == 3 && g.sharded()) {  // rows of nodes another slab owns are that slab's business
+				const int zl = base[D - 1] + ((c >> (D - 1)) & 1) - g.zoff;
+				own[c]       = ok[c] && zl >= g.zown0 && zl < g.zown1;
 			}
 			pc[c]  = ok[c] ? p[node[c]] : T(0);
 			out[c] = 0;
@@ -628,7 +636,7 @@ __global__ void __launch_bounds__(kThreads) apply_blocks_kernel(Geom g, int64_t 
 		}
 #pragma unroll
 		for (int c = 0; c < C; ++c) {
-			if (ok[c]) {
+			if (own[c]) {
 				atomic_add(&q[node[c]], out[c]);
 				mine[0] += static_cast<double>(pc[c]) * static_cast<double>(out[c]);
 			}

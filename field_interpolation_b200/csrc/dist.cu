@@ -1,0 +1,287 @@
+// Multi-GPU: one process per GPU, the 3D lattice partitioned into contiguous z slabs.
+//
+// x is the fastest axis and z the slowest (reference field_interpolation.hpp:104-111), so a z plane is one
+// contiguous run of nx*ny values and a halo is a plain contiguous range: no pack kernels.  Each slab stores its
+// owned planes plus R halo planes either side (R = highest active model order).  Per PCG iteration:
+//   * the fused direction+stencil kernel recomputes the new direction on the halo planes from r, M^-1 and p_old
+//     (bit-identical to what the neighbour computes for the same planes), so only r's halo is exchanged:
+//     R planes to each neighbour (ncclSend / ncclRecv in one group, in stream order, captured in the CUDA graph);
+//   * two scalar all-reduces: p.Ap, and (r.M^-1 r, r.r) together.
+// The data term needs no exchange: every slab keeps the cell blocks of all cells that touch a plane it owns
+// (points are filtered by floor(z) on the device) and applies only the rows of nodes it owns.
+//
+// NCCL is loaded at run time (dlopen of libnccl.so.2: the copy PyTorch already mapped when the caller is a
+// torchrun rank, else the system one), so single-GPU users of libfi_b200.so do not need it.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <mutex>
+
+#include "solver.hpp"
+
+namespace fi {
+
+namespace {
+
+struct Nccl
+{
+	void* lib = nullptr;
+	ncclResult_t (*GetUniqueId)(ncclUniqueId*)                                                            = nullptr;
+	ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int)                                      = nullptr;
+	ncclResult_t (*CommDestroy)(ncclComm_t)                                                                = nullptr;
+	ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t)               = nullptr;
+	ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t)                     = nullptr;
+	ncclResult_t (*GroupStart)()                                                                           = nullptr;
+	ncclResult_t (*GroupEnd)()                                                                             = nullptr;
+	const char* (*GetErrorString)(ncclResult_t)                                                            = nullptr;
+	std::string error;
+};
+
+Nccl& nccl()
+{
+	static Nccl           n;
+	static std::once_flag once;
+	std::call_once(once, [] {
+		for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+			n.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+			if (n.lib) { break; }
+		}
+		if (!n.lib) {
+			n.error = std::string("cannot load libnccl: ") + dlerror();
+			return;
+		}
+		auto sym = [&](const char* s) {
+			void* p = dlsym(n.lib, s);
+			if (!p && n.error.empty()) { n.error = std::string("libnccl lacks ") + s; }
+			return p;
+		};
+		n.GetUniqueId    = reinterpret_cast<decltype(n.GetUniqueId)>(sym("ncclGetUniqueId"));
+		n.CommInitRank   = reinterpret_cast<decltype(n.CommInitRank)>(sym("ncclCommInitRank"));
+		n.CommDestroy    = reinterpret_cast<decltype(n.CommDestroy)>(sym("ncclCommDestroy"));
+		n.AllReduce      = reinterpret_cast<decltype(n.AllReduce)>(sym("ncclAllReduce"));
+		n.Send           = reinterpret_cast<decltype(n.Send)>(sym("ncclSend"));
+		n.Recv           = reinterpret_cast<decltype(n.Recv)>(sym("ncclRecv"));
+		n.GroupStart     = reinterpret_cast<decltype(n.GroupStart)>(sym("ncclGroupStart"));
+		n.GroupEnd       = reinterpret_cast<decltype(n.GroupEnd)>(sym("ncclGroupEnd"));
+		n.GetErrorString = reinterpret_cast<decltype(n.GetErrorString)>(sym("ncclGetErrorString"));
+	});
+	FI_REQUIRE(n.error.empty(), FI_ERR_COMM, n.error);
+	return n;
+}
+
+#define FI_NCCL(expr)                                                                                         \
+	do {                                                                                                      \
+		ncclResult_t fi_r_ = (expr);                                                                          \
+		if (fi_r_ != ncclSuccess) {                                                                           \
+			throw ::fi::Error{FI_ERR_COMM, std::string(#expr) + ": " + nccl().GetErrorString(fi_r_)};         \
+		}                                                                                                     \
+	} while (0)
+
+}  // namespace
+
+void slab_range(int nz, int world, int rank, int* z0, int* z1)
+{
+	// contiguous, balanced to within one plane
+	*z0 = static_cast<int>(static_cast<int64_t>(nz) * rank / world);
+	*z1 = static_cast<int>(static_cast<int64_t>(nz) * (rank + 1) / world);
+}
+
+}  // namespace fi
+
+struct fi_comm
+{
+	ncclComm_t comm  = nullptr;
+	int        rank  = 0;
+	int        world = 1;
+	~fi_comm()
+	{
+		if (comm) { fi::nccl().CommDestroy(comm); }
+	}
+};
+
+namespace fi {
+
+namespace {
+
+// Halo exchange + scalar all-reduce of one slab over NCCL.
+struct SlabHooks final : DistHooks
+{
+	fi_comm* c;
+	Geom     g;
+	int      halo;
+	SlabHooks(fi_comm* comm, const Geom& geom, int h) : c(comm), g(geom), halo(h) {}
+
+	void allreduce(double* d_ptr, int count, cudaStream_t s) override
+	{
+		FI_NCCL(nccl().AllReduce(d_ptr, d_ptr, static_cast<size_t>(count), ncclDouble, ncclSum, c->comm, s));
+		count_launch();
+	}
+
+	void exchange_halo(void* d_vec, size_t elem, cudaStream_t s) override
+	{
+		if (c->world == 1 || halo == 0) { return; }
+		Nccl&        n     = nccl();
+		const size_t plane = static_cast<size_t>(g.stride[2]) * elem;  // bytes per plane
+		char*        base  = static_cast<char*>(d_vec);
+		const size_t bytes = plane * halo;
+		// owned planes are [zown0, zown1); lower halo [zown0 - halo, zown0), upper halo [zown1, zown1 + halo)
+		FI_NCCL(n.GroupStart());
+		if (c->rank > 0) {
+			FI_NCCL(n.Send(base + plane * g.zown0, bytes, ncclChar, c->rank - 1, c->comm, s));
+			FI_NCCL(n.Recv(base + plane * (g.zown0 - halo), bytes, ncclChar, c->rank - 1, c->comm, s));
+		}
+		if (c->rank + 1 < c->world) {
+			FI_NCCL(n.Send(base + plane * (g.zown1 - halo), bytes, ncclChar, c->rank + 1, c->comm, s));
+			FI_NCCL(n.Recv(base + plane * g.zown1, bytes, ncclChar, c->rank + 1, c->comm, s));
+		}
+		FI_NCCL(n.GroupEnd());
+		count_launch();
+	}
+};
+
+template <typename T>
+void slab_solve_typed(fi_comm* c, const Geom& g, int halo, const ModelAccum& model, const PointStore& pts, const fi_solve_options& o,
+                      const float* d_guess_own, float* d_out_own, fi_solve_stats* st, cudaStream_t s)
+{
+	HostRows  none;
+	auto      op = build_operator<T>(g, model, pts, none, s);
+	SlabHooks hooks(c, g, halo);
+	op->dist     = &hooks;
+	op->use_fast = kStencilAuto;
+	// the fused kernel evaluates p = M^-1 r + beta p_old on the halo planes too: it needs the neighbours' M^-1 there
+	hooks.exchange_halo(op->minv.data(), sizeof(T), s);
+	const int64_t off = g.own_offset(), n = g.own_cells();
+	DevBuf<T>     x(g.N);
+	x.zero(s);
+	if (d_guess_own) {
+		if (std::is_same<T, float>::value) {
+			FI_CUDA(cudaMemcpyAsync(x.data() + off, d_guess_own, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+		} else {
+			convert(d_guess_own, reinterpret_cast<double*>(x.data()) + off, n, s);
+		}
+	}
+	const PcgResult r = pcg_solve<T>(*op, nullptr, x.data(), o.tolerance, o.max_iterations, o.check_every, true, s);
+	if (std::is_same<T, float>::value) {
+		FI_CUDA(cudaMemcpyAsync(d_out_own, x.data() + off, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+	} else {
+		convert(reinterpret_cast<const double*>(x.data()) + off, d_out_own, n, s);
+	}
+	FI_CUDA(cudaStreamSynchronize(s));
+	if (st) {
+		std::memset(st, 0, sizeof(*st));
+		st->iterations        = r.iterations;
+		st->relative_residual = r.rel_residual;
+		st->true_residual     = r.true_residual;
+		st->initial_residual  = r.initial_residual;
+		st->setup_ms          = op->setup_ms;
+		st->solve_ms          = r.solve_ms;
+		st->converged         = r.converged ? 1 : 0;
+		st->occupied_cells    = op->data.nocc;
+		st->generic_rows      = op->data.nrows;
+	}
+}
+
+}  // namespace
+
+// add_model_impl's arithmetic (abi.cu) for one Weights value
+void accumulate_model(const fi_weights& w, ModelAccum& m);
+
+void slab_sdf_solve(fi_comm* c, const int32_t* sizes, const fi_weights& w, int64_t num_points, const float* positions, const float* normals,
+                    const float* point_weights, int loc, const fi_solve_options& o, const float* guess_own, float* solution_own,
+                    int sol_loc, fi_solve_stats* st)
+{
+	FI_REQUIRE(c != nullptr && c->comm != nullptr, FI_ERR_INVALID, "communicator is null");
+	FI_REQUIRE(o.precision == FI_F32 || o.precision == FI_F64, FI_ERR_UNSUPPORTED, "slab solves run in FI_F32 or FI_F64");
+	FI_REQUIRE(w.gradient_smoothness == 0.0f, FI_ERR_UNSUPPORTED, "slab solves need the star-shaped operator (gradient_smoothness = 0)");
+	FI_REQUIRE(normals == nullptr || w.gradient_kernel != FI_GRADIENT_LINEAR_INTERPOLATION, FI_ERR_UNSUPPORTED,
+	           "slab solves keep the data term in cell blocks: linear-interpolation gradient rows are not supported");
+	ModelAccum model;
+	accumulate_model(w, model);
+	int halo = 0;
+	for (int k = 0; k <= 4; ++k) {
+		if (model.on[k]) { halo = k; }
+	}
+	FI_REQUIRE(halo >= 1, FI_ERR_UNSUPPORTED, "slab solves need a smoothness order >= 1");
+	int z0 = 0, z1 = 0;
+	slab_range(sizes[2], c->world, c->rank, &z0, &z1);
+	FI_REQUIRE(z1 - z0 >= halo, FI_ERR_INVALID, "slabs thinner than the stencil radius: use fewer ranks");
+	const Geom g = make_slab_geom(sizes, z0, z1, halo);
+
+	cudaStream_t s = nullptr;
+	FI_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+	try {
+		const int      D = 3;
+		DevBuf<float>  dpos, dnrm, dpw;
+		const float *  ppos = positions, *pnrm = normals, *ppw = point_weights;
+		if (loc == FI_HOST && num_points > 0) {
+			dpos.resize(num_points * D);
+			FI_CUDA(cudaMemcpyAsync(dpos.data(), positions, num_points * D * sizeof(float), cudaMemcpyHostToDevice, s));
+			ppos = dpos.data();
+			if (normals) {
+				dnrm.resize(num_points * D);
+				FI_CUDA(cudaMemcpyAsync(dnrm.data(), normals, num_points * D * sizeof(float), cudaMemcpyHostToDevice, s));
+				pnrm = dnrm.data();
+			}
+			if (point_weights) {
+				dpw.resize(num_points);
+				FI_CUDA(cudaMemcpyAsync(dpw.data(), point_weights, num_points * sizeof(float), cudaMemcpyHostToDevice, s));
+				ppw = dpw.data();
+			}
+		}
+		PointStore pts;
+		canonicalise_points(g, pts, w.data_pos, w.value_kernel, w.data_gradient, w.gradient_kernel, num_points, ppos, pnrm, ppw, nullptr, s);
+		const int64_t n = g.own_cells();
+		DevBuf<float> d_guess, d_out;
+		const float*  gptr = guess_own;
+		float*        optr = solution_own;
+		if (sol_loc == FI_HOST) {
+			d_out.resize(n);
+			optr = d_out.data();
+			if (guess_own) {
+				d_guess.resize(n);
+				FI_CUDA(cudaMemcpyAsync(d_guess.data(), guess_own, n * sizeof(float), cudaMemcpyHostToDevice, s));
+				gptr = d_guess.data();
+			}
+		}
+		if (o.precision == FI_F32) {
+			slab_solve_typed<float>(c, g, halo, model, pts, o, gptr, optr, st, s);
+		} else {
+			slab_solve_typed<double>(c, g, halo, model, pts, o, gptr, optr, st, s);
+		}
+		if (sol_loc == FI_HOST) {
+			FI_CUDA(cudaMemcpyAsync(solution_own, d_out.data(), n * sizeof(float), cudaMemcpyDeviceToHost, s));
+			FI_CUDA(cudaStreamSynchronize(s));
+		}
+	} catch (...) {
+		cudaStreamDestroy(s);
+		throw;
+	}
+	cudaStreamDestroy(s);
+}
+
+void comm_unique_id(void* id, int64_t capacity)
+{
+	FI_REQUIRE(id != nullptr && capacity >= static_cast<int64_t>(sizeof(ncclUniqueId)), FI_ERR_INVALID, "id buffer must hold 128 bytes");
+	ncclUniqueId u;
+	FI_NCCL(nccl().GetUniqueId(&u));
+	std::memcpy(id, &u, sizeof(u));
+}
+
+void comm_destroy(fi_comm* c) { delete c; }
+
+fi_comm* comm_create(int rank, int world, const void* id)
+{
+	FI_REQUIRE(world >= 1 && rank >= 0 && rank < world && id != nullptr, FI_ERR_INVALID, "bad rank / world / id");
+	ncclUniqueId u;
+	std::memcpy(&u, id, sizeof(u));
+	auto c   = std::make_unique<fi_comm>();
+	c->rank  = rank;
+	c->world = world;
+	FI_NCCL(nccl().CommInitRank(&c->comm, world, u, rank));
+	return c.release();
+}
+
+}  // namespace fi

@@ -10,9 +10,19 @@ namespace fi {
 struct Geom  // LatticeField geometry, reference field_interpolation.hpp:97-114 (x fastest)
 {
 	int     ndim = 0;
-	int     size[kMaxDim]   = {1, 1, 1};
+	int     size[kMaxDim]   = {1, 1, 1};   // the whole lattice (also when this process holds one z slab of it)
 	int64_t stride[kMaxDim] = {1, 1, 1};
-	int64_t N = 1;
+	int64_t N = 1;                         // cells stored locally = nx * ny * nzl
+	// z-slab window (multi-GPU, dist.cu).  Local plane l holds lattice plane l + zoff; planes whose lattice z
+	// falls outside [0, size[2]) exist in memory but stay zero.  Unsharded: zoff = 0, nzl = size[2].
+	int     zoff = 0;
+	int     nzl = 1;                       // planes stored locally
+	int     zown0 = 0, zown1 = 1;          // local planes this process owns (computes rows for): [zown0, zown1)
+	int64_t shift = 0;                     // = -stride[2] * zoff: local index = sum coord[d] * stride[d] + shift
+
+	__host__ __device__ bool sharded() const { return zown0 != 0 || zown1 != nzl; }
+	__host__ __device__ int64_t own_offset() const { return static_cast<int64_t>(zown0) * (ndim == 3 ? stride[2] : 0); }
+	__host__ __device__ int64_t own_cells() const { return ndim == 3 ? static_cast<int64_t>(zown1 - zown0) * stride[2] : N; }
 };
 
 inline Geom make_geom(int ndim, const int32_t* sizes)
@@ -26,6 +36,21 @@ inline Geom make_geom(int ndim, const int32_t* sizes)
 		s *= sizes[d];
 	}
 	g.N = s;
+	g.nzl   = ndim == 3 ? sizes[2] : 1;
+	g.zown1 = g.nzl;
+	return g;
+}
+
+// The slab of lattice planes [z0, z1) with `halo` planes stored on either side (3D only).
+inline Geom make_slab_geom(const int32_t* sizes, int z0, int z1, int halo)
+{
+	Geom g  = make_geom(3, sizes);
+	g.zoff  = z0 - halo;
+	g.nzl   = (z1 - z0) + 2 * halo;
+	g.zown0 = halo;
+	g.zown1 = halo + (z1 - z0);
+	g.shift = -g.stride[2] * g.zoff;
+	g.N     = g.stride[2] * g.nzl;
 	return g;
 }
 
@@ -150,5 +175,14 @@ template <typename T>
 void stencil_apply(const Geom& g, const StencilTables& t, const T* p, T* q, double* d_dot_out, double* d_partial,
                    unsigned* d_ticket, const int* d_done, int mode, cudaStream_t s);
 int stencil_partial_slots(const Geom& g);  // upper bound of blocks any stencil launch uses (size of d_partial)
+
+// ---- dist.cu ------------------------------------------------------------------------------------------------
+void     slab_range(int nz, int world, int rank, int* z0, int* z1);
+void     comm_unique_id(void* id, int64_t capacity);
+fi_comm* comm_create(int rank, int world, const void* id);
+void     comm_destroy(fi_comm* c);
+void     slab_sdf_solve(fi_comm* c, const int32_t* sizes, const fi_weights& w, int64_t num_points, const float* positions, const float* normals,
+                        const float* point_weights, int loc, const fi_solve_options& o, const float* guess_own, float* solution_own,
+                        int sol_loc, fi_solve_stats* st);
 
 }  // namespace fi

@@ -74,7 +74,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads) pcg_init_kernel(int64_t n, const T* __restrict__ b, const T* __restrict__ q,
                                                             const T* __restrict__ minv, T* __restrict__ r, T* __restrict__ p,
                                                             PcgState* st, double tol, long long max_iters, double* partial,
-                                                            unsigned* ticket)
+                                                            unsigned* ticket, int dist)
 {
 	__shared__ double red[32];
 	double            acc[3] = {0, 0, 0};
@@ -91,6 +91,12 @@ __global__ void __launch_bounds__(kThreads) pcg_init_kernel(int64_t n, const T* 
 	acc[1] = block_sum(acc[1], red);
 	acc[2] = block_sum(acc[2], red);
 	grid_sum<3>(acc, partial, ticket, red, [&](const double(&tot)[3]) {
+		if (dist) {  // partial sums of this slab: all-reduced, then pcg_init_finish_kernel
+			st->part[0] = tot[0];
+			st->part[1] = tot[1];
+			st->part[2] = tot[2];
+			return;
+		}
 		st->rho[0]    = tot[0];
 		st->rho[1]    = 0;
 		st->pq        = 0;
@@ -105,11 +111,37 @@ __global__ void __launch_bounds__(kThreads) pcg_init_kernel(int64_t n, const T* 
 	});
 }
 
+__global__ void pcg_init_finish_kernel(PcgState* st, double tol, long long max_iters)
+{
+	const double rho = st->part[0], rr = st->part[1], bb = st->part[2];
+	st->rho[0]    = rho;
+	st->rho[1]    = 0;
+	st->pq        = 0;
+	st->rr        = rr;
+	st->rr0       = rr;
+	st->bb        = bb;
+	st->tol2bb    = tol * tol * bb;
+	st->iters     = 0;
+	st->max_iters = max_iters;
+	st->breakdown = 0;
+	st->done      = (bb == 0.0 || rr <= tol * tol * bb || max_iters <= 0) ? 1 : 0;
+}
+
+__global__ void pcg_update_finish_kernel(PcgState* st, int par)
+{
+	if (st->done) { return; }
+	const double rho = st->part[0], rr = st->part[1];
+	st->rho[par ^ 1] = rho;
+	st->rr           = rr;
+	st->iters += 1;
+	if (rr <= st->tol2bb || st->iters >= st->max_iters || !(rho > 0.0)) { st->done = 1; }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads) pcg_update_kernel(int64_t n, T* __restrict__ x, T* __restrict__ r,
                                                               const T* __restrict__ p, const T* __restrict__ q,
                                                               const T* __restrict__ minv, PcgState* st, int par,
-                                                              double* partial, unsigned* ticket)
+                                                              double* partial, unsigned* ticket, int dist)
 {
 	__shared__ double red[32];
 	if (st->done) { return; }
@@ -156,6 +188,11 @@ __global__ void __launch_bounds__(kThreads) pcg_update_kernel(int64_t n, T* __re
 	acc[0] = block_sum(acc[0], red);
 	acc[1] = block_sum(acc[1], red);
 	grid_sum<2>(acc, partial, ticket, red, [&](const double(&tot)[2]) {
+		if (dist) {  // all-reduced, then pcg_update_finish_kernel
+			st->part[0] = tot[0];
+			st->part[1] = tot[1];
+			return;
+		}
 		st->rho[par ^ 1] = tot[0];
 		st->rr           = tot[1];
 		st->iters += 1;
@@ -235,7 +272,7 @@ __global__ void add_f32_f64_kernel(int64_t n, const float* __restrict__ e, doubl
 }
 
 template <typename T>
-void ensure_work(Operator<T>& op)
+void ensure_work(Operator<T>& op, cudaStream_t s)
 {
 	PcgWork<T>& w = op.work;
 	const size_t n = static_cast<size_t>(op.g.N);
@@ -244,10 +281,16 @@ void ensure_work(Operator<T>& op)
 		w.p.resize(n);
 		w.q.resize(n);
 		w.p2.resize(n);
+		// halo planes and (slabs) planes beyond the lattice are read by the stencil kernels: start finite
+		// (on the solver's own stream: it is non-blocking, so work on the null stream is not ordered with it)
+		w.r.zero(s);
+		w.p.zero(s);
+		w.p2.zero(s);
+		w.q.zero(s);
 		w.partial.resize(static_cast<size_t>(3) * (static_cast<size_t>(sm_count()) * 8 + 8));
 		w.ticket.resize(1);
 		w.state.resize(1);
-		FI_CUDA(cudaMemset(w.ticket.data(), 0, sizeof(unsigned)));
+		w.ticket.zero(s);
 	}
 }
 
@@ -304,13 +347,16 @@ std::unique_ptr<Operator<T>> build_operator(const Geom& g, const ModelAccum& m, 
 template <typename T>
 void residual(Operator<T>& op, const T* b, const T* x, T* r, double* rr, double* bb, cudaStream_t s)
 {
-	ensure_work(op);
-	PcgWork<T>& w = op.work;
+	ensure_work(op, s);
+	PcgWork<T>&   w   = op.work;
+	const int64_t off = op.g.own_offset(), n = op.g.own_cells();
+	if (op.dist) { op.dist->exchange_halo(const_cast<T*>(x), sizeof(T), s); }
 	op.apply(x, w.q.data(), nullptr, nullptr, s);
 	DevBuf<double> out(2);
 	auto kern = residual_kernel<T>;
-	FI_LAUNCH(kern, vec_grid(op.g.N), kThreads, 0, s, op.g.N, b ? b : op.atb.data(), w.q.data(), r, out.data(), w.partial.data(),
-	          w.ticket.data());
+	FI_LAUNCH(kern, vec_grid(n), kThreads, 0, s, n, (b ? b : op.atb.data()) + off, w.q.data() + off, r ? r + off : nullptr, out.data(),
+	          w.partial.data(), w.ticket.data());
+	if (op.dist) { op.dist->allreduce(out.data(), 2, s); }
 	double h[2];
 	FI_CUDA(cudaMemcpyAsync(h, out.data(), sizeof(h), cudaMemcpyDeviceToHost, s));
 	FI_CUDA(cudaStreamSynchronize(s));
@@ -322,11 +368,15 @@ template <typename T>
 PcgResult pcg_solve(Operator<T>& op, const T* b, T* x, double tol, long long max_iter, int check_every, bool want_true_residual,
                     cudaStream_t s)
 {
-	ensure_work(op);
+	ensure_work(op, s);
 	PcgWork<T>&   w = op.work;
-	const int64_t n = op.g.N;
+	// vector kernels run over the planes this process owns (everything, unless the lattice is slab-sharded)
+	const int64_t off = op.g.own_offset(), n = op.g.own_cells();
+	DistHooks*    dist = op.dist;
 	const T*      rhs = b ? b : op.atb.data();
-	if (max_iter <= 0) { max_iter = 2 * n; }  // Eigen: maxIterations() = 2 * cols by default
+	if (max_iter <= 0) {  // Eigen: maxIterations() = 2 * cols by default
+		max_iter = 2 * static_cast<long long>(op.g.size[0]) * op.g.size[1] * op.g.size[2];
+	}
 	if (!(tol > 0)) { tol = std::is_same<T, float>::value ? 1.1920929e-07 : 2.220446049250313e-16; }
 	check_every = std::max(2, check_every <= 0 ? 32 : check_every);
 	check_every += check_every & 1;  // whole parity pairs per graph
@@ -337,11 +387,17 @@ PcgResult pcg_solve(Operator<T>& op, const T* b, T* x, double tol, long long max
 	FI_CUDA(cudaEventRecord(e0, s));
 
 	const int grid = vec_grid(n);
+	if (dist) { dist->exchange_halo(x, sizeof(T), s); }
 	op.apply(x, w.q.data(), nullptr, nullptr, s);
 	{
 		auto kern = pcg_init_kernel<T>;
-		FI_LAUNCH(kern, grid, kThreads, 0, s, n, rhs, w.q.data(), op.minv.data(), w.r.data(), w.p.data(), w.state.data(), tol,
-		          max_iter, w.partial.data(), w.ticket.data());
+		FI_LAUNCH(kern, grid, kThreads, 0, s, n, rhs + off, w.q.data() + off, op.minv.data() + off, w.r.data() + off, w.p.data() + off,
+		          w.state.data(), tol, max_iter, w.partial.data(), w.ticket.data(), dist ? 1 : 0);
+		if (dist) {
+			dist->allreduce(w.state.data()->part, 3, s);
+			FI_LAUNCH(pcg_init_finish_kernel, 1, 1, 0, s, w.state.data(), tol, max_iter);
+			dist->exchange_halo(w.r.data(), sizeof(T), s);
+		}
 	}
 	PcgState h;
 	FI_CUDA(cudaMemcpyAsync(&h, w.state.data(), sizeof(h), cudaMemcpyDeviceToHost, s));
@@ -351,7 +407,7 @@ PcgResult pcg_solve(Operator<T>& op, const T* b, T* x, double tol, long long max
 	res.zero_rhs         = (h.bb == 0.0);
 	res.initial_residual = h.bb > 0 ? std::sqrt(h.rr0 / h.bb) : 0.0;
 	if (res.zero_rhs) {
-		FI_CUDA(cudaMemsetAsync(x, 0, n * sizeof(T), s));  // Eigen: rhs == 0 => x = 0
+		FI_CUDA(cudaMemsetAsync(x + off, 0, n * sizeof(T), s));  // Eigen: rhs == 0 => x = 0
 	} else if (!h.done) {
 		const int* d_done = &w.state.data()->done;
 		double*    d_pq   = &w.state.data()->pq;
@@ -369,14 +425,21 @@ PcgResult pcg_solve(Operator<T>& op, const T* b, T* x, double tol, long long max
 				                                         w.state.data(), par, d_pq, op.partial.data(), op.ticket.data(), d_done, s);
 				if (fused) {
 					apply_data_term<T>(op.g, op.data, pp[par ^ 1], w.q.data(), d_pq, d_done, s);
+					if (dist) { dist->allreduce(d_pq, 1, s); }
 					auto ku = pcg_update_kernel<T>;
-					FI_LAUNCH(ku, grid, kThreads, 0, s, n, x, w.r.data(), pp[par ^ 1], w.q.data(), op.minv.data(), w.state.data(), par,
-					          w.partial.data(), w.ticket.data());
+					FI_LAUNCH(ku, grid, kThreads, 0, s, n, x + off, w.r.data() + off, pp[par ^ 1] + off, w.q.data() + off, op.minv.data() + off,
+					          w.state.data(), par, w.partial.data(), w.ticket.data(), dist ? 1 : 0);
+					if (dist) {
+						dist->allreduce(w.state.data()->part, 2, s);
+						FI_LAUNCH(pcg_update_finish_kernel, 1, 1, 0, s, w.state.data(), par);
+						dist->exchange_halo(w.r.data(), sizeof(T), s);
+					}
 				} else {
+					FI_REQUIRE(dist == nullptr, FI_ERR_UNSUPPORTED, "a slab-sharded solve needs the fused 3D stencil kernel");
 					op.apply(w.p.data(), w.q.data(), d_pq, d_done, s);
 					auto ku = pcg_update_kernel<T>;
 					FI_LAUNCH(ku, grid, kThreads, 0, s, n, x, w.r.data(), w.p.data(), w.q.data(), op.minv.data(), w.state.data(), par,
-					          w.partial.data(), w.ticket.data());
+					          w.partial.data(), w.ticket.data(), 0);
 					auto kd = pcg_direction_kernel<T>;
 					FI_LAUNCH(kd, grid, kThreads, 0, s, n, w.r.data(), op.minv.data(), w.p.data(), w.state.data(), par);
 				}
@@ -434,7 +497,7 @@ PcgResult pcg_solve(Operator<T>& op, const T* b, T* x, double tol, long long max
 template <typename T>
 void jacobi_sweeps(Operator<T>& op, T* x, int iterations, T weight, cudaStream_t s)
 {
-	ensure_work(op);
+	ensure_work(op, s);
 	PcgWork<T>& w = op.work;
 	for (int it = 0; it < iterations; ++it) {
 		op.apply(x, w.q.data(), nullptr, nullptr, s);
@@ -448,7 +511,7 @@ void jacobi_sweeps(Operator<T>& op, T* x, int iterations, T weight, cudaStream_t
 template <typename T>
 void time_kernels(Operator<T>& op, int iterations, int check_every, double* out, cudaStream_t s)
 {
-	ensure_work(op);
+	ensure_work(op, s);
 	PcgWork<T>&   w = op.work;
 	const int64_t n = op.g.N;
 	DevBuf<T>     x(n);
@@ -458,7 +521,8 @@ void time_kernels(Operator<T>& op, int iterations, int check_every, double* out,
 	out[0] = r.loop_ms;
 	// re-arm the state so the kernels do real work when launched on their own
 	PcgState h;
-	FI_CUDA(cudaMemcpy(&h, w.state.data(), sizeof(h), cudaMemcpyDeviceToHost));
+	FI_CUDA(cudaMemcpyAsync(&h, w.state.data(), sizeof(h), cudaMemcpyDeviceToHost, s));
+	FI_CUDA(cudaStreamSynchronize(s));
 	h.done      = 0;
 	h.max_iters = 1ll << 60;
 	h.tol2bb    = 0;
@@ -466,7 +530,8 @@ void time_kernels(Operator<T>& op, int iterations, int check_every, double* out,
 	if (!(h.rho[0] > 0)) { h.rho[0] = 1; }
 	if (!(h.rho[1] > 0)) { h.rho[1] = 1; }
 	if (!(h.pq > 0)) { h.pq = 1; }
-	FI_CUDA(cudaMemcpy(w.state.data(), &h, sizeof(h), cudaMemcpyHostToDevice));
+	FI_CUDA(cudaMemcpyAsync(w.state.data(), &h, sizeof(h), cudaMemcpyHostToDevice, s));
+	FI_CUDA(cudaStreamSynchronize(s));
 	cudaEvent_t e0, e1;
 	FI_CUDA(cudaEventCreate(&e0));
 	FI_CUDA(cudaEventCreate(&e1));
@@ -494,11 +559,12 @@ void time_kernels(Operator<T>& op, int iterations, int check_every, double* out,
 	});
 	// alpha = rho/pq is recomputed from the (frozen) state each launch; a tiny alpha keeps the vectors finite
 	h.pq = 1e30;
-	FI_CUDA(cudaMemcpy(w.state.data(), &h, sizeof(h), cudaMemcpyHostToDevice));
+	FI_CUDA(cudaMemcpyAsync(w.state.data(), &h, sizeof(h), cudaMemcpyHostToDevice, s));
+	FI_CUDA(cudaStreamSynchronize(s));
 	out[2] = timed([&](int i) {
 		auto ku = pcg_update_kernel<T>;
 		FI_LAUNCH(ku, vec_grid(n), kThreads, 0, s, n, x.data(), w.r.data(), w.p.data(), w.q.data(), op.minv.data(), w.state.data(), 0,
-		          w.partial.data(), w.ticket.data());  // reads rho[0], pq (frozen); writes rho[1], rr, iters
+		          w.partial.data(), w.ticket.data(), 0);  // reads rho[0], pq (frozen); writes rho[1], rr, iters
 	});
 	out[3] = 0.0;
 	if (!fused) {

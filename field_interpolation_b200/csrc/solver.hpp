@@ -19,6 +19,17 @@ struct PcgState
 	int    breakdown;
 	long long iters;
 	long long max_iters;
+	double part[4];  // multi-GPU: this rank's partial sums, all-reduced in place before the finish kernels read them
+};
+
+// Multi-GPU plumbing of one z-slab solve (dist.cu); nullptr everywhere else.
+struct DistHooks
+{
+	virtual ~DistHooks() = default;
+	// in-place sum over ranks of `count` doubles in device memory, enqueued on s (capturable)
+	virtual void allreduce(double* d_ptr, int count, cudaStream_t s) = 0;
+	// fills the halo planes of a local lattice vector from the neighbouring slabs' owned planes
+	virtual void exchange_halo(void* d_vec, size_t elem_size, cudaStream_t s) = 0;
 };
 
 template <typename T>
@@ -44,6 +55,7 @@ struct Operator
 	int              use_fast = kStencilAuto;  // StencilMode
 	double           setup_ms = 0;
 	PcgWork<T>       work;
+	DistHooks*       dist = nullptr;  // set for a z-slab of a lattice shared with other ranks
 
 	// q = (S + P) p; when d_dot is non-null it receives p.q (deterministic apart from the order of the data
 	// term's atomics into q).
@@ -67,6 +79,7 @@ struct PcgResult
 };
 
 // Solves A x = b from the guess in x (device, N elements of T).  b == nullptr: the operator's own A^T b.
+// With op.dist set, x / b are local slab vectors (halo planes included) and every rank calls this together.
 template <typename T>
 PcgResult pcg_solve(Operator<T>& op, const T* b, T* x, double tol, long long max_iter, int check_every, bool want_true_residual,
                     cudaStream_t s);

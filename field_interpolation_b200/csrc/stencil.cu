@@ -54,10 +54,15 @@ __device__ __forceinline__ int lap1(int i, int n, int o)
 
 __device__ __forceinline__ void coords_of(const Geom& g, int64_t index, int* c)
 {
+	// lattice coordinates of local cell `index` (the slowest axis runs over the locally stored planes)
 	c[0] = c[1] = c[2] = 0;
 	for (int d = 0; d < g.ndim; ++d) {
-		c[d] = static_cast<int>(index % g.size[d]);
-		index /= g.size[d];
+		if (d == g.ndim - 1) {
+			c[d] = static_cast<int>(index) + (d == 2 ? g.zoff : 0);
+		} else {
+			c[d] = static_cast<int>(index % g.size[d]);
+			index /= g.size[d];
+		}
 	}
 }
 
@@ -68,6 +73,7 @@ __global__ void diagonal_kernel(Geom g, DevTables<T> tab, T* __restrict__ diag)
 	if (i >= g.N) { return; }
 	int c[kMaxDim];
 	coords_of(g, i, c);
+	if (c[2] < 0 || c[2] >= g.size[2]) { return; }  // slab planes beyond the lattice stay zero
 	T acc = 0;
 	for (int d = 0; d < g.ndim; ++d) { acc += tab.band[d][row_class(c[d], g.size[d])][4]; }
 	if (tab.gs2 != T(0)) {

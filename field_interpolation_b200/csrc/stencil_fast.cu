@@ -255,7 +255,7 @@ template <typename T>
 bool eligible(const Geom& g, const StencilTables& t)
 {
 	constexpr int V = 16 / sizeof(T);
-	return g.ndim == 3 && t.gs2 == 0.0 && t.radius >= 1 && g.size[0] % V == 0 && g.size[0] >= 32 && g.size[1] >= 8 && g.size[2] >= 8;
+	return g.ndim == 3 && t.gs2 == 0.0 && t.radius >= 1 && g.size[0] % V == 0 && g.size[0] >= 32 && g.size[1] >= 8 && g.size[2] >= 8 && !g.sharded();
 }
 
 }  // namespace

@@ -120,7 +120,8 @@ __global__ void __launch_bounds__(256, MINB)
     stencil3d_tma_kernel(const __grid_constant__ CUtensorMap map_a,  // p (plain) or r (fused)
                          const __grid_constant__ CUtensorMap map_b,  // M^-1 (fused)
                          const __grid_constant__ CUtensorMap map_c,  // p_old (fused)
-                         int nx, int ny, int nz, int zchunk, TmaTables<T> tab, T* __restrict__ q, T* __restrict__ p_new,
+                         int nx, int ny, int nzl, int zo0, int zo1, int zoff, int nzg, int zchunk, TmaTables<T> tab,
+                         T* __restrict__ q, T* __restrict__ p_new,
                          const PcgState* st, int par, double* dot_out, double* partial, unsigned* ticket, const int* done)
 {
 	using G           = Tile<T, R>;
@@ -147,8 +148,13 @@ __global__ void __launch_bounds__(256, MINB)
 	const int y0t = blockIdx.y * G::TY;
 	const int x0  = x0t + tx * V;
 	const int y   = y0t + ty;
-	const int zb  = blockIdx.z * zchunk;
-	const int ze  = min(nz, zb + zchunk);
+	// local planes [zo0, zo1) are owned (q is computed there) and split into chunks; lattice z = local z + zoff
+	const int zb  = zo0 + blockIdx.z * zchunk;
+	const int ze  = min(zo1, zb + zchunk);
+	// the new direction is also written on up to R stored planes either side of the owned range (slab halos:
+	// every slab recomputes its neighbours' boundary planes instead of exchanging p)
+	const int wlo = blockIdx.z == 0 ? max(0, zo0 - R) : zb;
+	const int whi = ze == zo1 ? min(nzl, zo1 + R) : ze;
 	const bool   in_xy = (x0 < nx) && (y < ny);
 	const size_t plane = static_cast<size_t>(nx) * ny;
 
@@ -237,7 +243,7 @@ __global__ void __launch_bounds__(256, MINB)
 			rg[own_at] = pipe[k].v;
 			if (has_yh) { rg[yh_at] = direction(sa, sb, sc, yh_at); }
 			if (has_xh) { rg[xh_at] = direction(sa, sb, sc, xh_at); }
-			if (Fused && in_xy && lp >= zb && lp < ze) { *reinterpret_cast<Pack*>(pout + static_cast<size_t>(lp) * plane) = pipe[k].v; }
+			if (Fused && in_xy && lp >= wlo && lp < whi) { *reinterpret_cast<Pack*>(pout + static_cast<size_t>(lp) * plane) = pipe[k].v; }
 			__syncthreads();
 			if (tid == 0 && i + S < n_iter) { issue(i + S); }
 
@@ -246,7 +252,7 @@ __global__ void __launch_bounds__(256, MINB)
 				int zslot = slot - R;
 				if (zslot < 0) { zslot += G::RING; }
 				const Pack* pz = ring_ptr(zslot);
-				const T*    cz = zband + row_class(z, nz) * W;
+				const T*    cz = zband + row_class(z + zoff, nzg) * W;
 				const PU&   ctr = pipe[(k + 1 + R) % W];
 				PU          out;
 #pragma unroll
@@ -326,7 +332,7 @@ CUtensorMap make_map(const Geom& g, const T* ptr)
 	std::memset(&m, 0, sizeof(m));
 	EncodeFn fn = encode_fn();
 	FI_REQUIRE(fn != nullptr, FI_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
-	const cuuint64_t dims[3]    = {static_cast<cuuint64_t>(g.size[0]), static_cast<cuuint64_t>(g.size[1]), static_cast<cuuint64_t>(g.size[2])};
+	const cuuint64_t dims[3]    = {static_cast<cuuint64_t>(g.size[0]), static_cast<cuuint64_t>(g.size[1]), static_cast<cuuint64_t>(g.nzl)};
 	const cuuint64_t strides[2] = {static_cast<cuuint64_t>(g.size[0]) * sizeof(T), static_cast<cuuint64_t>(g.size[0]) * g.size[1] * sizeof(T)};
 	const cuuint32_t box[3]     = {static_cast<cuuint32_t>(G::BXP * G::V), static_cast<cuuint32_t>(G::BY), 1u};
 	const cuuint32_t estr[3]    = {1u, 1u, 1u};
@@ -356,9 +362,10 @@ void launch(const Geom& g, const StencilTables& t, const T* a, const T* b, const
 	const int64_t resident    = static_cast<int64_t>(sm_count()) * MINB;
 	const int64_t want_blocks = resident * 8;
 	int           chunks      = static_cast<int>(std::max<int64_t>(1, want_blocks / (static_cast<int64_t>(tiles_x) * tiles_y)));
-	chunks                    = std::min(chunks, std::max(1, g.size[2] / 16));
-	const int zchunk          = div_up(g.size[2], chunks);
-	chunks                    = div_up(g.size[2], zchunk);
+	const int nown            = g.zown1 - g.zown0;
+	chunks                    = std::min(chunks, std::max(1, nown / 16));
+	const int zchunk          = div_up(nown, chunks);
+	chunks                    = div_up(nown, zchunk);
 	dim3 grid(tiles_x, tiles_y, chunks);
 	auto kern = stencil3d_tma_kernel<T, R, S, Fused, MINB>;
 	constexpr size_t smem = smem_bytes<T, R, S, Fused>();
@@ -367,16 +374,16 @@ void launch(const Geom& g, const StencilTables& t, const T* a, const T* b, const
 		FI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
 		configured = true;
 	}
-	FI_LAUNCH(kern, grid, 256, smem, s, ma, mb, mc, g.size[0], g.size[1], g.size[2], zchunk, tab, q, p_new, st, par, d_dot_out,
-	          d_partial, d_ticket, d_done);
+	FI_LAUNCH(kern, grid, 256, smem, s, ma, mb, mc, g.size[0], g.size[1], g.nzl, g.zown0, g.zown1, g.zoff, g.size[2], zchunk, tab, q, p_new,
+	          st, par, d_dot_out, d_partial, d_ticket, d_done);
 }
 
 template <typename T>
 bool eligible(const Geom& g, const StencilTables& t)
 {
 	constexpr int V = 16 / sizeof(T);
-	return g.ndim == 3 && t.gs2 == 0.0 && t.radius >= 1 && g.size[0] % V == 0 && g.size[0] >= 32 && g.size[1] >= 8 && g.size[2] >= 8 &&
-	       encode_fn() != nullptr;
+	return g.ndim == 3 && t.gs2 == 0.0 && t.radius >= 1 && g.size[0] % V == 0 && g.size[0] >= 32 && g.size[1] >= 8 && g.zown1 - g.zown0 >= 1 &&
+	       (g.sharded() || g.size[2] >= 8) && encode_fn() != nullptr;
 }
 
 template <typename T, bool Fused>

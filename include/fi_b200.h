@@ -199,6 +199,26 @@ FI_API int fi_sdf_solve_cascade(int32_t ndim, const int32_t* sizes, const fi_wei
                          const float* unit_positions, const float* normals, const float* point_weights,
                          const fi_cascade_options* opt, float* solution, int32_t loc, fi_cascade_stats* stats);
 
+/* ---- multi-GPU: one process per GPU, z-slab partition of a 3D lattice ---------------------- */
+/* The reference is single-process; this is the scale-out of the same solve.  Ranks share an NCCL communicator
+ * created from a 128-byte id that rank 0 obtains and the caller distributes (MPI, torch.distributed, a file).
+ * NCCL is loaded at run time; FI_ERR_COMM when it is missing or a collective fails. */
+typedef struct fi_comm fi_comm;
+FI_API int fi_comm_unique_id(void* id, int64_t capacity /* >= 128 */);
+FI_API int fi_comm_create(int32_t rank, int32_t world, const void* id, fi_comm** out); /* binds the current device */
+FI_API int fi_comm_destroy(fi_comm* c);
+/* Planes [z0, z1) of an nz-plane lattice owned by `rank` (contiguous, balanced to one plane).  Pure host code. */
+FI_API int fi_slab_range(int32_t nz, int32_t world, int32_t rank, int32_t* z0, int32_t* z1);
+/* sdf_from_points + PCG on the slab of this rank: every rank passes the whole point cloud (positions in lattice
+ * coordinates of the full lattice) and receives its owned planes, (z1 - z0) * nx * ny floats, in solution_own.
+ * Collective: all ranks of the communicator call it together with the same arguments except the buffers.
+ * guess_own (nullable) is this rank's part of the starting guess.  FI_F32 or FI_F64; star-shaped smoothness
+ * (gradient_smoothness = 0), nearest / cell-edge gradient kernels. */
+FI_API int fi_slab_sdf_solve(fi_comm* c, const int32_t* sizes /* 3 */, const fi_weights* w, int64_t num_points,
+                      const float* positions, const float* normals, const float* point_weights, int32_t loc,
+                      const fi_solve_options* opt, const float* guess_own, float* solution_own, int32_t solution_loc,
+                      fi_solve_stats* stats);
+
 /* ---- instrumentation -------------------------------------------------------------------------- */
 /* Number of kernels this library has launched on the calling thread's device since load (bench.py's
  * gpu_launches), and a reset. */

@@ -1,0 +1,55 @@
+"""Multi-GPU parity check (run under torchrun on >= 2 GPUs): the z-slab sharded solve against the single-GPU
+solve of the same system, iterate for iterate.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 scripts/slab_check.py
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import field_interpolation_b200 as fi
+from field_interpolation_b200 import dist as fid
+from field_interpolation_b200 import workloads as W
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+ok = True
+for sizes, npts, orders in (([64, 48, 40], 4000, {}), ([128, 64, 37], 20000, dict(model_1=0.3)), ([96, 40, 64], 8000, dict(model_2=0.0, model_4=0.2)),
+                            ([256, 256, 256], 1000000, {})):
+    cloud = W.sphere_torus_3d(npts, seed=1)
+    pos = W.to_lattice(cloud["unit_pos"], sizes)
+    weights = fi.Weights(**orders)
+    runner = fid.SlabRunner(sizes, weights, rank, world, dist)
+    d_pos, d_nrm = torch.from_numpy(pos).cuda(), torch.from_numpy(cloud["normals"]).cuda()
+    for prec, name, tol in ((fi.FI_F32, "f32", 2e-4), (fi.FI_F64, "f64", 1e-10)):
+        for its in (1, 2, 25):
+            opt = fi.solve_options(prec, its, 1e-30, check_every=8)
+            out = torch.zeros(runner.local_cells, device="cuda")
+            st = runner.step(d_pos, d_nrm, opt, out)
+            parts = [torch.zeros(fid.slab_range(sizes[2], world, r)[1] * sizes[0] * sizes[1] - fid.slab_range(sizes[2], world, r)[0] * sizes[0] * sizes[1],
+                                 device="cuda") for r in range(world)]
+            dist.all_gather(parts, out)
+            full = torch.cat(parts).cpu().numpy()
+            if rank == 0:
+                f = fi.sdf_from_points(sizes, weights, d_pos, d_nrm)
+                ref, st1 = f.solve(opt, out=torch.zeros(int(np.prod(sizes)), device="cuda"))
+                ref = ref.cpu().numpy()
+                err = float(np.linalg.norm(full - ref) / max(np.linalg.norm(ref), 1e-300))
+                good = err <= tol and st["iterations"] == st1["iterations"] == its and abs(st["relative_residual"] - st1["relative_residual"]) <= 1e-3 * st1["relative_residual"] + 1e-12
+                ok = ok and good
+                print(json.dumps({"sizes": sizes, "prec": name, "its": its, "rel_diff_vs_single": err, "relres_slab": st["relative_residual"],
+                                  "relres_single": st1["relative_residual"], "true_slab": st["true_residual"], "true_single": st1["true_residual"], "ok": bool(good)}), flush=True)
+                f.close()
+    runner.close()
+flag = torch.tensor([1 if ok else 0], device="cuda")
+dist.broadcast(flag, src=0)
+dist.destroy_process_group()
+if rank == 0:
+    print("SLAB CHECK", "PASSED" if ok else "FAILED")
+sys.exit(0 if int(flag.item()) else 1)
