@@ -99,6 +99,8 @@ SIGNATURES = {
     "fi_slab_range": (C.c_int, [_i32, _i32, _i32, _pi32, _pi32]),
     "fi_slab_sdf_solve": (C.c_int, [_vp, _pi32, _p(fi_weights), _i64, _vp, _vp, _vp, _i32, _p(fi_solve_options), _vp, _vp, _i32,
                                     _p(fi_solve_stats)]),
+    "fi_trim_memory": (C.c_int, []),
+    "fi_cached_bytes": (_i64, []),
     "fi_kernel_launches": (_i64, []),
     "fi_kernel_launches_reset": (None, []),
     "fi_field_time_iterations": (C.c_int, [_vp, _p(fi_solve_options), _i32, _pd]),

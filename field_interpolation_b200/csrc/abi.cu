@@ -1,9 +1,14 @@
 // C ABI of libfi_b200 (declared in include/fi_b200.h): the LatticeField handle, the constraint builders, the
 // triplet view, the solvers and the coarse-to-fine driver.  Everything crosses the boundary as plain pointers
 // and sizes; C++ exceptions stop here and become status codes.
+#include <time.h>
+
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <exception>
+#include <map>
+#include <mutex>
 #include <new>
 
 #include "solver.hpp"
@@ -26,6 +31,128 @@ int sm_count()
 		cached_dev = dev;
 	}
 	return cached;
+}
+
+// ---- tracing ---------------------------------------------------------------------------------------------
+static double now_ms()
+{
+	timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+bool trace_enabled()
+{
+	static const bool on = [] {
+		const char* e = getenv("FI_B200_TRACE");
+		return e && *e && *e != '0';
+	}();
+	return on;
+}
+static thread_local int t_trace_depth = 0;
+TraceScope::TraceScope(const char* n) : name(n), t0(0)
+{
+	if (trace_enabled()) {
+		t0 = now_ms();
+		++t_trace_depth;
+	}
+}
+TraceScope::~TraceScope()
+{
+	if (trace_enabled()) {
+		--t_trace_depth;
+		fprintf(stderr, "[fi_b200] %*s%s: %.3f ms\n", 2 * t_trace_depth, "", name, now_ms() - t0);
+	}
+}
+
+// ---- device memory cache -----------------------------------------------------------------------------------
+namespace {
+struct Pool
+{
+	std::mutex                        mu;
+	std::multimap<size_t, void*>      free_blocks;  // per device: keyed by (device, bytes) folded into one size_t below
+	size_t                            cached = 0;
+	bool                              dirty  = false;  // blocks were released since the last device synchronisation
+	size_t                            limit  = 0;
+};
+Pool& pool()
+{
+	static Pool p;
+	return p;
+}
+size_t round_block(size_t bytes) { return bytes >= (1u << 20) ? ((bytes + (2u << 20) - 1) >> 21) << 21 : ((bytes + 511) >> 9) << 9; }
+size_t pool_key(size_t rounded)
+{
+	int dev = 0;
+	cudaGetDevice(&dev);
+	return rounded * 16 + static_cast<size_t>(dev & 15);  // sizes are multiples of 512: the low bits are free for the device
+}
+}  // namespace
+
+void* pool_alloc(size_t bytes)
+{
+	Pool&        P = pool();
+	const size_t rb = round_block(bytes), key = pool_key(rb);
+	{
+		std::lock_guard<std::mutex> lock(P.mu);
+		auto it = P.free_blocks.find(key);
+		if (it != P.free_blocks.end()) {
+			void* p = it->second;
+			P.free_blocks.erase(it);
+			P.cached -= rb;
+			if (P.dirty) {  // whoever released it may still have had work in flight on some stream
+				cudaDeviceSynchronize();
+				P.dirty = false;
+			}
+			return p;
+		}
+	}
+	void*       p = nullptr;
+	cudaError_t e = cudaMalloc(&p, rb);
+	if (e != cudaSuccess) {  // give the cache back and retry once
+		cudaGetLastError();
+		pool_trim();
+		e = cudaMalloc(&p, rb);
+	}
+	if (e != cudaSuccess) {
+		throw Error{FI_ERR_CUDA, std::string("cudaMalloc of ") + std::to_string(rb) + " bytes: " + cudaGetErrorString(e)};
+	}
+	return p;
+}
+
+void pool_free(void* p, size_t bytes)
+{
+	if (!p) { return; }
+	Pool&        P = pool();
+	const size_t rb = round_block(bytes);
+	std::lock_guard<std::mutex> lock(P.mu);
+	if (P.limit == 0) {
+		const char* e = getenv("FI_B200_POOL_GB");
+		P.limit       = static_cast<size_t>((e ? atof(e) : 96.0) * 1073741824.0) + 1;
+	}
+	if (P.cached + rb > P.limit) {
+		cudaFree(p);
+		return;
+	}
+	P.free_blocks.emplace(pool_key(rb), p);
+	P.cached += rb;
+	P.dirty = true;
+}
+
+void pool_trim()
+{
+	Pool& P = pool();
+	std::lock_guard<std::mutex> lock(P.mu);
+	for (auto& kv : P.free_blocks) { cudaFree(kv.second); }
+	P.free_blocks.clear();
+	P.cached = 0;
+	P.dirty  = false;
+}
+
+size_t pool_cached_bytes()
+{
+	Pool& P = pool();
+	std::lock_guard<std::mutex> lock(P.mu);
+	return P.cached;
 }
 
 template <typename F>
@@ -204,6 +331,7 @@ void add_points_impl(fi_field* f, float value_weight, int value_kernel, float gr
                      int64_t n, const float* pos, const float* nrm, const float* pw, const float* val, int loc,
                      int64_t* rows_added)
 {
+	TraceScope trace("add_points (stage + canonicalise)");
 	FI_REQUIRE(n >= 0, FI_ERR_INVALID, "negative point count");
 	FI_REQUIRE(value_kernel == 0 || value_kernel == 1, FI_ERR_INVALID, "unknown value kernel");
 	FI_REQUIRE(gradient_kernel >= 0 && gradient_kernel <= 2, FI_ERR_INVALID, "unknown gradient kernel");
@@ -411,7 +539,10 @@ int fi_field_create(int32_t ndim, const int32_t* sizes, fi_field** out)
 
 int fi_field_destroy(fi_field* f)
 {
-	return guarded([&] { delete f; });
+	return guarded([&] {
+		TraceScope trace("fi_field_destroy");
+		delete f;
+	});
 }
 
 int fi_field_add_model(fi_field* f, const fi_weights* w)
@@ -637,6 +768,7 @@ int fi_field_diagonal(fi_field* f, int32_t precision, void* diag) { return copy_
 int fi_field_solve(fi_field* f, const fi_solve_options* opt, const float* guess, float* solution, int32_t loc, fi_solve_stats* stats)
 {
 	return guarded([&] {
+		TraceScope trace("fi_field_solve");
 		FI_REQUIRE(f && solution, FI_ERR_INVALID, "null argument");
 		fi_solve_options o;
 		if (opt) { o = *opt; } else { fi_solve_options_default(&o); }
@@ -834,6 +966,13 @@ int fi_slab_sdf_solve(fi_comm* c, const int32_t* sizes, const fi_weights* w, int
 		slab_sdf_solve(c, sizes, *w, num_points, positions, normals, point_weights, loc, o, guess_own, solution_own, solution_loc, stats);
 	});
 }
+
+int fi_trim_memory(void)
+{
+	return guarded([&] { pool_trim(); });
+}
+
+int64_t fi_cached_bytes(void) { return static_cast<int64_t>(pool_cached_bytes()); }
 
 int64_t fi_kernel_launches(void) { return g_launches; }
 void    fi_kernel_launches_reset(void) { g_launches = 0; }

@@ -581,11 +581,53 @@ __global__ void shift_ptr_kernel(uint64_t* ptr, int64_t n, uint64_t add)
 }
 
 // ---- apply: q += P p ------------------------------------------------------------------------------------------
+// Decodes the sorted cell keys once per operator build: corner-0 index and which corners exist / are owned.
+template <int D>
+__global__ void cell_nodes_kernel(Geom g, int64_t nocc, const uint64_t* __restrict__ cell_key, int64_t* __restrict__ cell_base,
+                                  uint32_t* __restrict__ cell_mask)
+{
+	constexpr int C = 1 << D;
+	const int64_t cell = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (cell >= nocc) { return; }
+	uint64_t key = cell_key[cell];
+	int      base[D];
+	int64_t  node = g.shift;
+#pragma unroll
+	for (int d = 0; d < D; ++d) {
+		const uint64_t ext = static_cast<uint64_t>(g.size[d] + 1);
+		base[d] = static_cast<int>(key % ext) - 1;
+		key /= ext;
+		node += g.stride[d] * base[d];
+	}
+	uint32_t mask = 0;
+#pragma unroll
+	for (int c = 0; c < C; ++c) {
+		bool ok = true;
+#pragma unroll
+		for (int d = 0; d < D; ++d) {
+			const int x = base[d] + ((c >> d) & 1);
+			ok          = ok && (0 <= x) && (x < g.size[d]);
+		}
+		bool own = ok;
+		if (D == 3 && g.sharded()) {  // rows of nodes another slab owns are that slab's business
+			const int zl = base[D - 1] + ((c >> (D - 1)) & 1) - g.zoff;
+			own          = ok && zl >= g.zown0 && zl < g.zown1;
+		}
+		mask |= (ok ? 1u : 0u) << c;
+		mask |= (own ? 1u : 0u) << (8 + c);
+	}
+	cell_base[cell] = node;
+	cell_mask[cell] = mask;
+}
+
+// q += P p over the occupied cells: one thread per cell reads its 2^D corner values of p, multiplies by the
+// symmetric block (upper triangle, [tri][cell] so that a warp reads consecutive cells of one entry) and adds the
+// 2^D results to q with atomics (neighbouring cells share corners).
 template <typename T, int D>
-__global__ void __launch_bounds__(kThreads) apply_blocks_kernel(Geom g, int64_t nocc, const uint64_t* __restrict__ cell_key,
-                                                                const T* __restrict__ blocks, const T* __restrict__ p,
-                                                                T* __restrict__ q, double* partial, unsigned* ticket, double* dot_accum,
-                                                                const int* done)
+__global__ void __launch_bounds__(kThreads, 3) apply_blocks_kernel(Geom g, int64_t nocc, const int64_t* __restrict__ cell_base,
+                                                                const uint32_t* __restrict__ cell_mask, const T* __restrict__ blocks,
+                                                                const T* __restrict__ p, T* __restrict__ q, double* partial,
+                                                                unsigned* ticket, double* dot_accum, const int* done)
 {
 	constexpr int C = 1 << D;
 	__shared__ double red[32];
@@ -593,34 +635,20 @@ __global__ void __launch_bounds__(kThreads) apply_blocks_kernel(Geom g, int64_t 
 	const int64_t cell = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
 	double        mine[1] = {0.0};
 	if (cell < nocc) {
-		uint64_t key = cell_key[cell];
-		int64_t  node[C];
-		bool     ok[C];    // the corner is a lattice node: p is read there
-		bool     own[C];   // ... whose row this process computes (always, unless the lattice is slab-sharded)
-		int      base[D];
+		// every load of this thread is issued before the first use: the kernel is latency-bound otherwise
+		constexpr int NT = C * (C + 1) / 2;
+		T             blk[NT];
 #pragma unroll
-		for (int d = 0; d < D; ++d) {
-			const uint64_t ext = static_cast<uint64_t>(g.size[d] + 1);
-			base[d] = static_cast<int>(key % ext) - 1;
-			key /= ext;
-		}
+		for (int t = 0; t < NT; ++t) { blk[t] = __ldcs(&blocks[static_cast<size_t>(t) * nocc + cell]); }
+		const int64_t  base = cell_base[cell];
+		const uint32_t mask = cell_mask[cell];
 		T pc[C], out[C];
 #pragma unroll
 		for (int c = 0; c < C; ++c) {
-			ok[c]   = true;
-			node[c] = g.shift;
+			int64_t off = 0;
 #pragma unroll
-			for (int d = 0; d < D; ++d) {
-				const int x = base[d] + ((c >> d) & 1);
-				ok[c]       = ok[c] && (0 <= x) && (x < g.size[d]);
-				node[c] += g.stride[d] * x;
-			}
-			own[c] = ok[c];
-			if (D == 3 && g.sharded()) {  // rows of nodes another slab owns are that slab's business
-				const int zl = base[D - 1] + ((c >> (D - 1)) & 1) - g.zoff;
-				own[c]       = ok[c] && zl >= g.zown0 && zl < g.zown1;
-			}
-			pc[c]  = ok[c] ? p[node[c]] : T(0);
+			for (int d = 0; d < D; ++d) { off += ((c >> d) & 1) ? g.stride[d] : 0; }
+			pc[c]  = ((mask >> c) & 1u) ? p[base + off] : T(0);
 			out[c] = 0;
 		}
 		int tri = 0;
@@ -628,19 +656,24 @@ __global__ void __launch_bounds__(kThreads) apply_blocks_kernel(Geom g, int64_t 
 		for (int ci = 0; ci < C; ++ci) {
 #pragma unroll
 			for (int cj = ci; cj < C; ++cj) {
-				const T b = blocks[static_cast<size_t>(tri) * nocc + cell];
+				const T b = blk[tri];
 				out[ci] += b * pc[cj];
 				if (cj != ci) { out[cj] += b * pc[ci]; }
 				++tri;
 			}
 		}
+		T dot = 0;
 #pragma unroll
 		for (int c = 0; c < C; ++c) {
-			if (own[c]) {
-				atomic_add(&q[node[c]], out[c]);
-				mine[0] += static_cast<double>(pc[c]) * static_cast<double>(out[c]);
+			if ((mask >> (8 + c)) & 1u) {
+				int64_t off = 0;
+#pragma unroll
+				for (int d = 0; d < D; ++d) { off += ((c >> d) & 1) ? g.stride[d] : 0; }
+				atomic_add(&q[base + off], out[c]);
+				dot += pc[c] * out[c];
 			}
 		}
+		mine[0] = static_cast<double>(dot);
 	}
 	if (dot_accum) {
 		mine[0] = block_sum(mine[0], red);
@@ -788,6 +821,13 @@ void build_data_term(const Geom& g, const PointStore& pts, const HostRows& user,
 			out.blocks.zero(s);
 			FI_LAUNCH(slots_kernel, div_up(V, kThreads), kThreads, 0, s, keys.data(), flags.data(), scan.data(), V, slot.data(),
 			          out.cell_key.data());
+			out.cell_base.resize(out.nocc);
+			out.cell_mask.resize(out.nocc);
+			by_dim(g.ndim, [&](auto dim) {
+				auto kern = cell_nodes_kernel<decltype(dim)::value>;
+				FI_LAUNCH(kern, div_up(out.nocc, kThreads), kThreads, 0, s, g, out.nocc, out.cell_key.data(), out.cell_base.data(),
+				          out.cell_mask.data());
+			});
 			// 3. warp-segmented scatter
 			const int grid = div_up(V, kThreads);
 			by_dim(g.ndim, [&](auto dim) {
@@ -851,7 +891,8 @@ void apply_data_term(const Geom& g, const DataTerm<T>& dt, const T* p, T* q, dou
 	if (gb > 0) {
 		by_dim(g.ndim, [&](auto dim) {
 			auto kern = apply_blocks_kernel<T, decltype(dim)::value>;
-			FI_LAUNCH(kern, gb, kThreads, 0, s, g, dt.nocc, dt.cell_key.data(), dt.blocks.data(), p, q, partial, ticket, d_dot_accum, d_done);
+			FI_LAUNCH(kern, gb, kThreads, 0, s, g, dt.nocc, dt.cell_base.data(), dt.cell_mask.data(), dt.blocks.data(), p, q, partial, ticket,
+				          d_dot_accum, d_done);
 		});
 	}
 	if (gr > 0) {

@@ -50,7 +50,26 @@ inline void count_launch(int n = 1) { g_launches += n; }
 		FI_CUDA(cudaGetLastError());                                      \
 	} while (0)
 
+// ---- tracing (the reference logs the wall time of each phase with loguru scopes, sparse_linear.cpp:62-198) ----
+// FI_B200_TRACE=1 prints one line per phase to stderr.
+bool trace_enabled();
+struct TraceScope
+{
+	const char* name;
+	double      t0;
+	explicit TraceScope(const char* n);
+	~TraceScope();
+};
+
 // ---- device memory ----------------------------------------------------------------------------------
+// Lattice-sized buffers come and go with every field and every solve; cudaMalloc / cudaFree of half-gigabyte
+// blocks costs milliseconds each, so freed blocks are kept in a per-process cache (exact-size reuse) and handed
+// out again.  A block is reused only after the device has been synchronised since it was released.
+void*  pool_alloc(size_t bytes);
+void   pool_free(void* p, size_t bytes);
+void   pool_trim();             // return every cached block to the driver
+size_t pool_cached_bytes();
+
 template <typename T>
 class DevBuf
 {
@@ -75,7 +94,7 @@ public:
 	}
 	void release()
 	{
-		if (p_) { cudaFree(p_); }
+		if (p_) { pool_free(p_, cap_ * sizeof(T)); }
 		p_ = nullptr;
 		n_ = cap_ = 0;
 	}
@@ -84,7 +103,7 @@ public:
 	{
 		if (n > cap_) {
 			release();
-			FI_CUDA(cudaMalloc(&p_, std::max<size_t>(n, 1) * sizeof(T)));
+			p_   = static_cast<T*>(pool_alloc(std::max<size_t>(n, 1) * sizeof(T)));
 			cap_ = std::max<size_t>(n, 1);
 		}
 		n_ = n;
@@ -94,11 +113,10 @@ public:
 	{
 		if (n > cap_) {
 			size_t ncap = std::max<size_t>(n, cap_ * 2);
-			T*     q    = nullptr;
-			FI_CUDA(cudaMalloc(&q, ncap * sizeof(T)));
+			T*     q    = static_cast<T*>(pool_alloc(ncap * sizeof(T)));
 			if (n_) { FI_CUDA(cudaMemcpyAsync(q, p_, n_ * sizeof(T), cudaMemcpyDeviceToDevice, s)); }
 			FI_CUDA(cudaStreamSynchronize(s));
-			if (p_) { cudaFree(p_); }
+			if (p_) { pool_free(p_, cap_ * sizeof(T)); }
 			p_   = q;
 			cap_ = ncap;
 		}

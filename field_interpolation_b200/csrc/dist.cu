@@ -17,7 +17,9 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <mutex>
+#include <vector>
 
 #include "solver.hpp"
 
@@ -32,6 +34,7 @@ struct Nccl
 	ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int)                                      = nullptr;
 	ncclResult_t (*CommDestroy)(ncclComm_t)                                                                = nullptr;
 	ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t)        = nullptr;
 	ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t)               = nullptr;
 	ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t)                     = nullptr;
 	ncclResult_t (*GroupStart)()                                                                           = nullptr;
@@ -62,6 +65,7 @@ Nccl& nccl()
 		n.CommInitRank   = reinterpret_cast<decltype(n.CommInitRank)>(sym("ncclCommInitRank"));
 		n.CommDestroy    = reinterpret_cast<decltype(n.CommDestroy)>(sym("ncclCommDestroy"));
 		n.AllReduce      = reinterpret_cast<decltype(n.AllReduce)>(sym("ncclAllReduce"));
+		n.AllGather      = reinterpret_cast<decltype(n.AllGather)>(sym("ncclAllGather"));
 		n.Send           = reinterpret_cast<decltype(n.Send)>(sym("ncclSend"));
 		n.Recv           = reinterpret_cast<decltype(n.Recv)>(sym("ncclRecv"));
 		n.GroupStart     = reinterpret_cast<decltype(n.GroupStart)>(sym("ncclGroupStart"));
@@ -96,8 +100,29 @@ struct fi_comm
 	ncclComm_t comm  = nullptr;
 	int        rank  = 0;
 	int        world = 1;
+	// peer-memory path (CUDA IPC over NVLink): mailboxes for the scalar sums, one shared lattice vector for r
+	bool               p2p = false;
+	fi::PeerLink       link;
+	void*              shared       = nullptr;  // this rank's peer-visible vector
+	size_t             shared_bytes = 0;
+	void*              shared_lo    = nullptr;  // rank - 1's vector, mapped here
+	void*              shared_hi    = nullptr;  // rank + 1's vector, mapped here
+	unsigned long long seq          = 0;
+
+	void close_shared()
+	{
+		if (shared_lo) { cudaIpcCloseMemHandle(shared_lo); }
+		if (shared_hi) { cudaIpcCloseMemHandle(shared_hi); }
+		shared_lo = shared_hi = nullptr;
+	}
 	~fi_comm()
 	{
+		close_shared();
+		if (shared) { cudaFree(shared); }
+		for (int j = 0; j < world && j < fi::kMaxPeers; ++j) {
+			if (j != rank && link.peer[j]) { cudaIpcCloseMemHandle(link.peer[j]); }
+		}
+		if (link.local) { cudaFree(link.local); }
 		if (comm) { fi::nccl().CommDestroy(comm); }
 	}
 };
@@ -106,13 +131,123 @@ namespace fi {
 
 namespace {
 
-// Halo exchange + scalar all-reduce of one slab over NCCL.
+// Gathers one CUDA IPC handle per rank (collective, through the NCCL communicator).
+std::vector<cudaIpcMemHandle_t> gather_handles(fi_comm* c, void* local_ptr, cudaStream_t s)
+{
+	cudaIpcMemHandle_t mine;
+	std::memset(&mine, 0, sizeof(mine));
+	if (local_ptr) { FI_CUDA(cudaIpcGetMemHandle(&mine, local_ptr)); }
+	DevBuf<unsigned char> send(sizeof(mine)), recv(sizeof(mine) * c->world);
+	FI_CUDA(cudaMemcpyAsync(send.data(), &mine, sizeof(mine), cudaMemcpyHostToDevice, s));
+	FI_NCCL(nccl().AllGather(send.data(), recv.data(), sizeof(mine), ncclChar, c->comm, s));
+	std::vector<cudaIpcMemHandle_t> all(c->world);
+	FI_CUDA(cudaMemcpyAsync(all.data(), recv.data(), sizeof(mine) * c->world, cudaMemcpyDeviceToHost, s));
+	FI_CUDA(cudaStreamSynchronize(s));
+	return all;
+}
+
+// All ranks agree (min over ranks) on a yes / no.
+bool all_agree(fi_comm* c, bool mine, cudaStream_t s)
+{
+	DevBuf<double> v(1);
+	const double   h = mine ? 1.0 : 0.0;
+	FI_CUDA(cudaMemcpyAsync(v.data(), &h, sizeof(h), cudaMemcpyHostToDevice, s));
+	FI_NCCL(nccl().AllReduce(v.data(), v.data(), 1, ncclDouble, ncclMin, c->comm, s));
+	double out = 0;
+	FI_CUDA(cudaMemcpyAsync(&out, v.data(), sizeof(out), cudaMemcpyDeviceToHost, s));
+	FI_CUDA(cudaStreamSynchronize(s));
+	return out > 0.5;
+}
+
+// Mailboxes: allocate, exchange IPC handles, map every peer's.  Leaves c->p2p false when any rank cannot.
+void setup_peer_link(fi_comm* c)
+{
+	const char* env = getenv("FI_B200_P2P");
+	bool        ok  = !(env && *env == '0') && c->world <= kMaxPeers && c->world > 1;
+	cudaStream_t s = nullptr;
+	FI_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+	try {
+		void* mb = nullptr;
+		if (ok && cudaMalloc(&mb, sizeof(Mailbox)) != cudaSuccess) {
+			cudaGetLastError();
+			ok = false;
+			mb = nullptr;
+		}
+		if (mb) { FI_CUDA(cudaMemset(mb, 0, sizeof(Mailbox))); }
+		FI_CUDA(cudaDeviceSynchronize());
+		c->link.rank  = c->rank;
+		c->link.world = c->world;
+		c->link.local = static_cast<Mailbox*>(mb);
+		const auto handles = gather_handles(c, mb, s);
+		for (int j = 0; ok && j < c->world; ++j) {
+			if (j == c->rank) {
+				c->link.peer[j] = c->link.local;
+				continue;
+			}
+			void* q = nullptr;
+			if (cudaIpcOpenMemHandle(&q, handles[j], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+				cudaGetLastError();
+				ok = false;
+				break;
+			}
+			c->link.peer[j] = static_cast<Mailbox*>(q);
+		}
+		c->p2p = all_agree(c, ok, s);
+	} catch (...) {
+		cudaStreamDestroy(s);
+		throw;
+	}
+	cudaStreamDestroy(s);
+}
+
+// Halo exchange + scalar all-reduce of one slab: NCCL for the one-off steps, peer memory inside the iteration.
 struct SlabHooks final : DistHooks
 {
 	fi_comm* c;
 	Geom     g;
 	int      halo;
 	SlabHooks(fi_comm* comm, const Geom& geom, int h) : c(comm), g(geom), halo(h) {}
+
+	const PeerLink* link() override { return c->p2p ? &c->link : nullptr; }
+	unsigned long long next_seq() override { return ++c->seq; }
+	int64_t peer_own_cells(int peer) override
+	{
+		int z0 = 0, z1 = 0;
+		slab_range(g.size[2], c->world, peer, &z0, &z1);
+		return static_cast<int64_t>(z1 - z0) * g.stride[2];
+	}
+
+	void* shared_vector(size_t bytes, void** lo, void** hi, cudaStream_t s) override
+	{
+		// grow collectively: every rank runs the same sequence of solves, but slabs differ by a plane, so the decision
+		// is taken on the largest request
+		DevBuf<double> need(1);
+		const double   mine = static_cast<double>(bytes);
+		FI_CUDA(cudaMemcpyAsync(need.data(), &mine, sizeof(mine), cudaMemcpyHostToDevice, s));
+		FI_NCCL(nccl().AllReduce(need.data(), need.data(), 1, ncclDouble, ncclMax, c->comm, s));
+		double most = 0;
+		FI_CUDA(cudaMemcpyAsync(&most, need.data(), sizeof(most), cudaMemcpyDeviceToHost, s));
+		FI_CUDA(cudaStreamSynchronize(s));
+		const size_t want = static_cast<size_t>(most);
+		if (want > c->shared_bytes) {
+			FI_CUDA(cudaDeviceSynchronize());
+			c->close_shared();
+			(void)gather_handles(c, nullptr, s);  // barrier: nobody maps the old vectors any more
+			if (c->shared) { FI_CUDA(cudaFree(c->shared)); }
+			c->shared       = nullptr;
+			c->shared_bytes = 0;
+			const size_t cap = want + want / 8;
+			FI_CUDA(cudaMalloc(&c->shared, cap));
+			c->shared_bytes = cap;
+			const auto handles = gather_handles(c, c->shared, s);
+			if (c->rank > 0) { FI_CUDA(cudaIpcOpenMemHandle(&c->shared_lo, handles[c->rank - 1], cudaIpcMemLazyEnablePeerAccess)); }
+			if (c->rank + 1 < c->world) { FI_CUDA(cudaIpcOpenMemHandle(&c->shared_hi, handles[c->rank + 1], cudaIpcMemLazyEnablePeerAccess)); }
+		}
+		FI_CUDA(cudaMemsetAsync(c->shared, 0, bytes, s));
+		*lo = c->shared_lo;
+		*hi = c->shared_hi;
+		return c->shared;
+	}
 
 	void allreduce(double* d_ptr, int count, cudaStream_t s) override
 	{
@@ -193,6 +328,7 @@ void slab_sdf_solve(fi_comm* c, const int32_t* sizes, const fi_weights& w, int64
                     const float* point_weights, int loc, const fi_solve_options& o, const float* guess_own, float* solution_own,
                     int sol_loc, fi_solve_stats* st)
 {
+	TraceScope trace("fi_slab_sdf_solve");
 	FI_REQUIRE(c != nullptr && c->comm != nullptr, FI_ERR_INVALID, "communicator is null");
 	FI_REQUIRE(o.precision == FI_F32 || o.precision == FI_F64, FI_ERR_UNSUPPORTED, "slab solves run in FI_F32 or FI_F64");
 	FI_REQUIRE(w.gradient_smoothness == 0.0f, FI_ERR_UNSUPPORTED, "slab solves need the star-shaped operator (gradient_smoothness = 0)");
@@ -281,6 +417,7 @@ fi_comm* comm_create(int rank, int world, const void* id)
 	c->rank  = rank;
 	c->world = world;
 	FI_NCCL(nccl().CommInitRank(&c->comm, world, u, rank));
+	setup_peer_link(c.get());
 	return c.release();
 }
 

@@ -108,6 +108,8 @@ struct DataTerm
 {
 	int64_t            nocc = 0;
 	DevBuf<uint64_t>   cell_key;  // per occupied cell: sum (base_d + 1) * kstride_d, sorted ascending
+	DevBuf<int64_t>    cell_base; // local index of the cell's corner 0 (may lie outside the lattice: see cell_mask)
+	DevBuf<uint32_t>   cell_mask; // bits 0..7: corner is a lattice node; bits 8..15: ... whose row this process owns
 	DevBuf<T>          blocks;    // [tri(2^D)][nocc]
 	int64_t            nrows = 0; // generic rows (derived + caller-appended)
 	DevBuf<uint64_t>   row_ptr;   // nrows + 1

@@ -111,6 +111,98 @@ __global__ void __launch_bounds__(kThreads) pcg_init_kernel(int64_t n, const T* 
 	});
 }
 
+// ---- peer-memory all-reduce (see solver.hpp) ----------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
+{
+	unsigned long long v;
+	asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
+{
+	asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// One thread: stores this rank's `count` (<= 2) partial sums and then the sequence number into every rank's mailbox.
+__device__ __forceinline__ void peer_publish(const PeerLink& L, int which, int par, unsigned long long seq, const double* v, int count)
+{
+	for (int j = 0; j < L.world; ++j) {
+		PeerSlot* sl = &L.peer[j]->slot[which][par][L.rank];
+		for (int k = 0; k < count; ++k) { reinterpret_cast<volatile double*>(sl->v)[k] = v[k]; }
+	}
+	__threadfence_system();
+	for (int j = 0; j < L.world; ++j) { st_release_sys(&L.peer[j]->slot[which][par][L.rank].seq, seq); }
+}
+
+// One thread: waits until every rank's slot carries `seq`, then adds the values in rank order.  Gives up after
+// ~10 s (a peer died): flags the mailbox and returns false.
+__device__ __forceinline__ bool peer_collect(const PeerLink& L, int which, int par, unsigned long long seq, double* out, int count)
+{
+	for (int k = 0; k < count; ++k) { out[k] = 0.0; }
+	const long long t0 = clock64();
+	for (int j = 0; j < L.world; ++j) {
+		const PeerSlot* sl = &L.local->slot[which][par][j];
+		while (ld_acquire_sys(&sl->seq) != seq) {
+			if (clock64() - t0 > 20000000000ll) {
+				L.local->error = 1;
+				return false;
+			}
+		}
+		for (int k = 0; k < count; ++k) { out[k] += reinterpret_cast<const volatile double*>(sl->v)[k]; }
+	}
+	return true;
+}
+
+// Sequence numbers of iteration `iters` of the solve with epoch number `base`: 2 * iters + 1 for p.Ap, + 2 for
+// (r.Mr, r.r).  Derived from the device-side iteration counter so that the kernels can sit in a CUDA graph.  Once
+// the solve is done the counter stops and the leftover iterations of a round re-publish the same numbers, which
+// every waiting peer accepts at once (their values are ignored: all ranks are done together).
+__device__ __forceinline__ unsigned long long seq_of(unsigned long long base, const PcgState* st, int which)
+{
+	return base + 2ull * static_cast<unsigned long long>(st->iters) + 1ull + static_cast<unsigned long long>(which);
+}
+
+__device__ __forceinline__ unsigned long long global_ns()
+{
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+
+__global__ void peer_publish_kernel(PeerLink L, int which, int par, unsigned long long base, const PcgState* st, const double* src, int count,
+                                    const int* done)
+{
+	if (threadIdx.x != 0 || blockIdx.x != 0) { return; }
+	const unsigned long long seq = seq_of(base, st, which);
+	double v[2] = {0.0, 0.0};
+	// a finished solve still publishes (zeros): the peers' kernels of this round are already waiting
+	if (!(done && *done)) {
+		for (int k = 0; k < count; ++k) { v[k] = src[k]; }
+		L.local->stamp[0][st->iters & 511] = global_ns();
+	}
+	peer_publish(L, which, par, seq, v, count);
+}
+
+// Ends an iteration on the peer-memory path: sums (r.Mr, r.r) over ranks and updates the shared CG state.
+__global__ void pcg_update_finish_peer_kernel(PcgState* st, int par, PeerLink L, unsigned long long base)
+{
+	if (threadIdx.x != 0 || blockIdx.x != 0) { return; }
+	const unsigned long long seq = seq_of(base, st, 1);
+	double tot[2];
+	const bool ok = peer_collect(L, 1, par, seq, tot, 2);
+	if (st->done) { return; }
+	if (!ok) {
+		st->breakdown = 2;
+		st->done      = 1;
+		return;
+	}
+	L.local->stamp[2][st->iters & 511] = global_ns();
+	st->rho[par ^ 1] = tot[0];
+	st->rr           = tot[1];
+	st->iters += 1;
+	if (tot[1] <= st->tol2bb || st->iters >= st->max_iters || !(tot[0] > 0.0)) { st->done = 1; }
+}
+
 __global__ void pcg_init_finish_kernel(PcgState* st, double tol, long long max_iters)
 {
 	const double rho = st->part[0], rr = st->part[1], bb = st->part[2];
@@ -197,6 +289,82 @@ __global__ void __launch_bounds__(kThreads) pcg_update_kernel(int64_t n, T* __re
 		st->rr           = tot[1];
 		st->iters += 1;
 		if (tot[1] <= st->tol2bb || st->iters >= st->max_iters || !(tot[0] > 0.0)) { st->done = 1; }
+	});
+}
+
+// The update kernel of a slab on the peer-memory path: waits for the all-reduced p.Ap in its mailbox, updates x
+// and r, stores the boundary planes of the new r straight into the neighbours' halo planes (NVLink peer stores),
+// and the last block publishes this slab's (r.Mr, r.r) to every rank.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) pcg_update_peer_kernel(int64_t n, T* __restrict__ x, T* __restrict__ r,
+                                                                   const T* __restrict__ p, const T* __restrict__ q,
+                                                                   const T* __restrict__ minv, PcgState* st, int par, double* partial,
+                                                                   unsigned* ticket, PeerLink L, HaloPush<T> push, unsigned long long base)
+{
+	__shared__ double red[32];
+	__shared__ double s_pq;
+	__shared__ int    s_ok;
+	const bool was_done = st->done != 0;
+	const unsigned long long seq_pq = seq_of(base, st, 0), seq_rr = seq_of(base, st, 1);
+	if (threadIdx.x == 0) {
+		double pq = 0.0;
+		s_ok      = peer_collect(L, 0, par, seq_pq, &pq, 1) ? 1 : 0;
+		s_pq      = pq;
+		if (blockIdx.x == 0 && !was_done) { L.local->stamp[1][st->iters & 511] = global_ns(); }
+	}
+	__syncthreads();
+	const double pq    = s_pq;
+	const bool   bad   = !s_ok || !(pq > 0.0);  // lost peer, or breakdown (singular direction / NaN): keep the last iterate
+	double       acc[2] = {0, 0};
+	if (!was_done && !bad) {
+		const T alpha = static_cast<T>(st->rho[par] / pq);
+		using P       = typename Pack<T>::type;
+		constexpr int V = Pack<T>::V;
+		const int64_t hi_from = n - push.count;
+		for_each_pack<T>(n, [&](int64_t k, bool packed) {
+			if (packed) {
+				P        xv = reinterpret_cast<P*>(x)[k], rv = reinterpret_cast<P*>(r)[k];
+				const P  pv = reinterpret_cast<const P*>(p)[k], qv = reinterpret_cast<const P*>(q)[k];
+				const P  mv = reinterpret_cast<const P*>(minv)[k];
+				T*       xa = reinterpret_cast<T*>(&xv);
+				T*       ra = reinterpret_cast<T*>(&rv);
+				const T* pa = reinterpret_cast<const T*>(&pv);
+				const T* qa = reinterpret_cast<const T*>(&qv);
+				const T* ma = reinterpret_cast<const T*>(&mv);
+#pragma unroll
+				for (int j = 0; j < V; ++j) {
+					xa[j] += alpha * pa[j];
+					ra[j] -= alpha * qa[j];
+					const double rd = static_cast<double>(ra[j]);
+					acc[0] += rd * static_cast<double>(ma[j] * ra[j]);
+					acc[1] += rd * rd;
+				}
+				reinterpret_cast<P*>(x)[k] = xv;
+				reinterpret_cast<P*>(r)[k] = rv;
+				const int64_t i = k * V;  // halo extents are whole planes of a lattice whose x size is a multiple of V
+				if (push.lo && i < push.count) { *reinterpret_cast<P*>(push.lo + i) = rv; }
+				if (push.hi && i >= hi_from) { *reinterpret_cast<P*>(push.hi + (i - hi_from)) = rv; }
+			} else {
+				x[k] += alpha * p[k];
+				const T ri = r[k] - alpha * q[k];
+				r[k]       = ri;
+				acc[0] += static_cast<double>(ri) * static_cast<double>(minv[k] * ri);
+				acc[1] += static_cast<double>(ri) * static_cast<double>(ri);
+				if (push.lo && k < push.count) { push.lo[k] = ri; }
+				if (push.hi && k >= hi_from) { push.hi[k - hi_from] = ri; }
+			}
+		});
+	}
+	acc[0] = block_sum(acc[0], red);
+	acc[1] = block_sum(acc[1], red);
+	// peer stores of every thread of this block are ordered before the ticket below (bar.sync above, fence here)
+	if (threadIdx.x == 0) { __threadfence_system(); }
+	grid_sum<2>(acc, partial, ticket, red, [&](const double(&tot)[2]) {
+		if (!was_done && bad) {
+			st->breakdown = s_ok ? 1 : 2;
+			st->done      = 1;
+		}
+		peer_publish(L, 1, par, seq_rr, tot, 2);
 	});
 }
 
@@ -315,6 +483,7 @@ template <typename T>
 std::unique_ptr<Operator<T>> build_operator(const Geom& g, const ModelAccum& m, const PointStore& pts, const HostRows& rows,
                                             cudaStream_t s)
 {
+	TraceScope  trace("build_operator (data term, diagonal, preconditioner)");
 	cudaEvent_t e0, e1;
 	FI_CUDA(cudaEventCreate(&e0));
 	FI_CUDA(cudaEventCreate(&e1));
@@ -368,6 +537,7 @@ template <typename T>
 PcgResult pcg_solve(Operator<T>& op, const T* b, T* x, double tol, long long max_iter, int check_every, bool want_true_residual,
                     cudaStream_t s)
 {
+	TraceScope trace("pcg_solve");
 	ensure_work(op, s);
 	PcgWork<T>&   w = op.work;
 	// vector kernels run over the planes this process owns (everything, unless the lattice is slab-sharded)
@@ -387,16 +557,29 @@ PcgResult pcg_solve(Operator<T>& op, const T* b, T* x, double tol, long long max
 	FI_CUDA(cudaEventRecord(e0, s));
 
 	const int grid = vec_grid(n);
+	// r lives in peer-visible memory when the neighbours push their boundary planes into it
+	const PeerLink* link = dist ? dist->link() : nullptr;
+	T*              r_vec = w.r.data();
+	HaloPush<T>     push;
+	if (link) {
+		void *lo = nullptr, *hi = nullptr;
+		r_vec = static_cast<T*>(dist->shared_vector(static_cast<size_t>(op.g.N) * sizeof(T), &lo, &hi, s));
+		const int64_t plane = op.g.stride[2], halo = op.g.zown0;
+		push.count = halo * plane;
+		// rank - 1 stores our first owned planes into its upper halo (behind its owned planes); rank + 1 into its lower halo (plane 0)
+		if (lo) { push.lo = static_cast<T*>(lo) + halo * plane + dist->peer_own_cells(link->rank - 1); }
+		if (hi) { push.hi = static_cast<T*>(hi); }
+	}
 	if (dist) { dist->exchange_halo(x, sizeof(T), s); }
 	op.apply(x, w.q.data(), nullptr, nullptr, s);
 	{
 		auto kern = pcg_init_kernel<T>;
-		FI_LAUNCH(kern, grid, kThreads, 0, s, n, rhs + off, w.q.data() + off, op.minv.data() + off, w.r.data() + off, w.p.data() + off,
+		FI_LAUNCH(kern, grid, kThreads, 0, s, n, rhs + off, w.q.data() + off, op.minv.data() + off, r_vec + off, w.p.data() + off,
 		          w.state.data(), tol, max_iter, w.partial.data(), w.ticket.data(), dist ? 1 : 0);
 		if (dist) {
 			dist->allreduce(w.state.data()->part, 3, s);
 			FI_LAUNCH(pcg_init_finish_kernel, 1, 1, 0, s, w.state.data(), tol, max_iter);
-			dist->exchange_halo(w.r.data(), sizeof(T), s);
+			dist->exchange_halo(r_vec, sizeof(T), s);
 		}
 	}
 	PcgState h;
@@ -411,28 +594,34 @@ PcgResult pcg_solve(Operator<T>& op, const T* b, T* x, double tol, long long max
 	} else if (!h.done) {
 		const int* d_done = &w.state.data()->done;
 		double*    d_pq   = &w.state.data()->pq;
-		// one graph = check_every iterations
-		cudaGraph_t     graph = nullptr;
-		cudaGraphExec_t exec  = nullptr;
-		const int64_t   before = g_launches;
-		FI_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-		try {
-			T* pp[2] = {w.p.data(), w.p2.data()};
+		// check_every iterations per convergence poll
+		T*   pp[2] = {w.p.data(), w.p2.data()};
+		// every solve gets its own block of mailbox sequence numbers (all ranks count solves alike)
+		const unsigned long long seq_base = link ? (dist->next_seq() << 40) : 0ull;
+		auto enqueue_round = [&] {
 			for (int it = 0; it < check_every; ++it) {
 				const int par = it & 1;
 				// fused form: direction update folded into the stencil's load stage (p ping-pongs between two buffers)
-				const bool fused = stencil_fused_step<T>(op.use_fast, op.g, op.tabs, w.r.data(), op.minv.data(), pp[par], pp[par ^ 1], w.q.data(),
+				const bool fused = stencil_fused_step<T>(op.use_fast, op.g, op.tabs, r_vec, op.minv.data(), pp[par], pp[par ^ 1], w.q.data(),
 				                                         w.state.data(), par, d_pq, op.partial.data(), op.ticket.data(), d_done, s);
-				if (fused) {
+				if (fused && link) {
+					// peer-memory path: no NCCL inside the iteration
+					apply_data_term<T>(op.g, op.data, pp[par ^ 1], w.q.data(), d_pq, d_done, s);
+					FI_LAUNCH(peer_publish_kernel, 1, 32, 0, s, *link, 0, par, seq_base, w.state.data(), d_pq, 1, d_done);
+					auto ku = pcg_update_peer_kernel<T>;
+					FI_LAUNCH(ku, grid, kThreads, 0, s, n, x + off, r_vec + off, pp[par ^ 1] + off, w.q.data() + off, op.minv.data() + off,
+					          w.state.data(), par, w.partial.data(), w.ticket.data(), *link, push, seq_base);
+					FI_LAUNCH(pcg_update_finish_peer_kernel, 1, 32, 0, s, w.state.data(), par, *link, seq_base);
+				} else if (fused) {
 					apply_data_term<T>(op.g, op.data, pp[par ^ 1], w.q.data(), d_pq, d_done, s);
 					if (dist) { dist->allreduce(d_pq, 1, s); }
 					auto ku = pcg_update_kernel<T>;
-					FI_LAUNCH(ku, grid, kThreads, 0, s, n, x + off, w.r.data() + off, pp[par ^ 1] + off, w.q.data() + off, op.minv.data() + off,
+					FI_LAUNCH(ku, grid, kThreads, 0, s, n, x + off, r_vec + off, pp[par ^ 1] + off, w.q.data() + off, op.minv.data() + off,
 					          w.state.data(), par, w.partial.data(), w.ticket.data(), dist ? 1 : 0);
 					if (dist) {
 						dist->allreduce(w.state.data()->part, 2, s);
 						FI_LAUNCH(pcg_update_finish_kernel, 1, 1, 0, s, w.state.data(), par);
-						dist->exchange_halo(w.r.data(), sizeof(T), s);
+						dist->exchange_halo(r_vec, sizeof(T), s);
 					}
 				} else {
 					FI_REQUIRE(dist == nullptr, FI_ERR_UNSUPPORTED, "a slab-sharded solve needs the fused 3D stencil kernel");
@@ -444,35 +633,75 @@ PcgResult pcg_solve(Operator<T>& op, const T* b, T* x, double tol, long long max
 					FI_LAUNCH(kd, grid, kThreads, 0, s, n, w.r.data(), op.minv.data(), w.p.data(), w.state.data(), par);
 				}
 			}
-		} catch (...) {
-			cudaStreamEndCapture(s, &graph);
-			if (graph) { cudaGraphDestroy(graph); }
-			throw;
-		}
-		FI_CUDA(cudaStreamEndCapture(s, &graph));
-		const int64_t per_graph = g_launches - before;
-		g_launches              = before;
-		FI_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+		};
 		cudaEvent_t l0, l1;
 		FI_CUDA(cudaEventCreate(&l0));
 		FI_CUDA(cudaEventCreate(&l1));
-		FI_CUDA(cudaEventRecord(l0, s));
-		while (true) {
-			FI_CUDA(cudaGraphLaunch(exec, s));
-			count_launch(static_cast<int>(per_graph));
-			FI_CUDA(cudaMemcpyAsync(&h, w.state.data(), sizeof(h), cudaMemcpyDeviceToHost, s));
-			FI_CUDA(cudaStreamSynchronize(s));
-			if (h.done) { break; }
+		if (dist && !link) {
+			// NCCL inside the iteration: launch directly.  Instantiating a graph that contains NCCL nodes costs tens of
+			// milliseconds, and with ~7 launches per iteration of >= 0.1 ms the host stays ahead of the device anyway.
+			TraceScope trl("iteration loop (direct launches)");
+			FI_CUDA(cudaEventRecord(l0, s));
+			while (true) {
+				enqueue_round();
+				FI_CUDA(cudaMemcpyAsync(&h, w.state.data(), sizeof(h), cudaMemcpyDeviceToHost, s));
+				FI_CUDA(cudaStreamSynchronize(s));
+				if (h.done) { break; }
+			}
+		} else {
+			// one CUDA graph = check_every iterations, replayed until the device-side flag says stop
+			cudaGraph_t     graph = nullptr;
+			cudaGraphExec_t exec  = nullptr;
+			const int64_t   before = g_launches;
+			FI_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+			try {
+				enqueue_round();
+			} catch (...) {
+				cudaStreamEndCapture(s, &graph);
+				if (graph) { cudaGraphDestroy(graph); }
+				throw;
+			}
+			FI_CUDA(cudaStreamEndCapture(s, &graph));
+			const int64_t per_graph = g_launches - before;
+			g_launches              = before;
+			{
+				TraceScope tr("cudaGraphInstantiate");
+				FI_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+			}
+			TraceScope trl("iteration loop (graph launches)");
+			FI_CUDA(cudaEventRecord(l0, s));
+			while (true) {
+				FI_CUDA(cudaGraphLaunch(exec, s));
+				count_launch(static_cast<int>(per_graph));
+				FI_CUDA(cudaMemcpyAsync(&h, w.state.data(), sizeof(h), cudaMemcpyDeviceToHost, s));
+				FI_CUDA(cudaStreamSynchronize(s));
+				if (h.done) { break; }
+			}
+			cudaGraphExecDestroy(exec);
+			cudaGraphDestroy(graph);
 		}
 		FI_CUDA(cudaEventRecord(l1, s));
 		FI_CUDA(cudaEventSynchronize(l1));
+		if (link && trace_enabled() && h.iters >= 8) {
+			// phase durations on this rank from the device timestamps of the last iterations
+			std::vector<unsigned long long> st3(3 * 512);
+			FI_CUDA(cudaMemcpy(st3.data(), link->local->stamp, sizeof(unsigned long long) * 3 * 512, cudaMemcpyDeviceToHost));
+			const long long last = h.iters - 1, first = std::max<long long>(1, h.iters - 400);
+			double a = 0, b = 0, c = 0;
+			for (long long k = first; k <= last; ++k) {
+				a += static_cast<double>(st3[0 * 512 + (k & 511)] - st3[2 * 512 + ((k - 1) & 511)]);  // finish(k-1) -> publish(k)
+				b += static_cast<double>(st3[1 * 512 + (k & 511)] - st3[0 * 512 + (k & 511)]);        // publish(k) -> update past wait
+				c += static_cast<double>(st3[2 * 512 + (k & 511)] - st3[1 * 512 + (k & 511)]);        // update -> finish(k)
+			}
+			const double cnt = static_cast<double>(last - first + 1) * 1e3;
+			fprintf(stderr, "[fi_b200] rank %d per-iteration us: stencil+data %.1f | wait p.Ap %.1f | update+wait r.r %.1f\n", link->rank, a / cnt,
+			        b / cnt, c / cnt);
+		}
 		float lms = 0;
 		FI_CUDA(cudaEventElapsedTime(&lms, l0, l1));
 		res.loop_ms = lms;
 		cudaEventDestroy(l0);
 		cudaEventDestroy(l1);
-		cudaGraphExecDestroy(exec);
-		cudaGraphDestroy(graph);
 	}
 	FI_CUDA(cudaEventRecord(e1, s));
 	FI_CUDA(cudaEventSynchronize(e1));

@@ -22,10 +22,59 @@ struct PcgState
 	double part[4];  // multi-GPU: this rank's partial sums, all-reduced in place before the finish kernels read them
 };
 
+// ---- multi-GPU: scalar all-reduce and halo push over NVLink peer memory, inside the CG kernels -------------
+// Every rank owns a mailbox in device memory that its peers map through CUDA IPC.  A kernel publishes this
+// rank's partial sums by storing {values, sequence number} into its slot of every peer's mailbox; the kernel
+// that needs the sum spins on its local mailbox until all slots carry the expected sequence number and adds
+// them in rank order (so every rank forms bit-identical sums).  Sequence numbers only grow: no resets, no ABA.
+constexpr int kMaxPeers = 8;  // one NVSwitch domain
+
+struct PeerSlot
+{
+	double             v[2];
+	unsigned long long seq;
+	unsigned long long pad;
+};
+
+struct Mailbox
+{
+	PeerSlot slot[2 /* which sum */][2 /* iteration parity */][kMaxPeers];
+	int      error;  // set by a kernel that gave up waiting for a peer
+	// device timestamps (ns) of the last 512 iterations, for FI_B200_TRACE: [0] p.Ap published (stencil + data term
+	// done), [1] update kernel past its wait, [2] iteration finished (all ranks' r.r collected)
+	unsigned long long stamp[3][512];
+};
+
+struct PeerLink  // passed to kernels by value
+{
+	int      rank = 0, world = 1;
+	Mailbox* local = nullptr;
+	Mailbox* peer[kMaxPeers] = {};  // peer[rank] == local
+};
+
+template <typename T>
+struct HaloPush  // where the update kernel stores its boundary planes of r in the neighbours' copies of r
+{
+	T*      lo = nullptr;  // rank - 1's upper halo planes (receives my first `count` owned values), or null
+	T*      hi = nullptr;  // rank + 1's lower halo planes (receives my last `count` owned values), or null
+	int64_t count = 0;     // halo planes * cells per plane
+};
+
 // Multi-GPU plumbing of one z-slab solve (dist.cu); nullptr everywhere else.
 struct DistHooks
 {
 	virtual ~DistHooks() = default;
+	// Peer-memory path.  link() is null when it is unavailable (then the NCCL calls below carry the iteration).
+	virtual const PeerLink* link() { return nullptr; }
+	// A lattice vector of `bytes` that the neighbouring ranks can store into (collective; contents zeroed on
+	// stream s).  lo / hi receive the neighbours' mappings of *their* vector (null at the ends).
+	virtual void* shared_vector(size_t bytes, void** lo, void** hi, cudaStream_t s)
+	{
+		(void)bytes; (void)lo; (void)hi; (void)s;
+		return nullptr;
+	}
+	virtual int64_t peer_own_cells(int peer) { (void)peer; return 0; }
+	virtual unsigned long long next_seq() { return 0; }
 	// in-place sum over ranks of `count` doubles in device memory, enqueued on s (capturable)
 	virtual void allreduce(double* d_ptr, int count, cudaStream_t s) = 0;
 	// fills the halo planes of a local lattice vector from the neighbouring slabs' owned planes

@@ -358,14 +358,28 @@ void launch(const Geom& g, const StencilTables& t, const T* a, const T* b, const
 	const CUtensorMap mb = Fused ? make_map<T, R>(g, b) : ma;
 	const CUtensorMap mc = Fused ? make_map<T, R>(g, c) : ma;
 	const int tiles_x = div_up(g.size[0], G::TXP * G::V), tiles_y = div_up(g.size[1], G::TY);
-	// z chunking: enough blocks for ~8 waves of MINB resident blocks per SM, chunks of at least 16 planes
-	const int64_t resident    = static_cast<int64_t>(sm_count()) * MINB;
-	const int64_t want_blocks = resident * 8;
-	int           chunks      = static_cast<int>(std::max<int64_t>(1, want_blocks / (static_cast<int64_t>(tiles_x) * tiles_y)));
-	const int nown            = g.zown1 - g.zown0;
-	chunks                    = std::min(chunks, std::max(1, nown / 16));
-	const int zchunk          = div_up(nown, chunks);
-	chunks                    = div_up(nown, zchunk);
+	// z chunking.  A block marches its chunk plane by plane and pays 2R halo planes plus the pipeline fill per
+	// chunk, so chunks should be long; blocks run in waves of `resident`, so their number should fill whole waves.
+	// Pick the chunk count that minimises waves * (planes per chunk + 2R + fill).
+	const int64_t resident = static_cast<int64_t>(sm_count()) * MINB;
+	const int64_t tiles    = static_cast<int64_t>(tiles_x) * tiles_y;
+	const int     nown     = g.zown1 - g.zown0;
+	int           chunks   = 1;
+	double        best     = 1e300;
+	for (int c = 1; c <= std::max(1, nown / (2 * R + 1)) && c <= 256; ++c) {
+		const int     zc    = div_up(nown, c);
+		const int     cc    = div_up(nown, zc);
+		const int64_t waves = (tiles * cc + resident - 1) / resident;
+		// a last wave that is mostly empty still costs a whole chunk: charge partial waves at least half
+		const double  frac  = static_cast<double>(tiles * cc) / static_cast<double>(resident);
+		const double  cost  = std::max(static_cast<double>(waves) - 0.5, frac) * (zc + 2 * R + S + 1);
+		if (cost < best - 1e-9) {
+			best   = cost;
+			chunks = cc;
+		}
+	}
+	const int zchunk = div_up(nown, chunks);
+	chunks           = div_up(nown, zchunk);
 	dim3 grid(tiles_x, tiles_y, chunks);
 	auto kern = stencil3d_tma_kernel<T, R, S, Fused, MINB>;
 	constexpr size_t smem = smem_bytes<T, R, S, Fused>();

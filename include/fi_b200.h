@@ -219,6 +219,12 @@ FI_API int fi_slab_sdf_solve(fi_comm* c, const int32_t* sizes /* 3 */, const fi_
                       const fi_solve_options* opt, const float* guess_own, float* solution_own, int32_t solution_loc,
                       fi_solve_stats* stats);
 
+/* ---- device memory ------------------------------------------------------------------------------------------ */
+/* Freed lattice-sized device blocks are cached per process for reuse (FI_B200_POOL_GB caps the cache, default 96).
+ * fi_trim_memory returns the cache to the driver; fi_cached_bytes reports its size. */
+FI_API int     fi_trim_memory(void);
+FI_API int64_t fi_cached_bytes(void);
+
 /* ---- instrumentation -------------------------------------------------------------------------- */
 /* Number of kernels this library has launched on the calling thread's device since load (bench.py's
  * gpu_launches), and a reset. */
