@@ -6,7 +6,7 @@ The product is the C-ABI library ``libfi_b200.so`` (include/fi_b200.h; CUDA sour
 is its Python host layer, mirroring the reference's C++ API name for name (see api.py).  There is no CPU
 fallback: importing is cheap, but every call needs the built library and a CUDA device.
 """
-from .api import (FI_DEVICE, FI_F32, FI_F64, FI_HOST, FI_MIXED, FiError, GradientKernel, LatticeField, LinearEquation,
+from .api import (FI_DEVICE, FI_F32, FI_F64, FI_HOST, FI_MIXED, FI_PRECOND_JACOBI, FI_PRECOND_MULTIGRID, FiError, GradientKernel, LatticeField, LinearEquation,
                   SolveOptions, ValueKernel, Weights, add_equation, add_field_constraints, add_gradient_constraint,
                   add_points, add_rows, add_value_constraint, add_value_constraint_nearest_neighbor, jacobi_iterations,
                   kernel_launches, kernel_launches_reset, sdf_from_points, sdf_solve_cascade, solve_options,

@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(HERE, "libfi_b200.so")
 FI_OK, FI_ERR_INVALID, FI_ERR_CUDA, FI_ERR_RANGE, FI_ERR_UNSUPPORTED, FI_ERR_COMM = range(6)
 FI_HOST, FI_DEVICE = 0, 1
 FI_F32, FI_F64, FI_MIXED = 0, 1, 2
+FI_PRECOND_JACOBI, FI_PRECOND_MULTIGRID = 0, 1
 
 
 class FiError(RuntimeError):
@@ -32,7 +33,8 @@ class fi_triplet(C.Structure):
 class fi_solve_options(C.Structure):
     _fields_ = [("precision", C.c_int32), ("max_iterations", C.c_int32), ("tolerance", C.c_double),
                 ("check_every", C.c_int32), ("use_fast_stencil", C.c_int32), ("refine_max_outer", C.c_int32),
-                ("refine_inner_tolerance", C.c_double)]
+                ("refine_inner_tolerance", C.c_double), ("preconditioner", C.c_int32), ("mg_smoothing_steps", C.c_int32),
+                ("mg_cheb_ratio", C.c_double)]
 
 
 class fi_solve_stats(C.Structure):

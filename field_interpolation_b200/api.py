@@ -13,7 +13,8 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import _lib as L
-from ._lib import FI_DEVICE, FI_F32, FI_F64, FI_HOST, FI_MIXED, FiError  # noqa: F401
+from ._lib import (FI_DEVICE, FI_F32, FI_F64, FI_HOST, FI_MIXED, FI_PRECOND_JACOBI, FI_PRECOND_MULTIGRID,  # noqa: F401
+                   FiError)
 
 
 class ValueKernel:  # field_interpolation.hpp:47-51
@@ -104,9 +105,11 @@ def _common_loc(bufs):
 
 
 def solve_options(precision=FI_F32, max_iterations=0, tolerance=1e-3, check_every=32, use_fast_stencil=True,
-                  refine_max_outer=20, refine_inner_tolerance=1e-3) -> L.fi_solve_options:
+                  refine_max_outer=20, refine_inner_tolerance=1e-3, preconditioner=FI_PRECOND_JACOBI, mg_smoothing_steps=3,
+                  mg_cheb_ratio=12.0) -> L.fi_solve_options:
     return L.fi_solve_options(int(precision), int(max_iterations), float(tolerance), int(check_every),
-                              int(use_fast_stencil), int(refine_max_outer), float(refine_inner_tolerance))
+                              int(use_fast_stencil), int(refine_max_outer), float(refine_inner_tolerance), int(preconditioner),
+                              int(mg_smoothing_steps), float(mg_cheb_ratio))
 
 
 class LatticeField:

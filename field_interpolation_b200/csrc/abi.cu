@@ -194,12 +194,29 @@ struct fi_field
 	fi::ModelAccum                         model;
 	std::unique_ptr<fi::Operator<float>>   op32;
 	std::unique_ptr<fi::Operator<double>>  op64;
+	std::unique_ptr<fi::Multigrid>         mg;      // hierarchy under op32 (FI_PRECOND_MULTIGRID)
+	fi::MgOptions                          mg_opt;
 	int                                    fast = fi::kStencilAuto;  // kernel choice of fi_field_apply
 
 	void invalidate()
 	{
+		mg.reset();
 		op32.reset();
 		op64.reset();
+	}
+	fi::Multigrid& get_mg(const fi_solve_options& o)
+	{
+		fi::MgOptions want;
+		if (o.mg_smoothing_steps > 0) { want.nu = o.mg_smoothing_steps; }
+		if (o.mg_cheb_ratio > 1.0) { want.cheb_ratio = o.mg_cheb_ratio; }
+		if (mg && (mg_opt.nu != want.nu || mg_opt.cheb_ratio != want.cheb_ratio)) { mg.reset(); }
+		if (!mg) {
+			fi::Operator<float>& fine = get32();
+			fine.use_fast             = fi::kStencilAuto;
+			mg                        = fi::build_multigrid(fine, model, pts, want, stream);
+			mg_opt                    = want;
+		}
+		return *mg;
 	}
 	fi::Operator<float>& get32()
 	{
@@ -213,6 +230,7 @@ struct fi_field
 	}
 	~fi_field()
 	{
+		mg.reset();
 		op32.reset();
 		op64.reset();
 		if (stream) { cudaStreamDestroy(stream); }
@@ -400,6 +418,45 @@ void solve_device(fi_field* f, const fi_solve_options& o, const float* d_guess, 
 	const int64_t N = f->g.N;
 	cudaStream_t  s = f->stream;
 	const int     fast = o.use_fast_stencil;
+	if (o.preconditioner == FI_PRECOND_MULTIGRID) {
+		const bool fresh = !f->mg;
+		double     setup = 0;
+		cudaEvent_t e0, e1;
+		FI_CUDA(cudaEventCreate(&e0));
+		FI_CUDA(cudaEventCreate(&e1));
+		FI_CUDA(cudaEventRecord(e0, s));
+		Multigrid& mg = f->get_mg(o);
+		if (o.precision == FI_F32) {
+			Operator<float>& op = f->get32();
+			FI_CUDA(cudaEventRecord(e1, s));
+			if (d_guess) {
+				if (d_guess != d_out) { FI_CUDA(cudaMemcpyAsync(d_out, d_guess, N * sizeof(float), cudaMemcpyDeviceToDevice, s)); }
+			} else {
+				FI_CUDA(cudaMemsetAsync(d_out, 0, N * sizeof(float), s));
+			}
+			const PcgResult r = mgpcg_solve<float>(op, mg, nullptr, d_out, o.tolerance, o.max_iterations, s);
+			float ms = 0;
+			FI_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+			setup = ms;
+			fill_stats(st, r, fresh ? setup : 0.0, op.data.nocc, op.data.nrows);
+		} else {  // FI_F64 and FI_MIXED: fp64 outer CG around the fp32 V-cycle
+			Operator<double>& op = f->get64();
+			op.use_fast          = fast;
+			FI_CUDA(cudaEventRecord(e1, s));
+			DevBuf<double> x(N);
+			if (d_guess) { convert(d_guess, x.data(), N, s); } else { x.zero(s); }
+			const PcgResult r = mgpcg_solve<double>(op, mg, nullptr, x.data(), o.tolerance, o.max_iterations, s);
+			convert(x.data(), d_out, N, s);
+			float ms = 0;
+			FI_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+			setup = ms;
+			fill_stats(st, r, fresh ? setup : 0.0, op.data.nocc, op.data.nrows);
+		}
+		cudaEventDestroy(e0);
+		cudaEventDestroy(e1);
+		FI_CUDA(cudaStreamSynchronize(s));
+		return;
+	}
 	if (o.precision == FI_F32) {
 		const bool fresh = !f->op32;
 		Operator<float>& op = f->get32();
@@ -526,6 +583,9 @@ void fi_solve_options_default(fi_solve_options* o)
 	o->use_fast_stencil       = 1;
 	o->refine_max_outer       = 20;
 	o->refine_inner_tolerance = 1e-3;
+	o->preconditioner         = FI_PRECOND_JACOBI;
+	o->mg_smoothing_steps     = 3;
+	o->mg_cheb_ratio          = 12.0;
 }
 
 int fi_field_create(int32_t ndim, const int32_t* sizes, fi_field** out)

@@ -1,6 +1,8 @@
 // Normal-equation operator and the preconditioned conjugate-gradient driver (solver.cu).
 #pragma once
 
+#include <vector>
+
 #include "internal.hpp"
 
 namespace fi {
@@ -155,6 +157,41 @@ inline bool stencil_fused_step(int mode, const Geom& g, const StencilTables& t, 
 	if (mode != kStencilGeneric && stencil_fast_3d_fused<T>(g, t, r, minv, p_old, p_new, q, st, par, d_dot_out, d_partial, d_ticket, d_done, s)) { return true; }
 	return false;
 }
+
+// ---- mg.cu: geometric multigrid preconditioner ----------------------------------------------------------------
+struct MgOptions
+{
+	int    nu               = 3;     // Chebyshev steps before and after the coarse-grid correction
+	double cheb_ratio       = 12.0;  // the smoother targets the eigenvalues of D^-1 A in [lambda_max / ratio, lambda_max]
+	int    coarsest_cells   = 600;   // coarsen until a level has at most this many cells (dense solve there)
+	int    power_iterations = 12;    // for lambda_max, per level, at setup
+};
+
+struct Multigrid
+{
+	struct Level;
+	MgOptions                           opt;
+	std::vector<std::unique_ptr<Level>> levels;      // 0 = finest
+	DevBuf<float>                       coarse_inv;  // dense inverse of the coarsest operator, row-major nc x nc
+	int                                 nc = 0;
+	cudaGraphExec_t                     exec = nullptr;  // the V-cycle for (graph_r -> graph_z)
+	const float*                        graph_r = nullptr;
+	float*                              graph_z = nullptr;
+	int64_t                             graph_launches = 0;
+
+	Multigrid();
+	~Multigrid();
+	// z = V-cycle(r): one application of the preconditioner (fp32, finest-level vectors of N floats)
+	void vcycle(const float* r, float* z, cudaStream_t s);
+};
+
+// Builds the hierarchy under `fine` (which must outlive it): re-discretised coarse operators from the same points
+// and the same smoothness model, Chebyshev bounds, dense coarsest inverse.
+std::unique_ptr<Multigrid> build_multigrid(Operator<float>& fine, const ModelAccum& model, const PointStore& pts, const MgOptions& opt, cudaStream_t s);
+
+// CG preconditioned by one V-cycle per iteration; same contract as pcg_solve.
+template <typename T>
+PcgResult mgpcg_solve(Operator<T>& op, Multigrid& mg, const T* b, T* x, double tol, long long max_iter, cudaStream_t s);
 
 template <typename T>
 void jacobi_sweeps(Operator<T>& op, T* x, int iterations, T weight, cudaStream_t s);

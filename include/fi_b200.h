@@ -52,6 +52,13 @@ enum fi_gradient_kernel { FI_GRADIENT_NEAREST_NEIGHBOR = 0, FI_GRADIENT_CELL_EDG
  * FI_F64 its double path (:154-184).  FI_MIXED = fp32 PCG inside fp64 iterative refinement. */
 enum fi_precision { FI_F32 = 0, FI_F64 = 1, FI_MIXED = 2 };
 
+/* Preconditioner of the CG solve.  FI_PRECOND_JACOBI = 1/diag(AtA), Eigen's DiagonalPreconditioner (what the
+ * reference's BiCGSTAB uses).  FI_PRECOND_MULTIGRID = one geometric-multigrid V-cycle per iteration: the reference's
+ * coarse-to-fine idea (the same problem re-assembled on coarser lattices, src/sdf_field.cpp:251-304) applied to the
+ * error on every level; iteration counts stop growing with the lattice size.  The V-cycle runs in fp32; with FI_F64
+ * (or FI_MIXED, the same thing here) the outer CG and its residual are fp64.  One GPU. */
+enum fi_preconditioner { FI_PRECOND_JACOBI = 0, FI_PRECOND_MULTIGRID = 1 };
+
 /* Weights, field_interpolation.hpp:75-95 (same field order and defaults; see fi_weights_default) */
 typedef struct fi_weights {
 	float   data_pos, data_gradient;
@@ -76,6 +83,9 @@ typedef struct fi_solve_options {
 	                           * when applicable, else the tiled one), 2: tiled 3D kernel without TMA */
 	int32_t refine_max_outer; /* FI_MIXED: max fp64 refinement sweeps; <= 0: 20 */
 	double  refine_inner_tolerance; /* FI_MIXED: relative tolerance of each inner fp32 solve; <= 0: 1e-3 */
+	int32_t preconditioner;   /* fi_preconditioner.  FI_PRECOND_JACOBI is what the reference's Eigen solvers use */
+	int32_t mg_smoothing_steps; /* FI_PRECOND_MULTIGRID: Chebyshev steps before and after each coarse correction; <= 0: 3 */
+	double  mg_cheb_ratio;    /* ... smoothed part of the spectrum is [lambda_max / ratio, lambda_max]; <= 0: 12 */
 } fi_solve_options;
 
 typedef struct fi_solve_stats {
