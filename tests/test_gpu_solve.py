@@ -231,3 +231,60 @@ def test_cascade_matches_manual_recipe(fi, port):
     _, stc = fi.sdf_solve_cascade(sizes, w, cloud["unit_pos"], cloud["normals"], options=fi.solve_options(fi.FI_F64, 0, 1e-6),
                                   factor=factor, coarsest_size=20)
     assert stc["level_iterations"][0] < st0["iterations"]
+
+
+# ---- multigrid-preconditioned CG (FI_PRECOND_MULTIGRID): same system, same stopping rule, different preconditioner ----
+@pytest.mark.parametrize("sizes,npts", [([97], 20), ([40, 37], 400), ([65, 64], 900), ([24, 20, 22], 1500), ([48, 33, 40], 4000)])
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_multigrid_pcg_vs_exact(fi, port, sizes, npts, prec):
+    D = len(sizes)
+    if D == 1:
+        rng = np.random.default_rng(5)
+        unit = rng.uniform(0.05, 0.95, (npts, 1)).astype(np.float32)
+        nrm = np.where(rng.uniform(size=(npts, 1)) < 0.5, -1.0, 1.0).astype(np.float32)
+        cloud = {"unit_pos": unit, "normals": nrm}
+    else:
+        cloud = W.circles_2d(npts, seed=2) if D == 2 else W.sphere_torus_3d(npts, seed=2)
+    pos = W.to_lattice(cloud["unit_pos"], sizes)
+    f = fi.sdf_from_points(sizes, fi.Weights(), pos, cloud["normals"])
+    sys_ = port.sdf_from_points(sizes, O.make_weights(), pos, cloud["normals"]).system()
+    n = int(np.prod(sizes))
+    exact = O.exact_solve(sys_, n)
+    if prec == "f64":
+        x, st = f.solve(fi.solve_options(fi.FI_F64, 0, 1e-11, preconditioner=fi.FI_PRECOND_MULTIGRID))
+        assert st["converged"] and rel(x, exact) <= TOL_F64, st
+        assert st["true_residual"] <= 1e-9, st
+    else:
+        x, st = f.solve(fi.solve_options(fi.FI_F32, 0, 1e-6, preconditioner=fi.FI_PRECOND_MULTIGRID))
+        assert rel(x, exact) <= TOL_F32, st
+    # the point of the preconditioner: far fewer iterations than Jacobi-PCG at the same tolerance
+    _, sj = f.solve(fi.solve_options(fi.FI_F64, 0, 1e-6))
+    _, sm = f.solve(fi.solve_options(fi.FI_F64, 0, 1e-6, preconditioner=fi.FI_PRECOND_MULTIGRID))
+    assert sm["converged"] and sm["iterations"] <= max(8, sj["iterations"] // 2), (sm["iterations"], sj["iterations"])
+
+
+@pytest.mark.parametrize("orders", [dict(model_2=0.0, model_1=0.7), dict(model_0=0.2, model_1=0.3, model_2=0.5),
+                                    dict(model_2=0.0, model_3=0.4), dict(model_2=0.3, gradient_smoothness=0.2)])
+def test_multigrid_pcg_other_models(fi, port, orders):
+    sizes = [33, 30, 28]
+    cloud = W.sphere_torus_3d(2500, seed=8)
+    pos = W.to_lattice(cloud["unit_pos"], sizes)
+    kw = dict(orders)
+    f = fi.sdf_from_points(sizes, fi.Weights(**kw), pos, cloud["normals"])
+    sys_ = port.sdf_from_points(sizes, O.make_weights(**kw), pos, cloud["normals"]).system()
+    exact = O.exact_solve(sys_, int(np.prod(sizes)))
+    x, st = f.solve(fi.solve_options(fi.FI_F64, 0, 1e-11, preconditioner=fi.FI_PRECOND_MULTIGRID))
+    assert st["converged"] and rel(x, exact) <= TOL_F64, st
+
+
+def test_multigrid_with_guess_and_cap(fi, port):
+    sizes = [40, 40, 40]
+    cloud = W.sphere_torus_3d(3000, seed=9)
+    pos = W.to_lattice(cloud["unit_pos"], sizes)
+    f = fi.sdf_from_points(sizes, fi.Weights(), pos, cloud["normals"])
+    x, st = f.solve(fi.solve_options(fi.FI_F64, 0, 1e-10, preconditioner=fi.FI_PRECOND_MULTIGRID))
+    # restarting from the solution stops at once; a cap of 2 iterations returns the last iterate, not an error
+    _, st2 = f.solve(fi.solve_options(fi.FI_F64, 0, 1e-8, preconditioner=fi.FI_PRECOND_MULTIGRID), guess=x)
+    assert st2["converged"] and st2["iterations"] <= 1, st2
+    _, st3 = f.solve(fi.solve_options(fi.FI_F64, 2, 1e-12, preconditioner=fi.FI_PRECOND_MULTIGRID))
+    assert not st3["converged"] and st3["iterations"] == 2, st3
