@@ -90,6 +90,7 @@ SIGNATURES = {
     "fi_field_rhs": (C.c_int, [_vp, _i32, _vp]),
     "fi_field_diagonal": (C.c_int, [_vp, _i32, _vp]),
     "fi_field_solve": (C.c_int, [_vp, _p(fi_solve_options), _vp, _vp, _i32, _p(fi_solve_stats)]),
+    "fi_field_solve_tiled": (C.c_int, [_vp, _p(fi_solve_options), _i32, _i32, _i32, _vp, _vp, _i32, _p(fi_solve_stats), _p(fi_solve_stats)]),
     "fi_field_jacobi": (C.c_int, [_vp, _pf, _i32, _f, _pf]),
     "fi_upscale_field": (C.c_int, [_i32, _pi32, _pi32, _vp, _vp, _i32]),
     "fi_error_map": (C.c_int, [_i64, _vp, _i64, _pf, _i64, _pf, _pf]),

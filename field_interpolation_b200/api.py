@@ -47,7 +47,7 @@ class Weights:  # field_interpolation.hpp:75-95, same defaults
 
 
 @dataclass
-class SolveOptions:  # sparse_linear.hpp:66-73 (tile phase: see DESIGN.md, not built yet)
+class SolveOptions:  # sparse_linear.hpp:66-73
     tile: bool = False
     tile_size: int = 16
     cg: bool = True
@@ -346,17 +346,19 @@ def solve_sparse_linear_with_guess(field: LatticeField, guess, max_iterations: i
     return _solve(field, solve_options(FI_F32, max_iterations, error_tolerance), guess)[0]
 
 
-def solve_tiled_with_guess(field: LatticeField, guess, sizes=None, options: Optional[SolveOptions] = None):
-    """sparse_linear.cpp:392-443.  The CG phase is built; the tile phase (options.tile) is not."""
+def solve_tiled_with_guess(field: LatticeField, guess, sizes=None, options: Optional[SolveOptions] = None, precision=FI_F32,
+                           return_stats: bool = False):
+    """sparse_linear.cpp:392-443: optional tile phase (tile_solver_square :246-390), then the optional CG phase."""
     o = options or SolveOptions()
-    g = np.asarray(guess, np.float32)
+    g = np.ascontiguousarray(guess, np.float32).ravel()
     if g.size != field.num_unknowns:
         return np.zeros(0, np.float32)  # "Incomplete guess." (:402-405)
-    if o.tile:
-        raise FiError(L.FI_ERR_UNSUPPORTED, "tile phase of solve_tiled_with_guess is not built (DESIGN.md)")
-    if not o.cg:
-        return g.copy()
-    return _solve(field, solve_options(FI_F32, o.max_iterations, o.error_tolerance), g)[0]
+    out = np.empty_like(g)
+    st, tst = L.fi_solve_stats(), L.fi_solve_stats()
+    opt = solve_options(precision, o.max_iterations, o.error_tolerance)
+    L.check(L.lib().fi_field_solve_tiled(field._h, C.byref(opt), int(bool(o.tile)), int(o.tile_size), int(bool(o.cg)),
+                                         C.c_void_p(g.ctypes.data), C.c_void_p(out.ctypes.data), FI_HOST, C.byref(st), C.byref(tst)))
+    return (out, st.as_dict(), tst.as_dict()) if return_stats else out
 
 
 def jacobi_iterations(field: LatticeField, guess, num_iterations: int, weight: float):

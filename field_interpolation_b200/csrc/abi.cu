@@ -845,6 +845,53 @@ int fi_field_solve(fi_field* f, const fi_solve_options* opt, const float* guess,
 	});
 }
 
+int fi_field_solve_tiled(fi_field* f, const fi_solve_options* opt, int32_t tile, int32_t tile_size, int32_t cg, const float* guess,
+                         float* solution, int32_t loc, fi_solve_stats* stats, fi_solve_stats* tile_stats)
+{
+	return guarded([&] {
+		TraceScope trace("fi_field_solve_tiled");
+		FI_REQUIRE(f && solution, FI_ERR_INVALID, "null argument");
+		FI_REQUIRE(guess != nullptr, FI_ERR_INVALID, "incomplete guess");  // sparse_linear.cpp:402-405
+		fi_solve_options o;
+		if (opt) { o = *opt; } else { fi_solve_options_default(&o); }
+		FI_REQUIRE(o.precision == FI_F32 || o.precision == FI_F64 || o.precision == FI_MIXED, FI_ERR_INVALID, "unknown precision");
+		const int64_t N = f->g.N;
+		cudaStream_t  s = f->stream;
+		DevBuf<float> staged;
+		float*        d_x = solution;
+		if (loc == FI_DEVICE) {
+			if (guess != solution) { FI_CUDA(cudaMemcpyAsync(solution, guess, N * sizeof(float), cudaMemcpyDeviceToDevice, s)); }
+		} else {
+			staged.resize(N);
+			d_x = staged.data();
+			FI_CUDA(cudaMemcpyAsync(d_x, guess, N * sizeof(float), cudaMemcpyHostToDevice, s));
+		}
+		if (stats) { std::memset(stats, 0, sizeof(*stats)); }
+		if (tile_stats) { std::memset(tile_stats, 0, sizeof(*tile_stats)); }
+		if (tile) {  // sparse_linear.cpp:423-425
+			if (o.precision == FI_F32) {
+				const bool       fresh = !f->op32;
+				Operator<float>& op    = f->get32();
+				op.use_fast            = o.use_fast_stencil;
+				const PcgResult r      = tile_phase<float>(op, tile_size, d_x, 1e-6, 0, o.check_every, s);
+				fill_stats(tile_stats, r, fresh ? op.setup_ms : 0.0, op.data.nocc, op.data.nrows);
+			} else {
+				const bool        fresh = !f->op64;
+				Operator<double>& op    = f->get64();
+				op.use_fast             = o.use_fast_stencil;
+				DevBuf<double> x(N);
+				convert(d_x, x.data(), N, s);
+				const PcgResult r = tile_phase<double>(op, tile_size, x.data(), 1e-12, 0, o.check_every, s);
+				convert(x.data(), d_x, N, s);
+				fill_stats(tile_stats, r, fresh ? op.setup_ms : 0.0, op.data.nocc, op.data.nrows);
+			}
+		}
+		if (cg) { solve_device(f, o, d_x, d_x, stats); }  // :427-440
+		if (loc != FI_DEVICE) { FI_CUDA(cudaMemcpyAsync(solution, d_x, N * sizeof(float), cudaMemcpyDeviceToHost, s)); }
+		FI_CUDA(cudaStreamSynchronize(s));
+	});
+}
+
 int fi_field_jacobi(fi_field* f, const float* guess, int32_t num_iterations, float weight, float* solution)
 {
 	return guarded([&] {

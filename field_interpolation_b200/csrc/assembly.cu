@@ -623,11 +623,14 @@ __global__ void cell_nodes_kernel(Geom g, int64_t nocc, const uint64_t* __restri
 // q += P p over the occupied cells: one thread per cell reads its 2^D corner values of p, multiplies by the
 // symmetric block (upper triangle, [tri][cell] so that a warp reads consecutive cells of one entry) and adds the
 // 2^D results to q with atomics (neighbouring cells share corners).
-template <typename T, int D>
+// TILED (tile mode, Geom::tile): entries between corners that lie in different tiles are dropped; the cell's base
+// coordinates come from its key.
+template <typename T, int D, bool TILED>
 __global__ void __launch_bounds__(kThreads, 3) apply_blocks_kernel(Geom g, int64_t nocc, const int64_t* __restrict__ cell_base,
                                                                 const uint32_t* __restrict__ cell_mask, const T* __restrict__ blocks,
                                                                 const T* __restrict__ p, T* __restrict__ q, double* partial,
-                                                                unsigned* ticket, double* dot_accum, const int* done)
+                                                                unsigned* ticket, double* dot_accum, const int* done,
+                                                                const uint64_t* __restrict__ cell_key)
 {
 	constexpr int C = 1 << D;
 	__shared__ double red[32];
@@ -651,12 +654,24 @@ __global__ void __launch_bounds__(kThreads, 3) apply_blocks_kernel(Geom g, int64
 			pc[c]  = ((mask >> c) & 1u) ? p[base + off] : T(0);
 			out[c] = 0;
 		}
+		int cross = 0;  // bit d: the cell straddles a tile boundary along axis d
+		if (TILED) {
+			uint64_t key = cell_key[cell];
+#pragma unroll
+			for (int d = 0; d < D; ++d) {
+				const uint64_t ext = static_cast<uint64_t>(g.size[d] + 1);
+				const int      b1  = static_cast<int>(key % ext);  // base coordinate + 1
+				key /= ext;
+				cross |= (b1 % g.tile == 0 ? 1 : 0) << d;
+			}
+		}
 		int tri = 0;
 #pragma unroll
 		for (int ci = 0; ci < C; ++ci) {
 #pragma unroll
 			for (int cj = ci; cj < C; ++cj) {
-				const T b = blk[tri];
+				T b = blk[tri];
+				if (TILED && ((ci ^ cj) & cross)) { b = T(0); }
 				out[ci] += b * pc[cj];
 				if (cj != ci) { out[cj] += b * pc[ci]; }
 				++tri;
@@ -697,6 +712,37 @@ __global__ void __launch_bounds__(kThreads) apply_rows_kernel(int64_t nrows, con
 		for (uint64_t k = b; k < e; ++k) { dot += static_cast<T>(val[k]) * p[col[k]]; }
 		for (uint64_t k = b; k < e; ++k) { atomic_add(&q[col[k]], static_cast<T>(val[k]) * dot); }
 		mine[0] = static_cast<double>(dot) * static_cast<double>(dot);
+	}
+	if (dot_accum) {
+		mine[0] = block_sum(mine[0], red);
+		grid_sum<1>(mine, partial, ticket, red, [&](const double(&tot)[1]) { *dot_accum += tot[0]; });
+	}
+}
+
+// Tile mode of the same: a row a contributes a_i a_j only for columns i, j of one tile, so every entry sums the
+// row's terms of its own tile (quadratic in the row length; generic rows are short).
+template <typename T>
+__global__ void __launch_bounds__(kThreads) apply_rows_tiled_kernel(Geom g, int64_t nrows, const uint64_t* __restrict__ row_ptr,
+                                                                    const int32_t* __restrict__ col, const float* __restrict__ val,
+                                                                    const T* __restrict__ p, T* __restrict__ q, double* partial,
+                                                                    unsigned* ticket, double* dot_accum, const int* done)
+{
+	__shared__ double red[32];
+	if (done && *done) { return; }
+	const int64_t r       = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	double        mine[1] = {0.0};
+	if (r < nrows) {
+		const uint64_t b = row_ptr[r], e = row_ptr[r + 1];
+		for (uint64_t k = b; k < e; ++k) {
+			const int64_t tk  = tile_of_node(g, col[k]);
+			T             dot = 0;
+			for (uint64_t j = b; j < e; ++j) {
+				if (tile_of_node(g, col[j]) == tk) { dot += static_cast<T>(val[j]) * p[col[j]]; }
+			}
+			const T add = static_cast<T>(val[k]) * dot;
+			atomic_add(&q[col[k]], add);
+			mine[0] += static_cast<double>(p[col[k]]) * static_cast<double>(add);
+		}
 	}
 	if (dot_accum) {
 		mine[0] = block_sum(mine[0], red);
@@ -890,12 +936,22 @@ void apply_data_term(const Geom& g, const DataTerm<T>& dt, const T* p, T* q, dou
 	unsigned* ticket  = const_cast<unsigned*>(dt.ticket.data());
 	if (gb > 0) {
 		by_dim(g.ndim, [&](auto dim) {
-			auto kern = apply_blocks_kernel<T, decltype(dim)::value>;
-			FI_LAUNCH(kern, gb, kThreads, 0, s, g, dt.nocc, dt.cell_base.data(), dt.cell_mask.data(), dt.blocks.data(), p, q, partial, ticket,
-				          d_dot_accum, d_done);
+			if (g.tile) {
+				auto kern = apply_blocks_kernel<T, decltype(dim)::value, true>;
+				FI_LAUNCH(kern, gb, kThreads, 0, s, g, dt.nocc, dt.cell_base.data(), dt.cell_mask.data(), dt.blocks.data(), p, q, partial, ticket,
+				          d_dot_accum, d_done, dt.cell_key.data());
+			} else {
+				auto kern = apply_blocks_kernel<T, decltype(dim)::value, false>;
+				FI_LAUNCH(kern, gb, kThreads, 0, s, g, dt.nocc, dt.cell_base.data(), dt.cell_mask.data(), dt.blocks.data(), p, q, partial, ticket,
+				          d_dot_accum, d_done, static_cast<const uint64_t*>(nullptr));
+			}
 		});
 	}
-	if (gr > 0) {
+	if (gr > 0 && g.tile) {
+		auto kern = apply_rows_tiled_kernel<T>;
+		FI_LAUNCH(kern, gr, kThreads, 0, s, g, dt.nrows, dt.row_ptr.data(), dt.col.data(), dt.val.data(), p, q,
+		          partial + gb + 1, ticket + 1, d_dot_accum, d_done);
+	} else if (gr > 0) {
 		auto kern = apply_rows_kernel<T>;
 		FI_LAUNCH(kern, gr, kThreads, 0, s, dt.nrows, dt.row_ptr.data(), dt.col.data(), dt.val.data(), p, q,
 		          partial + gb + 1, ticket + 1, d_dot_accum, d_done);

@@ -19,11 +19,29 @@ struct Geom  // LatticeField geometry, reference field_interpolation.hpp:97-114 
 	int     nzl = 1;                       // planes stored locally
 	int     zown0 = 0, zown1 = 1;          // local planes this process owns (computes rows for): [zown0, zown1)
 	int64_t shift = 0;                     // = -stride[2] * zoff: local index = sum coord[d] * stride[d] + shift
+	// Tile mode (tile_solver_square, reference sparse_linear.cpp:246-390): with tile >= 2 the operator kernels drop
+	// every entry (i, j) of A^T A whose nodes lie in different tile^D tiles and add tile_reg to the diagonal
+	// (:306-309), i.e. they apply the block-diagonal matrix the reference factorises tile by tile.  Unsharded only.
+	int     tile = 0;
+	float   tile_reg = 0.0f;
 
 	__host__ __device__ bool sharded() const { return zown0 != 0 || zown1 != nzl; }
 	__host__ __device__ int64_t own_offset() const { return static_cast<int64_t>(zown0) * (ndim == 3 ? stride[2] : 0); }
 	__host__ __device__ int64_t own_cells() const { return ndim == 3 ? static_cast<int64_t>(zown1 - zown0) * stride[2] : N; }
 };
+
+// Linear tile number of unsharded lattice node `index` (x fastest over ceil(size / tile) tiles per axis).
+__host__ __device__ inline int64_t tile_of_node(const Geom& g, int64_t index)
+{
+	int64_t t = 0, ts = 1;
+	for (int d = 0; d < g.ndim; ++d) {
+		const int c = static_cast<int>(index % g.size[d]);
+		index /= g.size[d];
+		t += static_cast<int64_t>(c / g.tile) * ts;
+		ts *= (g.size[d] + g.tile - 1) / g.tile;
+	}
+	return t;
+}
 
 inline Geom make_geom(int ndim, const int32_t* sizes)
 {

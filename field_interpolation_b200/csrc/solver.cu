@@ -736,6 +736,82 @@ void jacobi_sweeps(Operator<T>& op, T* x, int iterations, T weight, cudaStream_t
 	FI_CUDA(cudaStreamSynchronize(s));
 }
 
+// ---- tile phase of solve_tiled_with_guess (tile_solver_square, reference sparse_linear.cpp:246-390) ---------------
+// rhs = Atb - 2 (A g - B g): every coupling between two tiles is moved to the right-hand side with the guess — twice,
+// because the reference visits both stored triangles of the symmetric AtA and subtracts at both ends each time
+// (:327-334).  minv = 1 / (diag + reg) (:306-309).  A tile counts as "regularisation only" (:345-348: skipped, the
+// guess is kept) when none of its nodes has a diagonal entry.
+template <typename T>
+__global__ void tile_prepare_kernel(Geom g, const T* __restrict__ atb, const T* __restrict__ Ag, const T* __restrict__ Bg,
+                                    const T* __restrict__ diag, T* __restrict__ rhs, T* __restrict__ minv, int* __restrict__ tile_active)
+{
+	const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (i >= g.N) { return; }
+	rhs[i]  = atb[i] - T(2) * (Ag[i] - Bg[i]);
+	minv[i] = T(1) / (diag[i] + static_cast<T>(g.tile_reg));
+	if (diag[i] != T(0)) { tile_active[tile_of_node(g, i)] = 1; }
+}
+
+template <typename T>
+__global__ void tile_merge_kernel(Geom g, const T* __restrict__ y, const int* __restrict__ tile_active, T* __restrict__ x)
+{
+	const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (i >= g.N) { return; }
+	if (tile_active[tile_of_node(g, i)]) { x[i] = y[i]; }
+}
+
+// x: the guess on entry, the tile-wise solution on exit.  Every tile's system (A_tile + reg I) y = rhs_tile is
+// solved by the same Jacobi-PCG as everything else, all tiles at once: the block-diagonal matrix is applied by the
+// operator kernels in tile mode (Geom::tile), so the tiles never exchange information and the result is the
+// per-tile exact solution up to `tol`.
+template <typename T>
+PcgResult tile_phase(Operator<T>& op, int tile_size, T* x, double tol, long long max_iter, int check_every, cudaStream_t s)
+{
+	TraceScope trace("tile_phase");
+	FI_REQUIRE(tile_size >= 2, FI_ERR_INVALID, "tile_size must be >= 2");  // CHECK_GE_F(tile_size, 2), :255
+	FI_REQUIRE(op.dist == nullptr && !op.g.sharded(), FI_ERR_UNSUPPORTED, "the tile phase runs on an unsharded lattice");
+	const int64_t n = op.g.N;
+	int64_t       tiles = 1;
+	for (int d = 0; d < op.g.ndim; ++d) { tiles *= (op.g.size[d] + tile_size - 1) / tile_size; }
+	DevBuf<T>   Ag(n), Bg(n), rhs(n), y(n), minv(n);
+	DevBuf<int> active(static_cast<size_t>(tiles));
+	active.zero(s);
+	const int  old_fast = op.use_fast;
+	const Geom old_g    = op.g;
+	bool       swapped  = false;
+	auto restore = [&] {
+		op.g        = old_g;
+		op.use_fast = old_fast;
+		if (swapped) { op.minv.swap(minv); swapped = false; }
+	};
+	PcgResult r;
+	try {
+		op.apply(x, Ag.data(), nullptr, nullptr, s);
+		op.g.tile     = tile_size;
+		op.g.tile_reg = 0.0f;
+		op.use_fast   = kStencilGeneric;
+		op.apply(x, Bg.data(), nullptr, nullptr, s);
+		op.g.tile_reg = 1e-6f;
+		{
+			auto kern = tile_prepare_kernel<T>;
+			FI_LAUNCH(kern, div_up(n, kThreads), kThreads, 0, s, op.g, op.atb.data(), Ag.data(), Bg.data(), op.diag.data(), rhs.data(), minv.data(),
+			          active.data());
+		}
+		op.minv.swap(minv);
+		swapped = true;
+		FI_CUDA(cudaMemcpyAsync(y.data(), x, n * sizeof(T), cudaMemcpyDeviceToDevice, s));
+		r = pcg_solve<T>(op, rhs.data(), y.data(), tol, max_iter, check_every, false, s);
+		auto kern = tile_merge_kernel<T>;
+		FI_LAUNCH(kern, div_up(n, kThreads), kThreads, 0, s, op.g, y.data(), active.data(), x);
+		FI_CUDA(cudaStreamSynchronize(s));
+	} catch (...) {
+		restore();
+		throw;
+	}
+	restore();
+	return r;
+}
+
 // Per-kernel device times for the roofline figures (fi_field_time_iterations).
 template <typename T>
 void time_kernels(Operator<T>& op, int iterations, int check_every, double* out, cudaStream_t s)
@@ -813,6 +889,8 @@ template std::unique_ptr<Operator<float>> build_operator<float>(const Geom&, con
 template std::unique_ptr<Operator<double>> build_operator<double>(const Geom&, const ModelAccum&, const PointStore&, const HostRows&, cudaStream_t);
 template PcgResult pcg_solve<float>(Operator<float>&, const float*, float*, double, long long, int, bool, cudaStream_t);
 template PcgResult pcg_solve<double>(Operator<double>&, const double*, double*, double, long long, int, bool, cudaStream_t);
+template PcgResult tile_phase<float>(Operator<float>&, int, float*, double, long long, int, cudaStream_t);
+template PcgResult tile_phase<double>(Operator<double>&, int, double*, double, long long, int, cudaStream_t);
 template void jacobi_sweeps<float>(Operator<float>&, float*, int, float, cudaStream_t);
 template void jacobi_sweeps<double>(Operator<double>&, double*, int, double, cudaStream_t);
 template void residual<float>(Operator<float>&, const float*, const float*, float*, double*, double*, cudaStream_t);

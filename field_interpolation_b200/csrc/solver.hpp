@@ -153,6 +153,7 @@ inline bool stencil_fused_step(int mode, const Geom& g, const StencilTables& t, 
                                T* q, const PcgState* st, int par, double* d_dot_out, double* d_partial, unsigned* d_ticket,
                                const int* d_done, cudaStream_t s)
 {
+	if (g.tile) { return false; }  // tile mode: generic kernels only
 	if (mode == kStencilAuto && stencil_tma_3d_fused<T>(g, t, r, minv, p_old, p_new, q, st, par, d_dot_out, d_partial, d_ticket, d_done, s)) { return true; }
 	if (mode != kStencilGeneric && stencil_fast_3d_fused<T>(g, t, r, minv, p_old, p_new, q, st, par, d_dot_out, d_partial, d_ticket, d_done, s)) { return true; }
 	return false;
@@ -192,6 +193,11 @@ std::unique_ptr<Multigrid> build_multigrid(Operator<float>& fine, const ModelAcc
 // CG preconditioned by one V-cycle per iteration; same contract as pcg_solve.
 template <typename T>
 PcgResult mgpcg_solve(Operator<T>& op, Multigrid& mg, const T* b, T* x, double tol, long long max_iter, cudaStream_t s);
+
+// Tile phase of solve_tiled_with_guess (reference sparse_linear.cpp:246-390): x holds the guess on entry and the
+// tile-by-tile solution on exit.  The returned statistics are those of the block-diagonal solve.
+template <typename T>
+PcgResult tile_phase(Operator<T>& op, int tile_size, T* x, double tol, long long max_iter, int check_every, cudaStream_t s);
 
 template <typename T>
 void jacobi_sweeps(Operator<T>& op, T* x, int iterations, T weight, cudaStream_t s);

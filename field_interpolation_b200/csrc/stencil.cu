@@ -102,13 +102,17 @@ __global__ void __launch_bounds__(kThreads) stencil_generic_kernel(Geom g, DevTa
 		coords_of(g, i, c);
 		T         acc = 0;
 		const int R   = tab.radius;
+		const int tl  = g.tile;  // >= 2: block-Jacobi mask (taps into another tile are dropped)
 		for (int d = 0; d < g.ndim; ++d) {
 			const T* row = band[d][row_class(c[d], g.size[d])];
 			for (int o = -R; o <= R; ++o) {
 				const T coef = row[o + 4];
-				if (coef != T(0)) { acc += coef * p[i + o * g.stride[d]]; }
+				if (coef == T(0)) { continue; }
+				if (tl && (c[d] + o < 0 || (c[d] + o) / tl != c[d] / tl)) { continue; }
+				acc += coef * p[i + o * g.stride[d]];
 			}
 		}
+		if (tl) { acc += static_cast<T>(g.tile_reg) * p[i]; }
 		if (tab.gs2 != T(0)) {
 			for (int d = 0; d < g.ndim; ++d) {
 				for (int o = d + 1; o < g.ndim; ++o) {
@@ -118,6 +122,7 @@ __global__ void __launch_bounds__(kThreads) stencil_generic_kernel(Geom g, DevTa
 						for (int b = -1; b <= 1; ++b) {
 							const int lb = lap1(c[o], g.size[o], b);
 							if (lb == 0) { continue; }
+							if (tl && ((c[d] + a) / tl != c[d] / tl || (c[o] + b) / tl != c[o] / tl)) { continue; }
 							acc += tab.gs2 * static_cast<T>(la * lb) * p[i + a * g.stride[d] + b * g.stride[o]];
 						}
 					}
@@ -193,6 +198,7 @@ template <typename T>
 void stencil_apply(const Geom& g, const StencilTables& t, const T* p, T* q, double* d_dot_out, double* d_partial,
                    unsigned* d_ticket, const int* d_done, int mode, cudaStream_t s)
 {
+	if (g.tile) { mode = kStencilGeneric; }  // only the generic kernel knows the tile mask
 	if (mode == kStencilAuto && stencil_tma_3d<T>(g, t, p, q, d_dot_out, d_partial, d_ticket, d_done, s)) { return; }
 	if (mode != kStencilGeneric && stencil_fast_3d<T>(g, t, p, q, d_dot_out, d_partial, d_ticket, d_done, s)) { return; }
 	auto kern = stencil_generic_kernel<T>;

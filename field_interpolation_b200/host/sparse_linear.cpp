@@ -64,19 +64,27 @@ const char* last_error() { return fi_last_error(); }
 
 // The device description to solve `eq` from: its own structured handle when it has one that is still
 // consistent with the triplet list, else a fresh generic-rows description of the whole list.
-static Structured* description_of(const LinearEquation& eq, long long num_columns, std::shared_ptr<Structured>* temp)
+// `lattice` (nullable): the lattice shape the caller states (solve_tiled_with_guess); a description of another
+// shape is not reused, and a fresh one is created with that shape so that tiles mean what the caller means.
+static Structured* description_of(const LinearEquation& eq, long long num_columns, std::shared_ptr<Structured>* temp,
+                                  const std::vector<int>* lattice = nullptr)
 {
 	Structured* st = eq.structured.get();
 	if (st) {
 		long long n = 1;
 		for (int s : st->sizes) { n *= s; }
-		if ((num_columns <= 0 || n == num_columns) && forward_tail_rows(eq, st)) { return st; }
+		const bool shape_ok = !lattice || st->sizes == *lattice;
+		if (shape_ok && (num_columns <= 0 || n == num_columns) && forward_tail_rows(eq, st)) { return st; }
 	}
 	if (num_columns <= 0) { return nullptr; }
 	auto g   = std::make_shared<Structured>();
 	g->sizes = {static_cast<int>(num_columns)};
-	const int32_t sz = static_cast<int32_t>(num_columns);
-	if (fi_field_create(1, &sz, &g->handle) != FI_OK) { return nullptr; }
+	if (lattice) {
+		if (lattice->empty() || lattice->size() > 3) { return nullptr; }
+		g->sizes = *lattice;
+	}
+	std::vector<int32_t> sz(g->sizes.begin(), g->sizes.end());
+	if (fi_field_create(static_cast<int32_t>(sz.size()), sz.data(), &g->handle) != FI_OK) { return nullptr; }
 	if (!forward_tail_rows(eq, g.get())) { return nullptr; }
 	*temp = g;
 	return g.get();
@@ -155,10 +163,21 @@ std::vector<float> solve_tiled_with_guess(const LinearEquation& eq, const std::v
 	size_t n = 1;
 	for (int s : sizes) { n *= static_cast<size_t>(s); }
 	if (guess.size() != n) { return {}; }  // "Incomplete guess", :402-405
-	std::vector<float> x = guess;
-	// The tile phase (options.tile, :423-425 -> :246-390) is a block-Jacobi improvement of the guess; it is not
-	// built on the GPU yet ("next" rows).  Skipping it only changes where the CG phase starts from.
-	if (options.cg) { x = b200::solve(eq, static_cast<int>(n), b200::Precision::kFloat, &x, options.max_iterations, options.error_tolerance, nullptr); }
+	if (!options.tile && !options.cg) { return guess; }
+	std::shared_ptr<b200::Structured> temp;
+	b200::Structured* st = b200::description_of(eq, static_cast<long long>(n), &temp, &sizes);
+	if (!st) { return {}; }
+	fi_solve_options o;
+	fi_solve_options_default(&o);
+	o.precision      = FI_F32;
+	o.max_iterations = options.max_iterations;
+	o.tolerance      = options.error_tolerance;
+	std::vector<float> x(n);
+	// tile phase (:423-425 -> tile_solver_square :246-390), then the CG phase (:427-440), both on the device
+	if (fi_field_solve_tiled(st->handle, &o, options.tile ? 1 : 0, options.tile_size, options.cg ? 1 : 0, guess.data(), x.data(), FI_HOST, nullptr,
+	                         nullptr) != FI_OK) {
+		return {};
+	}
 	return x;
 }
 

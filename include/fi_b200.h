@@ -169,6 +169,17 @@ FI_API int fi_field_diagonal(fi_field* f, int32_t precision, void* diag);
 FI_API int fi_field_solve(fi_field* f, const fi_solve_options* opt, const float* guess, float* solution, int32_t loc,
                    fi_solve_stats* stats);
 
+/* solve_tiled_with_guess, sparse_linear.cpp:392-443, with the fields of SolveOptions (sparse_linear.hpp:66-73) as
+ * arguments: when tile != 0 the guess is first replaced by the tile-by-tile solution of tile_solver_square (:246-390
+ * — tile_size^D tiles; couplings between tiles moved to the right-hand side with the guess, applied twice as the
+ * reference does; 1e-6 diagonal regularisation; tiles without any entry keep the guess), then, when cg != 0, the CG
+ * phase runs from there with opt's max_iterations / tolerance (fi_field_solve).  The tile systems are solved by
+ * Jacobi-PCG on the block-diagonal matrix, all tiles at once, to a relative residual of 1e-6 (FI_F32) or 1e-12
+ * (FI_F64 / FI_MIXED) in place of the reference's per-tile Cholesky.  guess is required (the reference returns an
+ * empty vector for an incomplete guess); stats (CG phase) and tile_stats (tile phase) are nullable. */
+FI_API int fi_field_solve_tiled(fi_field* f, const fi_solve_options* opt, int32_t tile, int32_t tile_size, int32_t cg,
+                         const float* guess, float* solution, int32_t loc, fi_solve_stats* stats, fi_solve_stats* tile_stats);
+
 /* jacobi_iterations, sparse_linear.cpp:214-241: x <- w*(Atb - R x)/D + (1-w)*x, fp32. Host buffers. */
 FI_API int fi_field_jacobi(fi_field* f, const float* guess, int32_t num_iterations, float weight, float* solution);
 

@@ -561,6 +561,106 @@ void jacobi(const Normal<T>& N, T* x_io, int iterations, T weight)
 	std::copy(x.begin(), x.end(), x_io);
 }
 
+// tile_solver_square, sparse_linear.cpp:246-390.  Each tile's matrix is dense here (tile_size^D unknowns) and
+// factorised by a plain Cholesky in T — Eigen's SimplicialLLT computes the same factor up to ordering and
+// rounding.  Returns the number of failed tiles (:338,:364-365: a failed tile keeps the guess).
+template <typename T>
+int tile_solve(const Normal<T>& N, const T* guess, int ndim, const int* sizes, int tile_size, T* out)
+{
+	const int64_t        n = N.M.ncols;
+	std::vector<int>     num_tiles(ndim);
+	int64_t              tiles_total = 1, per_tile = 1;
+	for (int d = 0; d < ndim; ++d) {  // :258-266
+		num_tiles[d] = (sizes[d] + tile_size - 1) / tile_size;
+		tiles_total *= num_tiles[d];
+		per_tile *= tile_size;
+	}
+	auto locate = [&](int64_t full, int64_t* tile, int64_t* in_tile) {  // calc_tile_and_index, :270-293
+		int64_t t = 0, i = 0, ts = 1, is = 1;
+		for (int d = 0; d < ndim; ++d) {
+			const int64_t x = full % sizes[d];
+			t += (x / tile_size) * ts;
+			i += (x % tile_size) * is;
+			full /= sizes[d];
+			ts *= num_tiles[d];
+			is *= tile_size;
+		}
+		*tile    = t;
+		*in_tile = i;
+	};
+	struct Entry { int64_t r, c; T v; };
+	std::vector<std::vector<Entry>> trip(tiles_total);
+	std::vector<std::vector<T>>     rhs(tiles_total, std::vector<T>(per_tile, T(0)));
+	for (int64_t full = 0; full < n; ++full) {  // :313-318
+		int64_t t, i;
+		locate(full, &t, &i);
+		rhs[t][i] = N.atb[full];
+	}
+	for (int64_t k = 0; k < n; ++k) {  // :320-336, every stored entry (both triangles)
+		for (int64_t e = N.M.ptr[k]; e < N.M.ptr[k + 1]; ++e) {
+			const int64_t row = N.M.idx[e], col = k;
+			const T       v   = N.M.val[e];
+			int64_t       rt, ri, ct, ci;
+			locate(row, &rt, &ri);
+			locate(col, &ct, &ci);
+			if (rt == ct) {
+				trip[rt].push_back({ri, ci, v});
+			} else {
+				rhs[rt][ri] -= v * guess[col];
+				rhs[ct][ci] -= v * guess[row];
+			}
+		}
+	}
+	std::copy(guess, guess + n, out);
+	int              failures = 0;
+	std::vector<T>   A(static_cast<size_t>(per_tile * per_tile)), y(per_tile);
+	for (int64_t t = 0; t < tiles_total; ++t) {
+		if (trip[t].empty()) { continue; }  // only the regularisation: skipped (:345-348)
+		std::fill(A.begin(), A.end(), T(0));
+		for (int64_t i = 0; i < per_tile; ++i) { A[i * per_tile + i] = T(1e-6f); }  // :306-309
+		for (const Entry& e : trip[t]) { A[e.r * per_tile + e.c] += e.v; }
+		bool ok = true;  // Cholesky A = L L^T in place (lower triangle)
+		for (int64_t j = 0; j < per_tile && ok; ++j) {
+			T d = A[j * per_tile + j];
+			for (int64_t k = 0; k < j; ++k) { d -= A[j * per_tile + k] * A[j * per_tile + k]; }
+			if (!(d > T(0))) { ok = false; break; }
+			d = std::sqrt(d);
+			A[j * per_tile + j] = d;
+			for (int64_t i = j + 1; i < per_tile; ++i) {
+				T s = A[i * per_tile + j];
+				for (int64_t k = 0; k < j; ++k) { s -= A[i * per_tile + k] * A[j * per_tile + k]; }
+				A[i * per_tile + j] = s / d;
+			}
+		}
+		if (!ok) { ++failures; continue; }
+		for (int64_t i = 0; i < per_tile; ++i) {
+			T s = rhs[t][i];
+			for (int64_t k = 0; k < i; ++k) { s -= A[i * per_tile + k] * y[k]; }
+			y[i] = s / A[i * per_tile + i];
+		}
+		for (int64_t i = per_tile - 1; i >= 0; --i) {
+			T s = y[i];
+			for (int64_t k = i + 1; k < per_tile; ++k) { s -= A[k * per_tile + i] * y[k]; }
+			y[i] = s / A[i * per_tile + i];
+		}
+		for (int64_t i = 0; i < per_tile; ++i) {  // :369-386: scatter back, unknowns outside the lattice dropped
+			int64_t tc = t, ic = i, stride = 1, full = 0;
+			bool    inside = true;
+			for (int d = 0; d < ndim; ++d) {
+				const int64_t x = (tc % num_tiles[d]) * tile_size + ic % tile_size;
+				inside          = inside && x < sizes[d];
+				full += x * stride;
+				tc /= num_tiles[d];
+				ic /= tile_size;
+				stride *= sizes[d];
+			}
+			if (inside) { out[full] = y[i]; }
+		}
+	}
+	return failures;
+}
+
+
 } // namespace
 
 extern "C" {
@@ -715,6 +815,14 @@ void ora_pcg_f64(void* n, double* x, int64_t max_iter, double tol, int64_t* iter
 void ora_jacobi_f32(void* n, float* x, int iterations, float weight)
 {
 	jacobi(*static_cast<Normal<float>*>(n), x, iterations, weight);
+}
+int ora_tile_solve_f32(void* n, const float* guess, int ndim, const int* sizes, int tile_size, float* out)
+{
+	return tile_solve(*static_cast<Normal<float>*>(n), guess, ndim, sizes, tile_size, out);
+}
+int ora_tile_solve_f64(void* n, const double* guess, int ndim, const int* sizes, int tile_size, double* out)
+{
+	return tile_solve(*static_cast<Normal<double>*>(n), guess, ndim, sizes, tile_size, out);
 }
 void ora_apply_f64(void* n, const double* x, double* y)
 {

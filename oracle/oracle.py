@@ -155,6 +155,8 @@ class CpuLib:
                 "pcg_f32": (None, [vp, pf, i64, f, pi64, pf]),
                 "pcg_f64": (None, [vp, pd, i64, C.c_double, pi64, pd]),
                 "jacobi_f32": (None, [vp, pf, i, f]),
+                "tile_solve_f32": (C.c_int, [vp, pf, i, C.POINTER(C.c_int), i, pf]),
+                "tile_solve_f64": (C.c_int, [vp, pd, i, C.POINTER(C.c_int), i, pd]),
                 "apply_f64": (None, [vp, pd, pd]), "apply_f32": (None, [vp, pf, pf]),
             }
             for name, (res, args) in T.items():
@@ -235,6 +237,15 @@ class Normal:
         x = np.array(guess, dtype=np.float32, copy=True)
         self.lib.fn("jacobi_f32")(self.h, _ptr(x), int(iterations), C.c_float(weight))
         return x
+
+    def tile_solve(self, guess, sizes, tile_size):
+        """tile_solver_square, sparse_linear.cpp:246-390.  Returns (solution, failed tiles)."""
+        dt, ct, nm = (np.float32, C.c_float, "tile_solve_f32") if self.prec == 0 else (np.float64, C.c_double, "tile_solve_f64")
+        g = np.ascontiguousarray(guess, dtype=dt).ravel()
+        sz = np.ascontiguousarray(sizes, dtype=np.int32)
+        out = np.empty_like(g)
+        fails = self.lib.fn(nm)(self.h, _ptr(g, ct), len(sz), _ptr(sz, C.c_int), int(tile_size), _ptr(out, ct))
+        return out, int(fails)
 
     def apply(self, x):
         dt, ct, nm = (np.float32, C.c_float, "apply_f32") if self.prec == 0 else (np.float64, C.c_double, "apply_f64")

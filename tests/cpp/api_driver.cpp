@@ -184,6 +184,14 @@ static int scenario_sdf_2d(const char* in_path)
 	const auto approx = solve_tiled_with_guess(field.eq, sdf, {width, height}, so);
 	put_f("approx", approx);
 	put_f("bad_guess", solve_tiled_with_guess(field.eq, small, {width, height}, so));  // wrong size -> {}
+	fi::SolveOptions tiles_only;  // the demo's "tile" checkbox with CG off: tile_solver_square alone
+	tiles_only.tile = true;
+	tiles_only.tile_size = 16;
+	tiles_only.cg = false;
+	put_f("tiled", solve_tiled_with_guess(field.eq, sdf, {width, height}, tiles_only));
+	fi::SolveOptions tiles_cg = so;
+	tiles_cg.tile = true;
+	put_f("tiled_cg", solve_tiled_with_guess(field.eq, sdf, {width, height}, tiles_cg));
 	put_f("heatmap", generate_error_map(field.eq.triplets, exact, field.eq.rhs));
 	put_f("jacobi", jacobi_iterations(field.eq, sdf, 5, 0.5f));
 	return 0;

@@ -159,6 +159,12 @@ def test_sdf_2d_caller_with_border_rows_and_coarse_to_fine(tmp_path, port):
     res = np.linalg.norm(M @ got["approx"].astype(np.float64) - atb) / np.linalg.norm(atb)
     assert res <= 2e-4 and rel(got["approx"], exact) <= 5e-2
     assert got["bad_guess"].size == 0
+    # tile phase (sparse_linear.cpp:246-390) through the C++ API, against the oracle's restatement
+    g = (got["upscaled"] * np.float32(factor)).astype(np.float32)
+    want_tiled, fails = port.normal(big, width * height, "f64").tile_solve(g.astype(np.float64), [width, height], 16)
+    assert fails == 0 and rel(got["tiled"], want_tiled) <= 1e-3
+    res_tc = np.linalg.norm(M @ got["tiled_cg"].astype(np.float64) - atb) / np.linalg.norm(atb)
+    assert res_tc <= 2e-4 and rel(got["tiled_cg"], exact) <= 5e-2
     np.testing.assert_allclose(got["heatmap"], port.generate_error_map(big, got["exact"]), rtol=2e-3, atol=1e-7)
     guess = (got["upscaled"] * np.float32(factor)).astype(np.float32)
     np.testing.assert_allclose(got["jacobi"], port.normal(big, width * height, "f32").jacobi(guess, 5, 0.5), rtol=1e-4, atol=1e-4)

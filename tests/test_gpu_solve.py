@@ -283,8 +283,92 @@ def test_multigrid_with_guess_and_cap(fi, port):
     pos = W.to_lattice(cloud["unit_pos"], sizes)
     f = fi.sdf_from_points(sizes, fi.Weights(), pos, cloud["normals"])
     x, st = f.solve(fi.solve_options(fi.FI_F64, 0, 1e-10, preconditioner=fi.FI_PRECOND_MULTIGRID))
-    # restarting from the solution stops at once; a cap of 2 iterations returns the last iterate, not an error
+    # restarting from the (fp32-rounded) solution needs next to nothing; a cap of 2 iterations returns the last
+    # iterate, not an error
     _, st2 = f.solve(fi.solve_options(fi.FI_F64, 0, 1e-8, preconditioner=fi.FI_PRECOND_MULTIGRID), guess=x)
-    assert st2["converged"] and st2["iterations"] <= 1, st2
+    assert st2["converged"] and st2["iterations"] <= 3 and st2["initial_residual"] <= 1e-4, st2
     _, st3 = f.solve(fi.solve_options(fi.FI_F64, 2, 1e-12, preconditioner=fi.FI_PRECOND_MULTIGRID))
     assert not st3["converged"] and st3["iterations"] == 2, st3
+
+
+# ---- tile phase of solve_tiled_with_guess (tile_solver_square, reference sparse_linear.cpp:246-390) ----------------
+def _tile_case(port, sizes, npts, seed, **wkw):
+    D = len(sizes)
+    if D == 1:
+        rng = np.random.default_rng(seed)
+        cloud = {"unit_pos": rng.uniform(0.05, 0.95, (npts, 1)).astype(np.float32),
+                 "normals": np.where(rng.uniform(size=(npts, 1)) < 0.5, -1.0, 1.0).astype(np.float32)}
+    else:
+        cloud = W.circles_2d(npts, seed=seed) if D == 2 else W.sphere_torus_3d(npts, seed=seed)
+    pos = W.to_lattice(cloud["unit_pos"], sizes)
+    sys_ = port.sdf_from_points(sizes, O.make_weights(**wkw), pos, cloud["normals"]).system()
+    return pos, cloud["normals"], sys_
+
+
+@pytest.mark.parametrize("sizes,tile,npts,wkw", [
+    ([50], 16, 12, {}), ([40, 37], 16, 400, {}), ([33, 20], 8, 200, dict(model_1=0.3, gradient_smoothness=0.2)),
+    ([16, 16], 16, 100, {}), ([18, 15, 17], 4, 900, {}), ([24, 20, 22], 8, 1500, dict(gradient_kernel=2)),
+    ([21, 22], 5, 300, dict(model_2=0.0, model_3=0.4, value_kernel=0))])
+def test_tile_phase_matches_reference_tile_solver(fi, port, sizes, tile, npts, wkw):
+    """Tile phase alone (cg off) against the oracle's restatement of tile_solver_square, float and double."""
+    pos, nrm, sys_ = _tile_case(port, sizes, npts, 11, **wkw)
+    n = int(np.prod(sizes))
+    f = fi.sdf_from_points(sizes, fi.Weights(**wkw), pos, nrm)
+    rng = np.random.default_rng(3)
+    guess = rng.normal(size=n).astype(np.float32)
+    opts = fi.SolveOptions(tile=True, tile_size=tile, cg=False)
+    want64, fails = port.normal(sys_, n, "f64").tile_solve(guess.astype(np.float64), sizes, tile)
+    assert fails == 0
+    got64, _, tst = fi.solve_tiled_with_guess(f, guess, sizes, opts, precision=fi.FI_F64, return_stats=True)
+    assert tst["converged"], tst
+    assert rel(got64, want64) <= TOL_F64, tst
+    got32 = fi.solve_tiled_with_guess(f, guess, sizes, opts)
+    assert rel(got32, want64) <= TOL_F32
+    want32, fails32 = port.normal(sys_, n, "f32").tile_solve(guess, sizes, tile)  # what the reference computes, in float
+    assert fails32 == 0 and rel(got32, want32) <= 2 * TOL_F32
+
+
+def test_tile_phase_then_cg_and_degenerate_options(fi, port):
+    sizes, tile = [40, 37], 16
+    pos, nrm, sys_ = _tile_case(port, sizes, 400, 5)
+    n = int(np.prod(sizes))
+    f = fi.sdf_from_points(sizes, fi.Weights(), pos, nrm)
+    exact = O.exact_solve(sys_, n)
+    guess = np.zeros(n, np.float32)
+    # neither phase: the guess comes back (sparse_linear.cpp:423-440 with both flags off)
+    assert np.array_equal(fi.solve_tiled_with_guess(f, guess + 2, sizes, fi.SolveOptions(tile=False, cg=False)), guess + 2)
+    # incomplete guess -> empty result (:402-405)
+    assert fi.solve_tiled_with_guess(f, guess[:-1], sizes, fi.SolveOptions()).size == 0
+    # tile + cg: the CG phase starts from the tile solution and reaches the exact solve
+    x, st, tst = fi.solve_tiled_with_guess(f, guess, sizes, fi.SolveOptions(tile=True, tile_size=tile, cg=True, error_tolerance=1e-7),
+                                           return_stats=True)
+    assert rel(x, exact) <= TOL_F32, (st, tst)
+    tiled = fi.solve_tiled_with_guess(f, guess, sizes, fi.SolveOptions(tile=True, tile_size=tile, cg=False))
+    M, atb = O.normal_equations_f64(sys_, n)
+    r_tiled = np.linalg.norm(atb - M @ tiled.astype(np.float64)) / np.linalg.norm(atb)
+    assert abs(st["initial_residual"] - r_tiled) <= 1e-3 * r_tiled + 1e-6
+    # the operator is back in its normal state after a tile phase: a plain solve still matches
+    x2, st2 = f.solve(fi.solve_options(fi.FI_F64, 0, 1e-11))
+    assert st2["converged"] and rel(x2, exact) <= TOL_F64
+
+
+def test_tile_phase_points_only_and_caller_rows(fi, port):
+    """No smoothness: tiles no row touches keep the guess (:345-348), untouched nodes of touched tiles become 0; plus
+    caller-appended rows that span tiles (generic-rows path)."""
+    sizes, tile = [16, 16], 4
+    of = port.field(sizes)
+    of.add_value_constraint([1.5, 2.5], 3.0, 1.0)
+    of.add_value_constraint([2.25, 1.75], -1.0, 2.0)
+    of.add_value_constraint([3.5, 3.5], 0.5, 1.0)      # straddles four tiles
+    of.add_equation(1.5, 2.0, [5, 200, 77], [1.0, -1.0, 0.5])  # a caller row across three tiles
+    sys_ = of.system()
+    f = fi.LatticeField(sizes)
+    for p, v, w in (([1.5, 2.5], 3.0, 1.0), ([2.25, 1.75], -1.0, 2.0), ([3.5, 3.5], 0.5, 1.0)):
+        assert fi.add_value_constraint(f, p, v, w)
+    fi.add_equation(f, 1.5, 2.0, [(5, 1.0), (200, -1.0), (77, 0.5)])
+    guess = np.arange(256, dtype=np.float32) / 16
+    want, fails = port.normal(sys_, 256, "f64").tile_solve(guess.astype(np.float64), sizes, tile)
+    got = fi.solve_tiled_with_guess(f, guess, sizes, fi.SolveOptions(tile=True, tile_size=tile, cg=False), precision=fi.FI_F64)
+    assert fails == 0 and rel(got, want) <= TOL_F64
+    untouched_tiles = np.isclose(want, guess.astype(np.float64)) & (guess != 0)
+    assert untouched_tiles.sum() > 100 and np.array_equal(got[untouched_tiles], guess[untouched_tiles])
