@@ -696,6 +696,58 @@ __global__ void __launch_bounds__(kThreads, 3) apply_blocks_kernel(Geom g, int64
 	}
 }
 
+// Epilogue form for the multigrid smoother: u = P in over the occupied cells, then res -= u and (d_new given)
+// d_new -= b minv u, e -= b minv u.
+template <typename T, int D>
+__global__ void __launch_bounds__(kThreads, 3) apply_blocks_epilogue_kernel(Geom g, int64_t nocc, const int64_t* __restrict__ cell_base,
+                                                                         const uint32_t* __restrict__ cell_mask, const T* __restrict__ blocks,
+                                                                         const T* __restrict__ in, T* res, const T* __restrict__ minv, T* e,
+                                                                         T* d_new, T b)
+{
+	constexpr int C  = 1 << D;
+	constexpr int NT = C * (C + 1) / 2;
+	const int64_t cell = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (cell >= nocc) { return; }
+	T blk[NT];
+#pragma unroll
+	for (int t = 0; t < NT; ++t) { blk[t] = __ldcs(&blocks[static_cast<size_t>(t) * nocc + cell]); }
+	const int64_t  base = cell_base[cell];
+	const uint32_t mask = cell_mask[cell];
+	T pc[C], out[C];
+	int64_t off[C];
+#pragma unroll
+	for (int c = 0; c < C; ++c) {
+		off[c] = 0;
+#pragma unroll
+		for (int d = 0; d < D; ++d) { off[c] += ((c >> d) & 1) ? g.stride[d] : 0; }
+		pc[c]  = ((mask >> c) & 1u) ? in[base + off[c]] : T(0);
+		out[c] = 0;
+	}
+	int tri = 0;
+#pragma unroll
+	for (int ci = 0; ci < C; ++ci) {
+#pragma unroll
+		for (int cj = ci; cj < C; ++cj) {
+			const T v = blk[tri];
+			out[ci] += v * pc[cj];
+			if (cj != ci) { out[cj] += v * pc[ci]; }
+			++tri;
+		}
+	}
+#pragma unroll
+	for (int c = 0; c < C; ++c) {
+		if ((mask >> (8 + c)) & 1u) {
+			const int64_t node = base + off[c];
+			atomic_add(&res[node], -out[c]);
+			if (d_new) {
+				const T dd = -b * minv[node] * out[c];
+				atomic_add(&d_new[node], dd);
+				atomic_add(&e[node], dd);
+			}
+		}
+	}
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads) apply_rows_kernel(int64_t nrows, const uint64_t* __restrict__ row_ptr,
                                                               const int32_t* __restrict__ col, const float* __restrict__ val,
@@ -958,6 +1010,23 @@ void apply_data_term(const Geom& g, const DataTerm<T>& dt, const T* p, T* q, dou
 	}
 }
 
+template <typename T>
+bool apply_data_term_epilogue(const Geom& g, const DataTerm<T>& dt, const T* in, T* res_out, const T* minv, T* e, T* d_new, T b,
+                              cudaStream_t s)
+{
+	if (dt.nrows > 0 || g.tile || g.sharded()) { return false; }
+	if (dt.nocc > 0) {
+		by_dim(g.ndim, [&](auto dim) {
+			auto kern = apply_blocks_epilogue_kernel<T, decltype(dim)::value>;
+			FI_LAUNCH(kern, div_up(dt.nocc, kThreads), kThreads, 0, s, g, dt.nocc, dt.cell_base.data(), dt.cell_mask.data(), dt.blocks.data(), in,
+			          res_out, minv, e, d_new, b);
+		});
+	}
+	return true;
+}
+
+template bool apply_data_term_epilogue<float>(const Geom&, const DataTerm<float>&, const float*, float*, const float*, float*, float*, float,
+                                              cudaStream_t);
 template void build_data_term<float>(const Geom&, const PointStore&, const HostRows&, DataTerm<float>&, float*, float*, cudaStream_t);
 template void build_data_term<double>(const Geom&, const PointStore&, const HostRows&, DataTerm<double>&, double*, double*, cudaStream_t);
 template void apply_data_term<float>(const Geom&, const DataTerm<float>&, const float*, float*, double*, const int*, cudaStream_t);

@@ -156,6 +156,13 @@ template <typename T>
 void apply_data_term(const Geom& g, const DataTerm<T>& dt, const T* p, T* q, double* d_dot_accum, const int* d_done,
                      cudaStream_t s);
 
+// The data term's share of the epilogue-mode stencil step (stencil_tma_3d_epilogue): with u = P in,
+// res_out -= u and, when d_new is given, d_new -= b minv u, e -= b minv u — by atomics over the occupied cells.
+// Cell blocks only: false (nothing done) when the data term has generic rows.
+template <typename T>
+bool apply_data_term_epilogue(const Geom& g, const DataTerm<T>& dt, const T* in, T* res_out, const T* minv, T* e, T* d_new, T b,
+                              cudaStream_t s);
+
 // ---- errormap.cu ------------------------------------------------------------------------------------------
 void error_map(int64_t nt, const fi_triplet* h_trips, int64_t n, const float* h_x, int64_t nrows, const float* h_rhs, float* h_out);
 

@@ -40,16 +40,17 @@ __global__ void coarsen_points_kernel(int D, int64_t n, const float* __restrict_
 }
 
 // ---- smoother ----------------------------------------------------------------------------------------------------
-// One Chebyshev step: res -= q (when q is given), d = a d + b M^-1 res, e += d.
-__global__ void __launch_bounds__(kThreads) cheb_step_kernel(int64_t n, float* __restrict__ res, const float* __restrict__ q, float* __restrict__ d,
-                                                             const float* __restrict__ minv, float* __restrict__ e, float a, float b, int e_is_zero)
+// One Chebyshev step: res_out = res_in - q (when q is given), d = a d + b M^-1 res, e += d.  res_in / res_out may alias.
+__global__ void __launch_bounds__(kThreads) cheb_step_kernel(int64_t n, const float* res_in, float* res_out, const float* __restrict__ q,
+                                                             float* __restrict__ d, const float* __restrict__ minv, float* __restrict__ e, float a, float b,
+                                                             int e_is_zero)
 {
 	const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
 	for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-		float r = res[i];
+		float r = res_in[i];
 		if (q) {
 			r -= q[i];
-			res[i] = r;
+			res_out[i] = r;
 		}
 		const float dn = (a != 0.0f ? a * d[i] : 0.0f) + b * minv[i] * r;
 		d[i]           = dn;
@@ -65,96 +66,76 @@ __global__ void __launch_bounds__(kThreads) residual_sub_kernel(int64_t n, const
 }
 
 // ---- transfers -----------------------------------------------------------------------------------------------------
-struct Xfer  // fine <-> coarse geometry of one level pair
+// Prolongation is upscale_field's multilinear, align-corners interpolation (field_interpolation.cpp:431-485): fine node
+// i of an axis sits at coarse position t = i * (nc - 1) / (nf - 1), between coarse nodes floor(t) and floor(t) + 1.
+// The per-axis tables are computed once on the host in double precision; both kernels read the same tables, so
+// restriction is exactly the transpose of prolongation.
+constexpr int kMaxFan = 6;  // fine nodes of one axis whose interpolation touches one coarse node (4 for a 2:1 ratio)
+
+struct Xfer  // fine <-> coarse geometry of one level pair; unused axes have nf = nc = 1
 {
-	int    D;
-	int    nf[kMaxDim], nc[kMaxDim];
-	double s[kMaxDim];  // coarse position of fine node i = i * s  (upscale_field: coord * (small - 1) / (large - 1))
+	int          nf[kMaxDim], nc[kMaxDim];
+	const int*   base[kMaxDim];   // [nf]  lower coarse node of fine node i
+	const float* frac[kMaxDim];   // [nf]  weight of the upper coarse node (lower gets 1 - frac)
+	const int*   first[kMaxDim];  // [nc]  first fine node with a non-zero weight on coarse node C
+	const int*   count[kMaxDim];  // [nc]  how many consecutive fine nodes
+	const float* weight[kMaxDim]; // [nc][kMaxFan]
 };
 
-// e_f += P e_c : every fine node gathers its 2^D coarse neighbours.
-__global__ void __launch_bounds__(kThreads) prolong_add_kernel(Xfer x, int64_t nfine, const float* __restrict__ ec, float* __restrict__ ef)
+// e_f += P e_c : every fine node gathers its 2^D coarse neighbours.  Block = 128 threads along x; y and z come from
+// the block index (no integer division per node).
+__global__ void __launch_bounds__(128) prolong_add_kernel(Xfer x, const float* __restrict__ ec, float* __restrict__ ef)
 {
-	const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-	if (i >= nfine) { return; }
-	int64_t rem = i;
-	int     base[kMaxDim] = {0, 0, 0};
-	float   fr[kMaxDim]   = {0, 0, 0};
-	for (int d = 0; d < x.D; ++d) {
-		const int c = static_cast<int>(rem % x.nf[d]);
-		rem /= x.nf[d];
-		const double t = c * x.s[d];
-		int          b = static_cast<int>(t);
-		if (b > x.nc[d] - 1) { b = x.nc[d] - 1; }
-		base[d] = b;
-		fr[d]   = static_cast<float>(t - b);
-	}
-	float acc = 0.0f;
-	for (int corner = 0; corner < (1 << x.D); ++corner) {
-		float   w   = 1.0f;
-		int64_t idx = 0, str = 1;
-		bool    ok  = true;
-		for (int d = 0; d < x.D; ++d) {
-			const int bit = (corner >> d) & 1;
-			const int c   = base[d] + bit;
-			w *= bit ? fr[d] : 1.0f - fr[d];
-			ok = ok && c < x.nc[d];
-			idx += str * c;
-			str *= x.nc[d];
-		}
-		if (ok && w != 0.0f) { acc += w * ec[idx]; }
-	}
+	const int ix = blockIdx.x * 128 + threadIdx.x, iy = blockIdx.y, iz = blockIdx.z;
+	if (ix >= x.nf[0]) { return; }
+	const int   bx = __ldg(x.base[0] + ix), by = __ldg(x.base[1] + iy), bz = __ldg(x.base[2] + iz);
+	const float fx = __ldg(x.frac[0] + ix), fy = __ldg(x.frac[1] + iy), fz = __ldg(x.frac[2] + iz);
+	// the upper neighbour of the last node does not exist; its weight is zero, the clamped read is harmless
+	const int   bx1 = min(bx + 1, x.nc[0] - 1), by1 = min(by + 1, x.nc[1] - 1), bz1 = min(bz + 1, x.nc[2] - 1);
+	const int64_t sy = x.nc[0], sz = static_cast<int64_t>(x.nc[0]) * x.nc[1];
+	const float*  p00 = ec + bz * sz + by * sy;
+	const float*  p01 = ec + bz * sz + by1 * sy;
+	const float*  p10 = ec + bz1 * sz + by * sy;
+	const float*  p11 = ec + bz1 * sz + by1 * sy;
+	const float   gx = 1.0f - fx, gy = 1.0f - fy, gz = 1.0f - fz;
+	const float   v00 = gx * __ldg(p00 + bx) + fx * __ldg(p00 + bx1);
+	const float   v01 = gx * __ldg(p01 + bx) + fx * __ldg(p01 + bx1);
+	const float   v10 = gx * __ldg(p10 + bx) + fx * __ldg(p10 + bx1);
+	const float   v11 = gx * __ldg(p11 + bx) + fx * __ldg(p11 + bx1);
+	const float   acc = gz * (gy * v00 + fy * v01) + fz * (gy * v10 + fy * v11);
+	const int64_t i   = (static_cast<int64_t>(iz) * x.nf[1] + iy) * x.nf[0] + ix;
 	ef[i] += acc;
 }
 
-// r_c = P^T res_f : every coarse node gathers the fine nodes whose interpolation stencil contains it, with exactly
-// the weights prolong_add_kernel uses (same double-precision position arithmetic), so that R = P^T.
-__global__ void __launch_bounds__(kThreads) restrict_kernel(Xfer x, int64_t ncoarse, const float* __restrict__ rf, float* __restrict__ rc)
+// r_c = P^T res_f : every coarse node gathers the fine nodes whose interpolation touches it.
+__global__ void __launch_bounds__(128) restrict_kernel(Xfer x, const float* __restrict__ rf, float* __restrict__ rc)
 {
-	const int64_t I = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-	if (I >= ncoarse) { return; }
-	int64_t rem = I;
-	int     cnt[kMaxDim] = {1, 1, 1};
-	int     idx[kMaxDim][6];
-	float   w[kMaxDim][6];
-	for (int d = 0; d < kMaxDim; ++d) {
-		idx[d][0] = 0;
-		w[d][0]   = 1.0f;
-	}
-	for (int d = 0; d < x.D; ++d) {
-		const int C = static_cast<int>(rem % x.nc[d]);
-		rem /= x.nc[d];
-		int first = 0, last = x.nf[d] - 1;
-		if (x.s[d] > 0.0) {  // fine nodes i with |i * s - C| < 1, plus a node of slack either side
-			first = max(first, static_cast<int>(floor((C - 1) / x.s[d])) - 1);
-			last  = min(last, static_cast<int>(ceil((C + 1) / x.s[d])) + 1);
-		}
-		int n = 0;
-		for (int i = first; i <= last && n < 6; ++i) {
-			const double t = i * x.s[d];
-			int          b = static_cast<int>(t);
-			if (b > x.nc[d] - 1) { b = x.nc[d] - 1; }
-			const float fr = static_cast<float>(t - b);
-			float       wt = 0.0f;
-			if (b == C) { wt = 1.0f - fr; } else if (b + 1 == C) { wt = fr; }
-			if (wt != 0.0f) {
-				idx[d][n] = i;
-				w[d][n]   = wt;
-				++n;
-			}
-		}
-		cnt[d] = n;
-	}
-	float         acc = 0.0f;
+	const int cx = blockIdx.x * 128 + threadIdx.x, cy = blockIdx.y, cz = blockIdx.z;
+	if (cx >= x.nc[0]) { return; }
+	const int    x0 = __ldg(x.first[0] + cx), y0 = __ldg(x.first[1] + cy), z0 = __ldg(x.first[2] + cz);
+	const int    nx = __ldg(x.count[0] + cx), ny = __ldg(x.count[1] + cy), nz = __ldg(x.count[2] + cz);
+	const float* wx = x.weight[0] + static_cast<size_t>(cx) * kMaxFan;
+	const float* wy = x.weight[1] + static_cast<size_t>(cy) * kMaxFan;
+	const float* wz = x.weight[2] + static_cast<size_t>(cz) * kMaxFan;
+	float wxr[kMaxFan];
+#pragma unroll
+	for (int i = 0; i < kMaxFan; ++i) { wxr[i] = i < nx ? __ldg(wx + i) : 0.0f; }
 	const int64_t sy = x.nf[0], sz = static_cast<int64_t>(x.nf[0]) * x.nf[1];
-	for (int k = 0; k < cnt[2]; ++k) {
-		for (int j = 0; j < cnt[1]; ++j) {
-			const float   wyz = w[2][k] * w[1][j];
-			const int64_t row = idx[2][k] * sz + idx[1][j] * sy;
-			for (int i = 0; i < cnt[0]; ++i) { acc += wyz * w[0][i] * rf[row + idx[0][i]]; }
+	float acc = 0.0f;
+	for (int k = 0; k < nz; ++k) {
+		const float wk = __ldg(wz + k);
+		for (int j = 0; j < ny; ++j) {
+			const float  wkj = wk * __ldg(wy + j);
+			const float* row = rf + (z0 + k) * sz + (y0 + j) * sy + x0;
+			float        s   = 0.0f;
+#pragma unroll
+			for (int i = 0; i < kMaxFan; ++i) {
+				if (i < nx) { s += wxr[i] * __ldg(row + i); }
+			}
+			acc += wkj * s;
 		}
 	}
-	rc[I] = acc;
+	rc[(static_cast<int64_t>(cz) * x.nc[1] + cy) * x.nc[0] + cx] = acc;
 }
 
 // ---- coarsest level: e = Ainv r (dense, one block per row) --------------------------------------------------------
@@ -326,10 +307,71 @@ struct Multigrid::Level
 	Operator<float>*                 op = nullptr;   // level 0: the caller's operator; coarser: owned below
 	std::unique_ptr<Operator<float>> owned;
 	PointStore                       pts;
-	DevBuf<float>                    r, e, res, d, q;  // r / e of level 0 are the caller's vectors
+	DevBuf<float>                    r, e, res, d, d2, q;  // r / e of level 0 are the caller's vectors; d / d2 ping-pong
 	double                           lmax = 0;
 	Xfer                             to_coarser;     // this level (fine) -> next level (coarse)
+	DevBuf<int>                      xfer_int;       // backing store of to_coarser's tables
+	DevBuf<float>                    xfer_float;
 };
+
+namespace {
+
+// Per-axis interpolation tables of the pair (lv = fine, gc = coarse); the arithmetic is upscale_field's position rule
+// evaluated in double.
+void build_xfer(Multigrid::Level& lv, const Geom& gc, cudaStream_t s)
+{
+	Xfer&            x = lv.to_coarser;
+	std::vector<int>   hi;
+	std::vector<float> hf;
+	size_t off_base[kMaxDim], off_first[kMaxDim], off_count[kMaxDim], off_frac[kMaxDim], off_weight[kMaxDim];
+	for (int d = 0; d < kMaxDim; ++d) {
+		const int nf = d < lv.g.ndim ? lv.g.size[d] : 1, nc = d < lv.g.ndim ? gc.size[d] : 1;
+		x.nf[d] = nf;
+		x.nc[d] = nc;
+		const double sc = nf > 1 ? static_cast<double>(nc - 1) / static_cast<double>(nf - 1) : 0.0;
+		std::vector<int>   base(nf), first(nc, 0), count(nc, 0);
+		std::vector<float> frac(nf), weight(static_cast<size_t>(nc) * kMaxFan, 0.0f);
+		for (int i = 0; i < nf; ++i) {
+			const double t = i * sc;
+			int          b = static_cast<int>(t);
+			if (b > nc - 1) { b = nc - 1; }
+			base[i] = b;
+			frac[i] = static_cast<float>(t - b);
+		}
+		for (int i = 0; i < nf; ++i) {  // transpose: scatter every fine node's two weights to its coarse nodes
+			const int   b = base[i];
+			const float w[2] = {1.0f - frac[i], frac[i]};
+			for (int k = 0; k < 2; ++k) {
+				const int C = b + k;
+				if (C >= nc || w[k] == 0.0f) { continue; }
+				if (count[C] == 0) { first[C] = i; }
+				const int at = i - first[C];
+				FI_REQUIRE(at < kMaxFan, FI_ERR_UNSUPPORTED, "multigrid: coarsening ratio too large for the transfer tables");
+				weight[static_cast<size_t>(C) * kMaxFan + at] = w[k];
+				count[C] = at + 1;
+			}
+		}
+		off_base[d]  = hi.size(); hi.insert(hi.end(), base.begin(), base.end());
+		off_first[d] = hi.size(); hi.insert(hi.end(), first.begin(), first.end());
+		off_count[d] = hi.size(); hi.insert(hi.end(), count.begin(), count.end());
+		off_frac[d]   = hf.size(); hf.insert(hf.end(), frac.begin(), frac.end());
+		off_weight[d] = hf.size(); hf.insert(hf.end(), weight.begin(), weight.end());
+	}
+	lv.xfer_int.resize(hi.size());
+	lv.xfer_float.resize(hf.size());
+	FI_CUDA(cudaMemcpyAsync(lv.xfer_int.data(), hi.data(), hi.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+	FI_CUDA(cudaMemcpyAsync(lv.xfer_float.data(), hf.data(), hf.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+	FI_CUDA(cudaStreamSynchronize(s));  // the host vectors go out of scope
+	for (int d = 0; d < kMaxDim; ++d) {
+		x.base[d]   = lv.xfer_int.data() + off_base[d];
+		x.first[d]  = lv.xfer_int.data() + off_first[d];
+		x.count[d]  = lv.xfer_int.data() + off_count[d];
+		x.frac[d]   = lv.xfer_float.data() + off_frac[d];
+		x.weight[d] = lv.xfer_float.data() + off_weight[d];
+	}
+}
+
+}  // namespace
 
 Multigrid::Multigrid()  = default;
 Multigrid::~Multigrid()
@@ -356,15 +398,16 @@ std::unique_ptr<Multigrid> build_multigrid(Operator<float>& fine, const ModelAcc
 		int32_t     nc[kMaxDim] = {1, 1, 1};
 		int64_t     cells = 1;
 		bool        shrunk = false;
-		int         smallest = 1 << 30;
+		int         smallest_next = 1 << 30;
 		for (int d = 0; d < D; ++d) {
 			nc[d] = (gf.size[d] + 1) / 2;
 			shrunk = shrunk || nc[d] < gf.size[d];
 			cells *= nc[d];
-			if (gf.size[d] > 1) { smallest = std::min(smallest, gf.size[d]); }
+			if (gf.size[d] > 1) { smallest_next = std::min(smallest_next, nc[d]); }
 		}
-		// stop once the current level is small enough for the dense solve
-		if (gf.N <= opt.coarsest_cells || !shrunk || smallest <= 2) { break; }
+		// stop once the current level is small enough for the dense solve, or the next one would have fewer than 4 nodes
+		// along an axis (too few for the higher-order difference rows to mean anything)
+		if (gf.N <= opt.coarsest_cells || !shrunk || smallest_next < 4) { break; }
 		auto lv = std::make_unique<Multigrid::Level>();
 		lv->g   = make_geom(D, nc);
 		mg->levels.push_back(std::move(lv));
@@ -418,14 +461,9 @@ std::unique_ptr<Multigrid> build_multigrid(Operator<float>& fine, const ModelAcc
 		if (l < L - 1) {
 			lv.res.resize(n);
 			lv.d.resize(n);
+			lv.d2.resize(n);
 			lv.q.resize(n);
-			Xfer& x = lv.to_coarser;
-			x.D     = D;
-			for (int d = 0; d < kMaxDim; ++d) {
-				x.nf[d] = lv.g.size[d];
-				x.nc[d] = mg->levels[l + 1]->g.size[d];
-				x.s[d]  = x.nf[d] > 1 ? static_cast<double>(x.nc[d] - 1) / static_cast<double>(x.nf[d] - 1) : 0.0;
-			}
+			build_xfer(lv, mg->levels[l + 1]->g, s);
 		}
 	}
 	// largest eigenvalue of D^-1 A per smoothed level: power iteration
@@ -490,29 +528,57 @@ std::unique_ptr<Multigrid> build_multigrid(Operator<float>& fine, const ModelAcc
 
 namespace {
 
-// nu Chebyshev steps on A e = r at one level.  e_zero: e starts at zero (pre-smoothing).  On return lv.res holds the
-// residual *before* the last correction d (so r - A e = res - A d).
-void smooth(Multigrid::Level& lv, const MgOptions& opt, const float* r, float* e, bool e_zero, cudaStream_t s)
+// res_out = res_in - A in and, with d_new, d_new = a in + b M^-1 res_out, e += d_new, in one pass over the level
+// (TMA stencil kernel in epilogue mode + the data term's fix-up).  false: not applicable here, nothing was done.
+bool fused_step(Multigrid::Level& lv, const float* in, const float* res_in, float* res_out, float* e, float* d_new, float a, float b, cudaStream_t s)
+{
+	Operator<float>& op = *lv.op;
+	if (op.data.nrows > 0 || op.use_fast != kStencilAuto) { return false; }
+	if (!stencil_tma_3d_epilogue<float>(op.g, op.tabs, in, res_in, res_out, op.minv.data(), e, d_new, a, b, s)) { return false; }
+	const bool ok = apply_data_term_epilogue<float>(op.g, op.data, in, res_out, op.minv.data(), e, d_new, b, s);
+	FI_REQUIRE(ok, FI_ERR_UNSUPPORTED, "multigrid: data-term epilogue refused after the stencil epilogue ran");
+	return true;
+}
+
+struct Smoothed
+{
+	const float* res;  // residual before the last correction: r - A e = res - A d
+	float*       d;    // the last correction
+};
+
+// nu Chebyshev steps on A e = r at one level.  e_zero: e starts at zero (pre-smoothing).
+Smoothed smooth(Multigrid::Level& lv, const MgOptions& opt, const float* r, float* e, bool e_zero, cudaStream_t s)
 {
 	const int64_t n     = lv.g.N;
 	const double  lmax  = lv.lmax, lmin = lmax / opt.cheb_ratio;
 	const double  theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
-	if (e_zero) {
-		FI_CUDA(cudaMemcpyAsync(lv.res.data(), r, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+	float *       d = lv.d.data(), *d_other = lv.d2.data(), *res = lv.res.data();
+	const float*  res_src = r;
+	const float   b0 = static_cast<float>(1.0 / theta);
+	if (e_zero) {  // res = r: d = b0 M^-1 r, e = d
+		FI_LAUNCH(cheb_step_kernel, vgrid(n), kThreads, 0, s, n, r, res, static_cast<const float*>(nullptr), d, lv.op->minv.data(), e, 0.0f, b0, 1);
+	} else if (fused_step(lv, e, r, res, nullptr, nullptr, 0.0f, 0.0f, s)) {  // res = r - A e, then the first step from it
+		FI_LAUNCH(cheb_step_kernel, vgrid(n), kThreads, 0, s, n, res, res, static_cast<const float*>(nullptr), d, lv.op->minv.data(), e, 0.0f, b0, 0);
+		res_src = res;
 	} else {
 		lv.op->apply(e, lv.q.data(), nullptr, nullptr, s);
-		FI_LAUNCH(residual_sub_kernel, vgrid(n), kThreads, 0, s, n, r, lv.q.data(), lv.res.data());
+		FI_LAUNCH(cheb_step_kernel, vgrid(n), kThreads, 0, s, n, r, res, static_cast<const float*>(lv.q.data()), d, lv.op->minv.data(), e, 0.0f, b0, 0);
+		res_src = res;
 	}
 	double rho = 1.0 / sigma;
-	FI_LAUNCH(cheb_step_kernel, vgrid(n), kThreads, 0, s, n, lv.res.data(), static_cast<const float*>(nullptr), lv.d.data(), lv.op->minv.data(), e, 0.0f,
-	          static_cast<float>(1.0 / theta), e_zero ? 1 : 0);
 	for (int k = 1; k < opt.nu; ++k) {
 		const double rho_new = 1.0 / (2.0 * sigma - rho);
-		lv.op->apply(lv.d.data(), lv.q.data(), nullptr, nullptr, s);
-		FI_LAUNCH(cheb_step_kernel, vgrid(n), kThreads, 0, s, n, lv.res.data(), static_cast<const float*>(lv.q.data()), lv.d.data(), lv.op->minv.data(), e,
-		          static_cast<float>(rho_new * rho), static_cast<float>(2.0 * rho_new / delta), 0);
-		rho = rho_new;
+		const float  a = static_cast<float>(rho_new * rho), b = static_cast<float>(2.0 * rho_new / delta);
+		if (fused_step(lv, d, res_src, res, e, d_other, a, b, s)) {
+			std::swap(d, d_other);
+		} else {
+			lv.op->apply(d, lv.q.data(), nullptr, nullptr, s);
+			FI_LAUNCH(cheb_step_kernel, vgrid(n), kThreads, 0, s, n, res_src, res, static_cast<const float*>(lv.q.data()), d, lv.op->minv.data(), e, a, b, 0);
+		}
+		res_src = res;
+		rho     = rho_new;
 	}
+	return Smoothed{res_src, d};
 }
 
 void vcycle_level(Multigrid& mg, int l, const float* r, float* e, cudaStream_t s)
@@ -524,13 +590,21 @@ void vcycle_level(Multigrid& mg, int l, const float* r, float* e, cudaStream_t s
 		return;
 	}
 	Multigrid::Level& lc = *mg.levels[l + 1];
-	smooth(lv, mg.opt, r, e, true, s);
+	const Smoothed    sm = smooth(lv, mg.opt, r, e, true, s);
 	// residual after the last correction, restricted
-	lv.op->apply(lv.d.data(), lv.q.data(), nullptr, nullptr, s);
-	FI_LAUNCH(residual_sub_kernel, vgrid(lv.g.N), kThreads, 0, s, lv.g.N, lv.res.data(), lv.q.data(), lv.res.data());
-	FI_LAUNCH(restrict_kernel, div_up(lc.g.N, kThreads), kThreads, 0, s, lv.to_coarser, lc.g.N, lv.res.data(), lc.r.data());
+	if (!fused_step(lv, sm.d, sm.res, lv.res.data(), nullptr, nullptr, 0.0f, 0.0f, s)) {
+		lv.op->apply(sm.d, lv.q.data(), nullptr, nullptr, s);
+		FI_LAUNCH(residual_sub_kernel, vgrid(lv.g.N), kThreads, 0, s, lv.g.N, sm.res, lv.q.data(), lv.res.data());
+	}
+	{
+		const Xfer& x = lv.to_coarser;
+		FI_LAUNCH(restrict_kernel, dim3(div_up(x.nc[0], 128), x.nc[1], x.nc[2]), 128, 0, s, x, lv.res.data(), lc.r.data());
+	}
 	vcycle_level(mg, l + 1, lc.r.data(), lc.e.data(), s);
-	FI_LAUNCH(prolong_add_kernel, div_up(lv.g.N, kThreads), kThreads, 0, s, lv.to_coarser, lv.g.N, lc.e.data(), e);
+	{
+		const Xfer& x = lv.to_coarser;
+		FI_LAUNCH(prolong_add_kernel, dim3(div_up(x.nf[0], 128), x.nf[1], x.nf[2]), 128, 0, s, x, lc.e.data(), e);
+	}
 	smooth(lv, mg.opt, r, e, false, s);
 }
 

@@ -147,6 +147,12 @@ bool stencil_tma_3d_fused(const Geom& g, const StencilTables& t, const T* r, con
                           const PcgState* st, int par, double* d_dot_out, double* d_partial, unsigned* d_ticket, const int* d_done,
                           cudaStream_t s);
 
+// stencil_tma.cu, epilogue mode (multigrid smoother): res_out = res_in - S in; with d_new: d_new = a in + b minv res_out,
+// e += d_new.  Nothing else is stored.  false: not applicable (then the caller uses apply + vector kernels).
+template <typename T>
+bool stencil_tma_3d_epilogue(const Geom& g, const StencilTables& t, const T* in, const T* res_in, T* res_out, const T* minv, T* e, T* d_new,
+                             T a, T b, cudaStream_t s);
+
 // The fused direction+stencil step in the given StencilMode; false when no fused kernel applies.
 template <typename T>
 inline bool stencil_fused_step(int mode, const Geom& g, const StencilTables& t, const T* r, const T* minv, const T* p_old, T* p_new,
@@ -164,7 +170,7 @@ struct MgOptions
 {
 	int    nu               = 3;     // Chebyshev steps before and after the coarse-grid correction
 	double cheb_ratio       = 12.0;  // the smoother targets the eigenvalues of D^-1 A in [lambda_max / ratio, lambda_max]
-	int    coarsest_cells   = 600;   // coarsen until a level has at most this many cells (dense solve there)
+	int    coarsest_cells   = 150;   // coarsen until a level has at most this many cells (dense solve there; the host inverts it)
 	int    power_iterations = 12;    // for lambda_max, per level, at setup
 };
 

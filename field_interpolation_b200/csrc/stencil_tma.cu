@@ -56,6 +56,22 @@ struct TmaTables
 	T band[kMaxDim][9][9];
 };
 
+// Epilogue mode (the multigrid smoother, mg.cu): instead of storing q = S p the kernel consumes it in place,
+//     res_out = res_in - q;   and, when d_new is given,   d_new = a p + b M^-1 res_out,   e += d_new,
+// i.e. one Chebyshev step (or a plain residual update) per pass over the lattice.  The pointwise operands of a
+// thread's own pack are prefetched one plane ahead into registers.  res_in / res_out and e are updated pointwise
+// and may alias; d_new must not alias the stencil input.
+template <typename T>
+struct EpiArgs
+{
+	const T* res_in = nullptr;
+	T*       res_out = nullptr;
+	const T* minv = nullptr;
+	T*       e = nullptr;
+	T*       d_new = nullptr;
+	T        a = 0, b = 0;
+};
+
 // ---- PTX wrappers ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
@@ -115,15 +131,16 @@ constexpr size_t smem_bytes()
 	       S * sizeof(uint64_t) + 9 * (2 * R + 1) * sizeof(T) + 32 * sizeof(double) + 64;
 }
 
-template <typename T, int R, int S, bool Fused, int MINB>
+template <typename T, int R, int S, bool Fused, int MINB, bool Epi>
 __global__ void __launch_bounds__(256, MINB)
     stencil3d_tma_kernel(const __grid_constant__ CUtensorMap map_a,  // p (plain) or r (fused)
                          const __grid_constant__ CUtensorMap map_b,  // M^-1 (fused)
                          const __grid_constant__ CUtensorMap map_c,  // p_old (fused)
                          int nx, int ny, int nzl, int zo0, int zo1, int zoff, int nzg, int zchunk, TmaTables<T> tab,
                          T* __restrict__ q, T* __restrict__ p_new,
-                         const PcgState* st, int par, double* dot_out, double* partial, unsigned* ticket, const int* done)
+                         const PcgState* st, int par, double* dot_out, double* partial, unsigned* ticket, const int* done, EpiArgs<T> epi)
 {
+	static_assert(!(Fused && Epi), "the epilogue mode takes a plain input");
 	using G           = Tile<T, R>;
 	constexpr int V   = G::V;
 	constexpr int NP  = G::NP;
@@ -225,6 +242,20 @@ __global__ void __launch_bounds__(256, MINB)
 	T*       qout = q + static_cast<size_t>(y) * nx + x0;
 	T*       pout = Fused ? p_new + static_cast<size_t>(y) * nx + x0 : nullptr;
 
+	// epilogue operands of this thread's pack, one plane ahead
+	PU         pre_r, pre_m, pre_e;
+	const bool epi_upd = Epi && epi.d_new != nullptr;
+	const size_t xy_off = static_cast<size_t>(y) * nx + x0;
+	auto epi_load = [&](int z) {
+		const size_t at = static_cast<size_t>(z) * plane + xy_off;
+		pre_r.v = *reinterpret_cast<const Pack*>(epi.res_in + at);
+		if (epi_upd) {
+			pre_m.v = *reinterpret_cast<const Pack*>(epi.minv + at);
+			pre_e.v = *reinterpret_cast<const Pack*>(epi.e + at);
+		}
+	};
+	if (Epi && in_xy && zb < ze) { epi_load(zb); }
+
 	int stage = 0, slot = 0;
 	uint32_t phase = 0;
 	for (int i0 = 0; i0 < n_iter; i0 += W) {
@@ -255,6 +286,13 @@ __global__ void __launch_bounds__(256, MINB)
 				const T*    cz = zband + row_class(z + zoff, nzg) * W;
 				const PU&   ctr = pipe[(k + 1 + R) % W];
 				PU          out;
+				PU          cur_r, cur_m, cur_e;
+				if (Epi) {
+					cur_r = pre_r;
+					cur_m = pre_m;
+					cur_e = pre_e;
+					if (z + 1 < ze) { epi_load(z + 1); }
+				}
 #pragma unroll
 				for (int j = 0; j < V; ++j) {
 					T s = T(0);
@@ -287,11 +325,29 @@ __global__ void __launch_bounds__(256, MINB)
 #pragma unroll
 					for (int t = 0; t < W; ++t) { out.a[j] += cx[j][t] * xs[NP * V + j + t - R]; }
 				}
-				*reinterpret_cast<Pack*>(qout + static_cast<size_t>(z) * plane) = out.v;
-				T d = T(0);
+				if (Epi) {
+					const size_t at = static_cast<size_t>(z) * plane + xy_off;
+					PU           rn;
 #pragma unroll
-				for (int j = 0; j < V; ++j) { d += out.a[j] * ctr.a[j]; }
-				acc += static_cast<double>(d);
+					for (int j = 0; j < V; ++j) { rn.a[j] = cur_r.a[j] - out.a[j]; }
+					if (epi.res_out) { *reinterpret_cast<Pack*>(epi.res_out + at) = rn.v; }
+					if (epi_upd) {
+						PU dn, en;
+#pragma unroll
+						for (int j = 0; j < V; ++j) {
+							dn.a[j] = epi.a * ctr.a[j] + epi.b * cur_m.a[j] * rn.a[j];
+							en.a[j] = cur_e.a[j] + dn.a[j];
+						}
+						*reinterpret_cast<Pack*>(epi.d_new + at) = dn.v;
+						*reinterpret_cast<Pack*>(epi.e + at)     = en.v;
+					}
+				} else {
+					*reinterpret_cast<Pack*>(qout + static_cast<size_t>(z) * plane) = out.v;
+					T d = T(0);
+#pragma unroll
+					for (int j = 0; j < V; ++j) { d += out.a[j] * ctr.a[j]; }
+					acc += static_cast<double>(d);
+				}
 			}
 			if (++stage == S) { stage = 0; phase ^= 1u; }
 			if (++slot == G::RING) { slot = 0; }
@@ -343,9 +399,9 @@ CUtensorMap make_map(const Geom& g, const T* ptr)
 	return m;
 }
 
-template <typename T, int R, int S, bool Fused, int MINB>
+template <typename T, int R, int S, bool Fused, int MINB, bool Epi = false>
 void launch(const Geom& g, const StencilTables& t, const T* a, const T* b, const T* c, T* q, T* p_new, const PcgState* st, int par,
-            double* d_dot_out, double* d_partial, unsigned* d_ticket, const int* d_done, cudaStream_t s)
+            double* d_dot_out, double* d_partial, unsigned* d_ticket, const int* d_done, cudaStream_t s, const EpiArgs<T>& epi = EpiArgs<T>())
 {
 	using G = Tile<T, R>;
 	TmaTables<T> tab;
@@ -381,7 +437,7 @@ void launch(const Geom& g, const StencilTables& t, const T* a, const T* b, const
 	const int zchunk = div_up(nown, chunks);
 	chunks           = div_up(nown, zchunk);
 	dim3 grid(tiles_x, tiles_y, chunks);
-	auto kern = stencil3d_tma_kernel<T, R, S, Fused, MINB>;
+	auto kern = stencil3d_tma_kernel<T, R, S, Fused, MINB, Epi>;
 	constexpr size_t smem = smem_bytes<T, R, S, Fused>();
 	static bool configured = false;  // per instantiation
 	if (!configured) {
@@ -389,7 +445,7 @@ void launch(const Geom& g, const StencilTables& t, const T* a, const T* b, const
 		configured = true;
 	}
 	FI_LAUNCH(kern, grid, 256, smem, s, ma, mb, mc, g.size[0], g.size[1], g.nzl, g.zown0, g.zown1, g.zoff, g.size[2], zchunk, tab, q, p_new,
-	          st, par, d_dot_out, d_partial, d_ticket, d_done);
+	          st, par, d_dot_out, d_partial, d_ticket, d_done, epi);
 }
 
 template <typename T>
@@ -434,6 +490,31 @@ bool stencil_tma_3d_fused(const Geom& g, const StencilTables& t, const T* r, con
 	return true;
 }
 
+// q is not formed: res_out = res_in - S in, and with d_new: d_new = a in + b minv res_out, e += d_new.  false: not applicable.
+template <typename T>
+bool stencil_tma_3d_epilogue(const Geom& g, const StencilTables& t, const T* in, const T* res_in, T* res_out, const T* minv, T* e, T* d_new,
+                             T a, T b, cudaStream_t s)
+{
+	if (!eligible<T>(g, t) || g.sharded()) { return false; }
+	EpiArgs<T> epi;
+	epi.res_in  = res_in;
+	epi.res_out = res_out;
+	epi.minv    = minv;
+	epi.e       = e;
+	epi.d_new   = d_new;
+	epi.a       = a;
+	epi.b       = b;
+	if (t.radius <= 1) {
+		launch<T, 1, 3, false, 2, true>(g, t, in, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, s, epi);
+	} else if (t.radius == 2) {
+		launch<T, 2, 3, false, 2, true>(g, t, in, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, s, epi);
+	} else {
+		launch<T, 4, 2, false, 1, true>(g, t, in, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, s, epi);
+	}
+	return true;
+}
+
+template bool stencil_tma_3d_epilogue<float>(const Geom&, const StencilTables&, const float*, const float*, float*, const float*, float*, float*, float, float, cudaStream_t);
 template bool stencil_tma_3d<float>(const Geom&, const StencilTables&, const float*, float*, double*, double*, unsigned*, const int*, cudaStream_t);
 template bool stencil_tma_3d<double>(const Geom&, const StencilTables&, const double*, double*, double*, double*, unsigned*, const int*, cudaStream_t);
 template bool stencil_tma_3d_fused<float>(const Geom&, const StencilTables&, const float*, const float*, const float*, float*, float*, const PcgState*, int, double*, double*, unsigned*, const int*, cudaStream_t);
