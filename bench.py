@@ -283,15 +283,23 @@ def main():
         B = 4 if args.precision == "f32" else 8
         words = 5 if t["fused"] else 2  # fused direction+stencil: read r, M^-1, p_old, write p_new, q; plain stencil: read p, write q
         apply_s, upd_s, it_s = t["apply_ms"] / 200e3, t["update_ms"] / 200e3, t["iteration_ms"] / 200e3
-        achieved = words * B * N / apply_s / 1e9
-        roof = {"bound": "hbm", "kernel": "stencil3d_tma_kernel<fused direction + stencil + p.q> (+ apply_blocks_kernel, the data term)" if t["fused"] else "stencil kernel",
+        sten_s, data_s = t["stencil_ms"] / 200e3, t["data_term_ms"] / 200e3
+        # dominant kernel = the lattice-sized stencil kernel, timed alone with CUDA events on the solver stream
+        # (200 back-to-back launches); the data-term kernel that completes the operator apply is listed beside it
+        achieved = words * B * N / sten_s / 1e9
+        roof = {"bound": "hbm", "kernel": "stencil3d_tma_kernel<fused direction + stencil + p.q>" if t["fused"] else "stencil kernel",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args.workload, args.precision),
-                "algorithmic_bytes_per_cell": words * B, "peak_source": peak_src, "avg_launch_ms": apply_s * 1e3}
+                "algorithmic_bytes_per_cell": words * B, "algorithmic_bytes_per_launch": words * B * N, "peak_source": peak_src,
+                "avg_launch_ms": sten_s * 1e3}
         extra = {"update_kernel": {"achieved": 7 * B * N / upd_s / 1e9, "frac": 7 * B * N / upd_s / 1e9 / peak, "avg_launch_ms": upd_s * 1e3,
                                    "algorithmic_bytes_per_cell": 7 * B},
+                 "data_term_kernels": {"avg_launch_ms": data_s * 1e3, "note": "apply_blocks_kernel over the occupied cells (+ generic rows)"},
+                 "apply_stencil_plus_data_term": {"achieved": words * B * N / apply_s / 1e9, "frac": words * B * N / apply_s / 1e9 / peak,
+                                                  "avg_ms": apply_s * 1e3},
                  "iteration": {"achieved_52B_convention": BYTES_PER_CELL_ITER[args.precision] * N / it_s / 1e9,
                                "frac_52B_convention": BYTES_PER_CELL_ITER[args.precision] * N / it_s / 1e9 / peak,
                                "achieved_actual_bytes": (words + 7 + (0 if t["fused"] else 4)) * B * N / it_s / 1e9,
+                               "frac_actual_bytes": (words + 7 + (0 if t["fused"] else 4)) * B * N / it_s / 1e9 / peak,
                                "ms_per_iteration": it_s * 1e3, "cell_iters_per_s_iterations_only": N / it_s}}
 
     ttt = None

@@ -204,9 +204,10 @@ class LatticeField:
     def time_iterations(self, iterations: int, options: Optional[L.fi_solve_options] = None):
         """Device ms (totals over `iterations` launches): whole iterations, apply kernels, update, direction; fused?"""
         opt = options if options is not None else solve_options()
-        ms = (C.c_double * 5)()
+        ms = (C.c_double * 8)()
         L.check(L.lib().fi_field_time_iterations(self._h, C.byref(opt), int(iterations), ms))
-        return {"iteration_ms": ms[0], "apply_ms": ms[1], "update_ms": ms[2], "direction_ms": ms[3], "fused": bool(ms[4])}
+        return {"iteration_ms": ms[0], "apply_ms": ms[1], "update_ms": ms[2], "direction_ms": ms[3], "fused": bool(ms[4]),
+                "stencil_ms": ms[5], "data_term_ms": ms[6]}
 
 
 # ---- builders (field_interpolation.hpp:116-173) ------------------------------------------------------

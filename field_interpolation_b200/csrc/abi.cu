@@ -209,6 +209,9 @@ struct fi_field
 		fi::MgOptions want;
 		if (o.mg_smoothing_steps > 0) { want.nu = o.mg_smoothing_steps; }
 		if (o.mg_cheb_ratio > 1.0) { want.cheb_ratio = o.mg_cheb_ratio; }
+		if (const char* e = getenv("FI_B200_MG_COARSEST")) {  // tuning knob: cells of the dense coarsest level
+			if (atoi(e) > 0) { want.coarsest_cells = atoi(e); }
+		}
 		if (mg && (mg_opt.nu != want.nu || mg_opt.cheb_ratio != want.cheb_ratio)) { mg.reset(); }
 		if (!mg) {
 			fi::Operator<float>& fine = get32();

@@ -261,42 +261,41 @@ __global__ void __launch_bounds__(kThreads) mg_direction_kernel(int64_t n, const
 	for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) { p[i] = static_cast<T>(z[i]) + beta * p[i]; }
 }
 
-void invert_spd(std::vector<double>& a, int n)  // in place, Gauss-Jordan with partial pivoting (n <= ~1000, setup only)
+// ---- coarsest level setup: dense inverse on the device -------------------------------------------------------------
+// M = (C + C^T) / 2 in fp64 (the applied operator is symmetric up to the fp32 rounding of the data term's atomics)
+__global__ void symmetrise_kernel(int n, const float* __restrict__ cols, double* __restrict__ M)
 {
-	std::vector<double> inv(static_cast<size_t>(n) * n, 0.0);
-	for (int i = 0; i < n; ++i) { inv[static_cast<size_t>(i) * n + i] = 1.0; }
-	for (int c = 0; c < n; ++c) {
-		int    piv  = c;
-		double best = std::fabs(a[static_cast<size_t>(c) * n + c]);
-		for (int r = c + 1; r < n; ++r) {
-			if (std::fabs(a[static_cast<size_t>(r) * n + c]) > best) {
-				best = std::fabs(a[static_cast<size_t>(r) * n + c]);
-				piv  = r;
-			}
-		}
-		FI_REQUIRE(best > 0.0, FI_ERR_INVALID, "multigrid: the coarsest operator is singular");
-		if (piv != c) {
-			for (int k = 0; k < n; ++k) {
-				std::swap(a[static_cast<size_t>(piv) * n + k], a[static_cast<size_t>(c) * n + k]);
-				std::swap(inv[static_cast<size_t>(piv) * n + k], inv[static_cast<size_t>(c) * n + k]);
-			}
-		}
-		const double d = 1.0 / a[static_cast<size_t>(c) * n + c];
-		for (int k = 0; k < n; ++k) {
-			a[static_cast<size_t>(c) * n + k] *= d;
-			inv[static_cast<size_t>(c) * n + k] *= d;
-		}
-		for (int r = 0; r < n; ++r) {
-			if (r == c) { continue; }
-			const double f = a[static_cast<size_t>(r) * n + c];
-			if (f == 0.0) { continue; }
-			for (int k = 0; k < n; ++k) {
-				a[static_cast<size_t>(r) * n + k] -= f * a[static_cast<size_t>(c) * n + k];
-				inv[static_cast<size_t>(r) * n + k] -= f * inv[static_cast<size_t>(c) * n + k];
-			}
-		}
-	}
-	a.swap(inv);
+	const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (t >= static_cast<int64_t>(n) * n) { return; }
+	const int i = static_cast<int>(t / n), j = static_cast<int>(t % n);
+	M[t] = 0.5 * (static_cast<double>(cols[static_cast<size_t>(i) * n + j]) + static_cast<double>(cols[static_cast<size_t>(j) * n + i]));
+}
+
+// Gauss-Jordan step c, first half: the scaled pivot row (with the identity's column folded in) and the pivot column.
+__global__ void gj_pivot_kernel(int n, int c, const double* __restrict__ M, double* __restrict__ prow, double* __restrict__ pcol, int* bad)
+{
+	const int k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= n) { return; }
+	const double p = M[static_cast<size_t>(c) * n + c];
+	if (k == 0 && !(p > 0.0)) { *bad = 1; }
+	const double inv = p != 0.0 ? 1.0 / p : 0.0;
+	prow[k] = (k == c ? 1.0 : M[static_cast<size_t>(c) * n + k]) * inv;
+	pcol[k] = M[static_cast<size_t>(k) * n + c];
+}
+
+// second half: row c <- pivot row; every other row r <- row r (column c cleared) - M[r][c] * pivot row
+__global__ void gj_update_kernel(int n, int c, double* __restrict__ M, const double* __restrict__ prow, const double* __restrict__ pcol)
+{
+	const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (t >= static_cast<int64_t>(n) * n) { return; }
+	const int r = static_cast<int>(t / n), k = static_cast<int>(t % n);
+	M[t] = r == c ? prow[k] : (k == c ? 0.0 : M[t]) - pcol[r] * prow[k];
+}
+
+__global__ void narrow_kernel(int64_t n, const double* __restrict__ in, float* __restrict__ out)
+{
+	const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (t < n) { out[t] = static_cast<float>(in[t]); }
 }
 
 }  // namespace
@@ -492,36 +491,34 @@ std::unique_ptr<Multigrid> build_multigrid(Operator<float>& fine, const ModelAcc
 			lv.lmax = lam * 1.1;  // the power iteration approaches lambda_max from below
 		}
 	}
-	// dense inverse of the coarsest operator
+	// dense inverse of the coarsest operator, computed on the device: the columns A e_k by n applies without a
+	// host round trip, then an in-place Gauss-Jordan sweep in fp64 (no pivoting: the matrix is SPD)
 	{
 		Multigrid::Level& lc = *mg->levels[L - 1];
 		const int         n  = static_cast<int>(lc.g.N);
 		mg->nc               = n;
-		if (L == 1) {
-			lc.r.resize(n);  // scratch for the unit vectors (level 0 owns no vectors otherwise)
-			lc.e.resize(n);
-		}
-		std::vector<double> A(static_cast<size_t>(n) * n);
-		std::vector<float>  col(n);
+		if (L == 1) { lc.r.resize(n); }  // scratch for the unit vectors (level 0 owns no vectors otherwise)
+		const size_t   nn = static_cast<size_t>(n) * n;
+		DevBuf<float>  cols(nn);
+		DevBuf<double> M(nn), prow(n), pcol(n);
 		for (int k = 0; k < n; ++k) {
 			FI_LAUNCH(unit_vector_kernel, div_up(n, kThreads), kThreads, 0, s, n, k, lc.r.data());
-			lc.op->apply(lc.r.data(), lc.e.data(), nullptr, nullptr, s);
-			FI_CUDA(cudaMemcpyAsync(col.data(), lc.e.data(), n * sizeof(float), cudaMemcpyDeviceToHost, s));
-			FI_CUDA(cudaStreamSynchronize(s));
-			for (int i = 0; i < n; ++i) { A[static_cast<size_t>(i) * n + k] = col[i]; }
+			lc.op->apply(lc.r.data(), cols.data() + static_cast<size_t>(k) * n, nullptr, nullptr, s);
 		}
-		for (int i = 0; i < n; ++i) {  // symmetrise (the operator is symmetric up to fp32 rounding of the atomics)
-			for (int j = i + 1; j < n; ++j) {
-				const double v = 0.5 * (A[static_cast<size_t>(i) * n + j] + A[static_cast<size_t>(j) * n + i]);
-				A[static_cast<size_t>(i) * n + j] = A[static_cast<size_t>(j) * n + i] = v;
-			}
+		const int g2 = static_cast<int>(div_up(static_cast<int64_t>(nn), kThreads));
+		FI_LAUNCH(symmetrise_kernel, g2, kThreads, 0, s, n, cols.data(), M.data());
+		DevBuf<int> bad(1);
+		bad.zero(s);
+		for (int c = 0; c < n; ++c) {
+			FI_LAUNCH(gj_pivot_kernel, div_up(n, kThreads), kThreads, 0, s, n, c, M.data(), prow.data(), pcol.data(), bad.data());
+			FI_LAUNCH(gj_update_kernel, g2, kThreads, 0, s, n, c, M.data(), prow.data(), pcol.data());
 		}
-		invert_spd(A, n);
-		std::vector<float> Af(A.size());
-		for (size_t i = 0; i < A.size(); ++i) { Af[i] = static_cast<float>(A[i]); }
-		mg->coarse_inv.resize(Af.size());
-		FI_CUDA(cudaMemcpyAsync(mg->coarse_inv.data(), Af.data(), Af.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+		mg->coarse_inv.resize(nn);
+		FI_LAUNCH(narrow_kernel, g2, kThreads, 0, s, static_cast<int64_t>(nn), M.data(), mg->coarse_inv.data());
+		int h_bad = 0;
+		FI_CUDA(cudaMemcpyAsync(&h_bad, bad.data(), sizeof(int), cudaMemcpyDeviceToHost, s));
 		FI_CUDA(cudaStreamSynchronize(s));
+		FI_REQUIRE(h_bad == 0, FI_ERR_INVALID, "multigrid: the coarsest operator is singular");
 	}
 	return mg;
 }

@@ -879,6 +879,22 @@ void time_kernels(Operator<T>& op, int iterations, int check_every, double* out,
 		});
 	}
 	out[4] = fused ? 1.0 : 0.0;
+	out[7] = 0.0;
+	// the two halves of the apply on their own: the lattice-sized stencil kernel (the dominant kernel of the roofline
+	// figure) and the data-term kernels over the occupied cells
+	out[5] = timed([&](int i) {
+		const int par = i & 1;
+		if (fused) {
+			stencil_fused_step<T>(op.use_fast, op.g, op.tabs, w.r.data(), op.minv.data(), pp[par], pp[par ^ 1], w.q.data(), w.state.data(), par,
+			                      dot.data(), op.partial.data(), op.ticket.data(), nullptr, s);
+		} else {
+			stencil_apply<T>(op.g, op.tabs, w.p.data(), w.q.data(), dot.data(), op.partial.data(), op.ticket.data(), nullptr, op.use_fast, s);
+		}
+	});
+	out[6] = timed([&](int i) {
+		const int par = i & 1;
+		apply_data_term<T>(op.g, op.data, fused ? pp[par ^ 1] : w.p.data(), w.q.data(), dot.data(), nullptr, s);
+	});
 	cudaEventDestroy(e0);
 	cudaEventDestroy(e1);
 }

@@ -170,7 +170,7 @@ struct MgOptions
 {
 	int    nu               = 3;     // Chebyshev steps before and after the coarse-grid correction
 	double cheb_ratio       = 12.0;  // the smoother targets the eigenvalues of D^-1 A in [lambda_max / ratio, lambda_max]
-	int    coarsest_cells   = 150;   // coarsen until a level has at most this many cells (dense solve there; the host inverts it)
+	int    coarsest_cells   = 600;   // coarsen until a level has at most this many cells (dense solve there, inverse computed on the device)
 	int    power_iterations = 12;    // for lambda_max, per level, at setup
 };
 
@@ -208,7 +208,7 @@ PcgResult tile_phase(Operator<T>& op, int tile_size, T* x, double tol, long long
 template <typename T>
 void jacobi_sweeps(Operator<T>& op, T* x, int iterations, T weight, cudaStream_t s);
 
-// out[0..4]: see fi_field_time_iterations in include/fi_b200.h.
+// out[0..7]: see fi_field_time_iterations in include/fi_b200.h.
 template <typename T>
 void time_kernels(Operator<T>& op, int iterations, int check_every, double* out, cudaStream_t s);
 

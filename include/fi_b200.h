@@ -259,7 +259,10 @@ FI_API void    fi_kernel_launches_reset(void);
  *         uses it, else the stencil kernel (plus the data-term kernels)
  *   ms[2] the update kernel alone (x += a p, r -= a q, r.Mr, r.r)
  *   ms[3] the direction kernel alone (0 when it is fused into the stencil)
- *   ms[4] 1 if the fused kernel is in use, else 0 */
+ *   ms[4] 1 if the fused kernel is in use, else 0
+ *   ms[5] the lattice-sized stencil kernel of ms[1] alone (the dominant kernel of the roofline figure)
+ *   ms[6] the data-term kernels of ms[1] alone (occupied-cell blocks + generic rows)
+ * `ms` must hold 8 doubles (ms[7] is reserved, written as 0). */
 FI_API int fi_field_time_iterations(fi_field* f, const fi_solve_options* opt, int32_t iterations, double* ms);
 
 #ifdef __cplusplus

@@ -84,7 +84,8 @@ def test_one_rank_slab_matches_plain_solve(orders):
     weights = fi.Weights(**orders)
     runner = fid.SlabRunner(sizes, weights, 0, 1, OneRank)
     f = fi.sdf_from_points(sizes, weights, pos, cloud["normals"])
-    for prec, tol in ((fi.FI_F64, 1e-12), (fi.FI_F32, 1e-5)):
+    # outputs are float32: the fp64 runs may differ by an ulp of the stored float where the two paths sum in another order
+    for prec, tol in ((fi.FI_F64, 2e-8), (fi.FI_F32, 1e-5)):
         for its in (1, 3, 30):
             opt = fi.solve_options(prec, its, 1e-30, check_every=4)
             out = np.zeros(runner.local_cells, np.float32)

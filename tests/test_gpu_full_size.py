@@ -1,0 +1,172 @@
+"""GPU: the BASELINE.json configurations at their full sizes, through size-independent properties.
+
+At 256^3 / 2048^2 the explicit triplet list is gigabytes and the oracle's sparse direct solve is out of reach, so
+these tests pin the full-size path with identities that hold for any lattice size:
+
+  * structure counts in closed form (KAT-3's rule: model rows per axis and order, 1 + D rows per kept point);
+  * an affine field x(c) = a.c + c0 is reproduced exactly by the multilinear value rows
+    (field_interpolation.cpp:15-80) and by the cell-edge gradient rows (:150-187), and is annihilated by every
+    difference row of order >= 2 (:273-301).  Hence, with default Weights,
+        x^T (AtA) x = sum_points (vw x(pos))^2 + sum_points sum_d (gw a_d)^2      (energy identity)
+        x^T (Atb)   = sum_points sum_d gw^2 a_d n_d                               (sdf values are 0)
+    — both sides computable on the host in O(points), independently of the lattice kernels;
+  * symmetry u.(A v) = v.(A u) and linearity of the operator on random vectors;
+  * the solved field satisfies |AtA x - Atb| <= tol |Atb| when the residual is recomputed from scratch through
+    fi_field_apply / fi_field_rhs (not the solver's own recurrence), and the fp32 solve agrees with the fp64 solve
+    within the north_star tolerance (relative L2 <= 1e-3).
+C2 (512^2, 10k value points) is small enough for the oracle's fp64 direct solve: checked directly, full size.
+"""
+import numpy as np
+import pytest
+
+from field_interpolation_b200 import workloads as W
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL_F64, TOL_F32 = 1e-5, 1e-3  # BASELINE.json north_star: relative L2 vs the exact solve
+
+
+@pytest.fixture(scope="module")
+def fi():
+    import field_interpolation_b200 as m
+    return m
+
+
+def rel(a, b):
+    return float(np.linalg.norm(np.asarray(a, np.float64) - np.asarray(b, np.float64)) / max(np.linalg.norm(b), 1e-300))
+
+
+def model_rows(sizes, order):
+    """Rows add_field_constraints emits for one difference order: per axis, every node with coord + order < size."""
+    n = int(np.prod(sizes))
+    return sum(n // s * max(0, s - order) for s in sizes)
+
+
+def inside_cell(pos, sizes):
+    """cell_index != -1 (field_interpolation.cpp:110-121): 0 <= floor(p) and floor(p) + 1 < size on every axis."""
+    fl = np.floor(pos)
+    return np.all((fl >= 0) & (fl + 1 < np.asarray(sizes)[None, :]), axis=1)
+
+
+def affine(sizes, a, c0):
+    grids = np.meshgrid(*[np.arange(s, dtype=np.float64) for s in reversed(sizes)], indexing="ij")  # slowest axis first
+    x = np.full(grids[0].shape, c0, np.float64)
+    for d, g in enumerate(reversed(grids)):  # reversed: axis 0 (fastest) last in the meshgrid order
+        x += a[d] * g
+    return x.reshape(-1)
+
+
+CONFIGS = {
+    # BASELINE configs[2] and configs[3]
+    "C3_sdf2d_2048_200k": dict(sizes=[2048, 2048], cloud=lambda: W.circles_2d(200_000, seed=0)),
+    "C4_sdf3d_256_1M": dict(sizes=[256, 256, 256], cloud=lambda: W.sphere_torus_3d(1_000_000, seed=0)),
+}
+
+
+@pytest.fixture(scope="module", params=sorted(CONFIGS))
+def full(request, fi):
+    cfg = CONFIGS[request.param]
+    sizes = cfg["sizes"]
+    cloud = cfg["cloud"]()
+    pos = W.to_lattice(cloud["unit_pos"], sizes)
+    f = fi.sdf_from_points(sizes, fi.Weights(), pos, cloud["normals"])
+    yield dict(name=request.param, sizes=sizes, pos=pos, nrm=cloud["normals"], field=f)
+    f.close()
+
+
+def test_full_size_structure_counts(fi, full):
+    sizes, D = full["sizes"], len(full["sizes"])
+    kept = int(inside_cell(full["pos"], sizes).sum())
+    assert kept == len(full["pos"])  # the synthetic clouds lie strictly inside the lattice
+    rows, trips = full["field"].counts()
+    m2 = model_rows(sizes, 2)  # default Weights: model_2 only
+    assert rows == m2 + kept * (1 + D)
+    assert trips == 3 * m2 + kept * (1 + D) * 2 ** D
+    if full["name"].startswith("C4"):
+        assert (m2, rows, trips) == (49_938_432, 53_938_432, 181_815_296)
+
+
+def test_full_size_affine_energy_and_rhs_identities(fi, full):
+    sizes, D, f = full["sizes"], len(full["sizes"]), full["field"]
+    a = np.array([0.37, -0.21, 0.11][:D])
+    c0 = -3.0
+    x = affine(sizes, a, c0)
+    w = fi.Weights()
+    vw, gw = float(np.float32(w.data_pos)), float(np.float32(w.data_gradient))
+    xp = c0 + full["pos"].astype(np.float64) @ a
+    energy = float(np.sum((vw * xp) ** 2) + len(xp) * np.sum((gw * a) ** 2))
+    y = f.apply(x, fi.FI_F64)
+    assert abs(float(x @ y) - energy) <= 2e-6 * energy  # fp32 multilerp weights inside A: ~1e-7 per coefficient
+    rhs = f.rhs(fi.FI_F64)
+    want = float(gw * gw * np.sum(full["nrm"].astype(np.float64) @ a))
+    scale = gw * gw * float(np.sum(np.abs(full["nrm"].astype(np.float64)) @ np.abs(a)))
+    assert abs(float(x @ rhs) - want) <= 2e-6 * scale
+    # no data near the lattice border: there the rows of AtA x are pure smoothness rows, and those vanish on an affine field
+    far = np.ones(sizes[::-1], bool)
+    lo = np.floor(full["pos"].min(axis=0)).astype(int) - 1
+    hi = np.ceil(full["pos"].max(axis=0)).astype(int) + 2
+    far[tuple(slice(lo[d], hi[d]) for d in reversed(range(D)))] = False
+    assert far.sum() > 0.2 * far.size
+    assert np.abs(y.reshape(sizes[::-1])[far]).max() <= 1e-9 * np.abs(x).max()
+    # fp32 operator, same identity
+    y32 = f.apply(x.astype(np.float32), fi.FI_F32)
+    assert abs(float(x @ y32.astype(np.float64)) - energy) <= 2e-3 * energy
+
+
+def test_full_size_symmetry_and_linearity(fi, full):
+    f, n = full["field"], int(np.prod(full["sizes"]))
+    rng = np.random.default_rng(5)
+    u, v = rng.normal(size=n), rng.normal(size=n)
+    Au, Av = f.apply(u, fi.FI_F64), f.apply(v, fi.FI_F64)
+    s1, s2 = float(v @ Au), float(u @ Av)
+    assert abs(s1 - s2) <= 1e-11 * (np.linalg.norm(u) * np.linalg.norm(Av))
+    w = f.apply(2.0 * u - 3.0 * v, fi.FI_F64)
+    assert rel(w, 2.0 * Au - 3.0 * Av) <= 1e-12
+    assert float(u @ Au) > 0 and float(v @ Av) > 0  # positive definite (points pin the null space of the model rows)
+
+
+def test_full_size_solve_to_1e6_independent_residual(fi, full):
+    f = full["field"]
+    rhs = f.rhs(fi.FI_F64)
+    x64, st64 = f.solve(fi.solve_options(fi.FI_F64, 500, 1e-6, preconditioner=fi.FI_PRECOND_MULTIGRID))
+    assert st64["converged"] and st64["iterations"] < 200
+    r = rhs - f.apply(x64.astype(np.float64), fi.FI_F64)
+    # the library's own from-scratch fp64 residual (before x is narrowed to the API's float32) meets the target ...
+    assert st64["true_residual"] <= 1.0e-6
+    # ... and so does the residual recomputed here from the returned float32 field, up to what that narrowing costs:
+    # |A dx| <= |A|_inf |dx|, |A|_inf <= 16 w2^2 D + data term < 20 with default Weights, |dx| <= 2^-24 |x|
+    assert np.linalg.norm(r) <= 1.0e-6 * np.linalg.norm(rhs) + 20.0 * 2.0 ** -24 * np.linalg.norm(x64)
+    x32, st32 = f.solve(fi.solve_options(fi.FI_F32, 500, 1e-6, preconditioner=fi.FI_PRECOND_MULTIGRID))
+    assert st32["iterations"] > 0
+    assert rel(x32, x64) <= TOL_F32
+    # Jacobi-PCG (the reference's preconditioner) from the multigrid solution stays there: same system, same fixed point
+    x_j, st_j = f.solve(fi.solve_options(fi.FI_F64, 50, 1e-6), guess=x64)
+    assert rel(x_j, x64) <= TOL_F64
+
+
+def test_c2_interpolate_2d_full_size_vs_oracle_exact(fi, port):
+    """BASELINE configs[1]: 512x512 lattice, 10k noisy value points, model_1 + model_2 — the oracle's fp64 direct solve
+    of the reference-assembled rows is feasible at this size, so this one is a direct full-size parity check."""
+    cfg = W.interpolate_2d(512, 10_000, seed=1)
+    sizes = cfg["sizes"]
+    pos = W.to_lattice(cfg["unit_pos"], sizes)
+    w = fi.Weights(**cfg["weights"])
+    f = fi.LatticeField(sizes)
+    fi.add_field_constraints(f, w)  # model rows first (src/interpolate_2d.cpp:32)
+    fi.add_points(f, w.data_pos, w.value_kernel, 0.0, w.gradient_kernel, pos, None, None, cfg["value"])
+    ref = port.field(sizes)
+    ref.add_field_constraints(O.make_weights(**cfg["weights"]))
+    for p, v in zip(pos, cfg["value"]):  # the caller's loop, src/interpolate_2d.cpp:34-44
+        ref.add_value_constraint(p, float(v), w.data_pos)
+    want = ref.system()
+    eq = f.eq
+    assert np.array_equal(eq.rows, want.rows) and np.array_equal(eq.cols, want.cols)
+    assert np.array_equal(eq.vals.view(np.uint32), want.vals.view(np.uint32))
+    assert np.array_equal(eq.rhs.view(np.uint32), want.rhs.view(np.uint32))
+    exact = O.exact_solve(want, f.num_unknowns)
+    x64, st = f.solve(fi.solve_options(fi.FI_F64, 2000, 1e-10, preconditioner=fi.FI_PRECOND_MULTIGRID))
+    assert st["converged"] and rel(x64, exact) <= TOL_F64
+    x32, _ = f.solve(fi.solve_options(fi.FI_F32, 2000, 1e-6, preconditioner=fi.FI_PRECOND_MULTIGRID))
+    assert rel(x32, exact) <= TOL_F32
+    f.close()
