@@ -211,9 +211,13 @@ def main():
     d_out = torch.empty(N if world == 1 else runner.local_cells, dtype=torch.float32, device="cuda")
     h_out = torch.empty(d_out.numel(), dtype=torch.float32).pin_memory()
 
+    last_stats = {}
+
     def step_device():
         if runner is not None:
-            return runner.step(d_pos, d_nrm, opt, d_out)
+            st = runner.step(d_pos, d_nrm, opt, d_out)
+            last_stats.update(st)
+            return st
         f = fi.sdf_from_points(sizes, weights, d_pos, d_nrm)
         _, st = f.solve(opt, out=d_out)
         f.close()
@@ -301,6 +305,17 @@ def main():
                                "achieved_actual_bytes": (words + 7 + (0 if t["fused"] else 4)) * B * N / it_s / 1e9,
                                "frac_actual_bytes": (words + 7 + (0 if t["fused"] else 4)) * B * N / it_s / 1e9 / peak,
                                "ms_per_iteration": it_s * 1e3, "cell_iters_per_s_iterations_only": N / it_s}}
+
+    if rank == 0 and runner is not None:
+        # z-slab sharding: what one iteration moves over NVLink (R boundary planes of r to each neighbour, pushed by the
+        # update kernel with peer stores, plus two 8/16-byte mailbox all-reduces), from rank 0's last step
+        R = 2  # default Weights: model_2 -> radius-2 star
+        it_ms = last_stats.get("solve_ms", 0.0) / max(1, last_stats.get("iterations", 1))
+        halo_bytes = 2 * R * n * n * (4 if args.precision == "f32" else 8)  # an interior rank: both neighbours
+        extra = {"slab": {"planes_per_rank": n // world, "setup_ms": last_stats.get("setup_ms"), "solve_ms": last_stats.get("solve_ms"),
+                          "ms_per_iteration": it_ms, "halo_bytes_per_iteration_per_interior_rank": halo_bytes,
+                          "halo_GBps_per_interior_rank_averaged_over_iteration": halo_bytes / max(it_ms, 1e-9) / 1e6,
+                          "path": "peer stores over NVLink inside pcg_update_peer_kernel" if os.environ.get("FI_B200_P2P", "1") != "0" else "ncclSend/ncclRecv"}}
 
     ttt = None
     if rank == 0 and runner is None and not args.no_time_to_tol:

@@ -696,6 +696,65 @@ __global__ void __launch_bounds__(kThreads, 3) apply_blocks_kernel(Geom g, int64
 	}
 }
 
+// The same product with one thread per (cell, corner row): a block covers 256 consecutive cells, thread group ci (one
+// warp in 3D) owns output row ci of every cell and walks the block's cells in 2^D strides of 256 / 2^D.  Each thread
+// issues 2^D coalesced block loads + 2^D gathers of p and one atomic — 2^D times the threads of the per-cell kernel
+// with 1 / 2^D of its dependent work each, which is what this latency-bound kernel needs (the per-cell form holds
+// 36 + 16 values in registers and runs at a third of the SM's warp slots).  A block element is read by the two rows
+// that share it; the second read hits L1.
+template <typename T, int D>
+__global__ void __launch_bounds__(kThreads) apply_blocks_split_kernel(Geom g, int64_t nocc, const int64_t* __restrict__ cell_base,
+                                                                      const uint32_t* __restrict__ cell_mask, const T* __restrict__ blocks,
+                                                                      const T* __restrict__ p, T* __restrict__ q, double* partial,
+                                                                      unsigned* ticket, double* dot_accum, const int* done)
+{
+	constexpr int C = 1 << D, CPB = kThreads / C;
+	__shared__ double red[32];
+	if (done && *done) { return; }
+	const int ci = threadIdx.x / CPB, lane = threadIdx.x % CPB;
+	int64_t   off[C];
+#pragma unroll
+	for (int c = 0; c < C; ++c) {
+		off[c] = 0;
+#pragma unroll
+		for (int d = 0; d < D; ++d) { off[c] += ((c >> d) & 1) ? g.stride[d] : 0; }
+	}
+	int64_t off_ci = 0;
+#pragma unroll
+	for (int d = 0; d < D; ++d) { off_ci += ((ci >> d) & 1) ? g.stride[d] : 0; }
+	T dot = 0;
+#pragma unroll 2
+	for (int it = 0; it < C; ++it) {
+		const int64_t cell = static_cast<int64_t>(blockIdx.x) * kThreads + it * CPB + lane;
+		if (cell >= nocc) { continue; }
+		T b[C];
+#pragma unroll
+		for (int cj = 0; cj < C; ++cj) {
+			const int lo = min(ci, cj), hi = max(ci, cj);
+			const int tri = lo * C - (lo * (lo - 1)) / 2 + (hi - lo);  // row-major upper triangle, as build_data_term stores it
+			b[cj] = __ldg(&blocks[static_cast<size_t>(tri) * nocc + cell]);
+		}
+		const int64_t  base = cell_base[cell];
+		const uint32_t mask = cell_mask[cell];
+		T out = 0, pci = 0;
+#pragma unroll
+		for (int cj = 0; cj < C; ++cj) {
+			const T pv = ((mask >> cj) & 1u) ? p[base + off[cj]] : T(0);
+			out += b[cj] * pv;
+			if (cj == ci) { pci = pv; }
+		}
+		if ((mask >> (8 + ci)) & 1u) {
+			atomic_add(&q[base + off_ci], out);
+			dot += pci * out;
+		}
+	}
+	if (dot_accum) {
+		double mine[1] = {static_cast<double>(dot)};
+		mine[0] = block_sum(mine[0], red);
+		grid_sum<1>(mine, partial, ticket, red, [&](const double(&tot)[1]) { *dot_accum += tot[0]; });
+	}
+}
+
 // Epilogue form for the multigrid smoother: u = P in over the occupied cells, then res -= u and (d_new given)
 // d_new -= b minv u, e -= b minv u.
 template <typename T, int D>
@@ -978,6 +1037,16 @@ void build_data_term(const Geom& g, const PointStore& pts, const HostRows& user,
 	FI_CUDA(cudaStreamSynchronize(s));
 }
 
+// FI_B200_DATA_TERM=cell selects the one-thread-per-cell kernel (kept for comparison); default: per (cell, row).
+static bool split_data_term()
+{
+	static const bool v = [] {
+		const char* e = getenv("FI_B200_DATA_TERM");
+		return !(e && e[0] == 'c');
+	}();
+	return v;
+}
+
 template <typename T>
 void apply_data_term(const Geom& g, const DataTerm<T>& dt, const T* p, T* q, double* d_dot_accum, const int* d_done,
                      cudaStream_t s)
@@ -992,6 +1061,10 @@ void apply_data_term(const Geom& g, const DataTerm<T>& dt, const T* p, T* q, dou
 				auto kern = apply_blocks_kernel<T, decltype(dim)::value, true>;
 				FI_LAUNCH(kern, gb, kThreads, 0, s, g, dt.nocc, dt.cell_base.data(), dt.cell_mask.data(), dt.blocks.data(), p, q, partial, ticket,
 				          d_dot_accum, d_done, dt.cell_key.data());
+			} else if (split_data_term()) {
+				auto kern = apply_blocks_split_kernel<T, decltype(dim)::value>;
+				FI_LAUNCH(kern, gb, kThreads, 0, s, g, dt.nocc, dt.cell_base.data(), dt.cell_mask.data(), dt.blocks.data(), p, q, partial, ticket,
+				          d_dot_accum, d_done);
 			} else {
 				auto kern = apply_blocks_kernel<T, decltype(dim)::value, false>;
 				FI_LAUNCH(kern, gb, kThreads, 0, s, g, dt.nocc, dt.cell_base.data(), dt.cell_mask.data(), dt.blocks.data(), p, q, partial, ticket,

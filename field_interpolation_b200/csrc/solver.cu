@@ -123,34 +123,51 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
 	asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// One thread: stores this rank's `count` (<= 2) partial sums and then the sequence number into every rank's mailbox.
-__device__ __forceinline__ void peer_publish(const PeerLink& L, int which, int par, unsigned long long seq, const double* v, int count)
+// The first warp of a block, all 32 lanes: lane j stores this rank's `count` (<= 2) partial sums and then the sequence
+// number into rank j's mailbox — every peer in parallel, one NVLink round trip in all (a single thread doing the
+// `world` release stores one after the other costs `world` round trips: 20+ us at 8 ranks, measured).
+__device__ __forceinline__ void peer_publish_warp(const PeerLink& L, int which, int par, unsigned long long seq, const double* v, int count)
 {
-	for (int j = 0; j < L.world; ++j) {
+	const int j = threadIdx.x & 31;
+	if (j < L.world) {
 		PeerSlot* sl = &L.peer[j]->slot[which][par][L.rank];
 		for (int k = 0; k < count; ++k) { reinterpret_cast<volatile double*>(sl->v)[k] = v[k]; }
+		// cumulative: also orders the halo stores of the other blocks, observed through the ticket, before the flag
+		__threadfence_system();
+		st_release_sys(&sl->seq, seq);
 	}
-	__threadfence_system();
-	for (int j = 0; j < L.world; ++j) { st_release_sys(&L.peer[j]->slot[which][par][L.rank].seq, seq); }
 }
 
-// One thread: waits until every rank's slot carries `seq`, then adds the values in rank order.  Gives up after
-// ~10 s (a peer died): flags the mailbox and returns false.
-__device__ __forceinline__ bool peer_collect(const PeerLink& L, int which, int par, unsigned long long seq, double* out, int count)
+// The first warp of a block, all 32 lanes: lane j waits until rank j's slot carries `seq`; lane 0 then adds the values in
+// rank order (every rank forms bit-identical sums).  Gives up after ~10 s (a peer died): flags the mailbox and returns
+// false.  The result is valid in lane 0 (and returned to every lane).
+__device__ __forceinline__ bool peer_collect_warp(const PeerLink& L, int which, int par, unsigned long long seq, double* out, int count)
 {
-	for (int k = 0; k < count; ++k) { out[k] = 0.0; }
-	const long long t0 = clock64();
-	for (int j = 0; j < L.world; ++j) {
+	const int j  = threadIdx.x & 31;
+	double    v0 = 0.0, v1 = 0.0;
+	bool      ok = true;
+	if (j < L.world) {
 		const PeerSlot* sl = &L.local->slot[which][par][j];
+		const long long t0 = clock64();
 		while (ld_acquire_sys(&sl->seq) != seq) {
 			if (clock64() - t0 > 20000000000ll) {
 				L.local->error = 1;
-				return false;
+				ok             = false;
+				break;
 			}
 		}
-		for (int k = 0; k < count; ++k) { out[k] += reinterpret_cast<const volatile double*>(sl->v)[k]; }
+		v0 = reinterpret_cast<const volatile double*>(sl->v)[0];
+		if (count > 1) { v1 = reinterpret_cast<const volatile double*>(sl->v)[1]; }
 	}
-	return true;
+	ok = __all_sync(0xffffffffu, ok);
+	double t0s = 0.0, t1s = 0.0;
+	for (int r = 0; r < L.world; ++r) {
+		t0s += __shfl_sync(0xffffffffu, v0, r);
+		t1s += __shfl_sync(0xffffffffu, v1, r);
+	}
+	out[0] = t0s;
+	if (count > 1) { out[1] = t1s; }
+	return ok;
 }
 
 // Sequence numbers of iteration `iters` of the solve with epoch number `base`: 2 * iters + 1 for p.Ap, + 2 for
@@ -172,25 +189,25 @@ __device__ __forceinline__ unsigned long long global_ns()
 __global__ void peer_publish_kernel(PeerLink L, int which, int par, unsigned long long base, const PcgState* st, const double* src, int count,
                                     const int* done)
 {
-	if (threadIdx.x != 0 || blockIdx.x != 0) { return; }
+	if (blockIdx.x != 0 || threadIdx.x >= 32) { return; }
 	const unsigned long long seq = seq_of(base, st, which);
 	double v[2] = {0.0, 0.0};
 	// a finished solve still publishes (zeros): the peers' kernels of this round are already waiting
 	if (!(done && *done)) {
 		for (int k = 0; k < count; ++k) { v[k] = src[k]; }
-		L.local->stamp[0][st->iters & 511] = global_ns();
+		if (threadIdx.x == 0) { L.local->stamp[0][st->iters & 511] = global_ns(); }
 	}
-	peer_publish(L, which, par, seq, v, count);
+	peer_publish_warp(L, which, par, seq, v, count);
 }
 
 // Ends an iteration on the peer-memory path: sums (r.Mr, r.r) over ranks and updates the shared CG state.
 __global__ void pcg_update_finish_peer_kernel(PcgState* st, int par, PeerLink L, unsigned long long base)
 {
-	if (threadIdx.x != 0 || blockIdx.x != 0) { return; }
+	if (blockIdx.x != 0 || threadIdx.x >= 32) { return; }
 	const unsigned long long seq = seq_of(base, st, 1);
 	double tot[2];
-	const bool ok = peer_collect(L, 1, par, seq, tot, 2);
-	if (st->done) { return; }
+	const bool ok = peer_collect_warp(L, 1, par, seq, tot, 2);
+	if (threadIdx.x != 0 || st->done) { return; }
 	if (!ok) {
 		st->breakdown = 2;
 		st->done      = 1;
@@ -302,15 +319,19 @@ __global__ void __launch_bounds__(kThreads) pcg_update_peer_kernel(int64_t n, T*
                                                                    unsigned* ticket, PeerLink L, HaloPush<T> push, unsigned long long base)
 {
 	__shared__ double red[32];
-	__shared__ double s_pq;
-	__shared__ int    s_ok;
+	__shared__ double s_pq, s_tot[2];
+	__shared__ int    s_ok, s_pub;
 	const bool was_done = st->done != 0;
 	const unsigned long long seq_pq = seq_of(base, st, 0), seq_rr = seq_of(base, st, 1);
-	if (threadIdx.x == 0) {
-		double pq = 0.0;
-		s_ok      = peer_collect(L, 0, par, seq_pq, &pq, 1) ? 1 : 0;
-		s_pq      = pq;
-		if (blockIdx.x == 0 && !was_done) { L.local->stamp[1][st->iters & 511] = global_ns(); }
+	if (threadIdx.x < 32) {
+		double     pq = 0.0;
+		const bool ok = peer_collect_warp(L, 0, par, seq_pq, &pq, 1);
+		if (threadIdx.x == 0) {
+			s_ok  = ok ? 1 : 0;
+			s_pq  = pq;
+			s_pub = 0;
+			if (blockIdx.x == 0 && !was_done) { L.local->stamp[1][st->iters & 511] = global_ns(); }
+		}
 	}
 	__syncthreads();
 	const double pq    = s_pq;
@@ -364,8 +385,16 @@ __global__ void __launch_bounds__(kThreads) pcg_update_peer_kernel(int64_t n, T*
 			st->breakdown = s_ok ? 1 : 2;
 			st->done      = 1;
 		}
-		peer_publish(L, 1, par, seq_rr, tot, 2);
+		s_tot[0] = tot[0];
+		s_tot[1] = tot[1];
+		s_pub    = 1;
 	});
+	__syncthreads();
+	// the last block to finish: its first warp publishes this slab's sums to every rank at once
+	if (s_pub && threadIdx.x < 32) {
+		const double tot[2] = {s_tot[0], s_tot[1]};
+		peer_publish_warp(L, 1, par, seq_rr, tot, 2);
+	}
 }
 
 template <typename T>
