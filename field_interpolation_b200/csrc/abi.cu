@@ -1051,6 +1051,24 @@ int fi_comm_destroy(fi_comm* c)
 	return guarded([&] { comm_destroy(c); });
 }
 
+int fi_slab_mg_plan(const int32_t* sizes, int32_t world, int32_t stencil_radius, int64_t gather_cells, int32_t* sharded_levels, int32_t* halo,
+                    int32_t* level_sizes, int32_t* plane_ranges)
+{
+	return guarded([&] {
+		FI_REQUIRE(sizes && sharded_levels && halo && level_sizes && plane_ranges && world >= 1 && world <= 64, FI_ERR_INVALID, "bad argument");
+		const SlabMgPlan plan = plan_slab_multigrid(sizes, world, stencil_radius, gather_cells > 0 ? gather_cells : 3000000);
+		*sharded_levels = plan.nd;
+		*halo           = plan.halo;
+		for (int l = 0; l <= plan.nd; ++l) {
+			for (int d = 0; d < 3; ++d) { level_sizes[l * 3 + d] = plan.size[l][d]; }
+			for (int k = 0; k < world; ++k) {
+				plane_ranges[(l * world + k) * 2 + 0] = plan.own[l][k].first;
+				plane_ranges[(l * world + k) * 2 + 1] = plan.own[l][k].second;
+			}
+		}
+	});
+}
+
 int fi_slab_range(int32_t nz, int32_t world, int32_t rank, int32_t* z0, int32_t* z1)
 {
 	return guarded([&] {

@@ -35,6 +35,7 @@ struct Nccl
 	ncclResult_t (*CommDestroy)(ncclComm_t)                                                                = nullptr;
 	ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
 	ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t)        = nullptr;
+	ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t)   = nullptr;
 	ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t)               = nullptr;
 	ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t)                     = nullptr;
 	ncclResult_t (*GroupStart)()                                                                           = nullptr;
@@ -66,6 +67,7 @@ Nccl& nccl()
 		n.CommDestroy    = reinterpret_cast<decltype(n.CommDestroy)>(sym("ncclCommDestroy"));
 		n.AllReduce      = reinterpret_cast<decltype(n.AllReduce)>(sym("ncclAllReduce"));
 		n.AllGather      = reinterpret_cast<decltype(n.AllGather)>(sym("ncclAllGather"));
+		n.Broadcast      = reinterpret_cast<decltype(n.Broadcast)>(sym("ncclBroadcast"));
 		n.Send           = reinterpret_cast<decltype(n.Send)>(sym("ncclSend"));
 		n.Recv           = reinterpret_cast<decltype(n.Recv)>(sym("ncclRecv"));
 		n.GroupStart     = reinterpret_cast<decltype(n.GroupStart)>(sym("ncclGroupStart"));
@@ -210,6 +212,32 @@ struct SlabHooks final : DistHooks
 
 	const PeerLink* link() override { return c->p2p ? &c->link : nullptr; }
 	unsigned long long next_seq() override { return ++c->seq; }
+	int rank() const override { return c->rank; }
+	int world() const override { return c->world; }
+	std::unique_ptr<DistHooks> for_geom(const Geom& geom, int h) override { return std::make_unique<SlabHooks>(c, geom, h); }
+
+	void allgather_planes(float* full, int64_t plane_cells, const std::vector<std::pair<int, int>>& own, cudaStream_t s) override
+	{
+		FI_REQUIRE(static_cast<int>(own.size()) == c->world, FI_ERR_INVALID, "allgather_planes: one plane range per rank");
+		if (c->world == 1) { return; }
+		Nccl&     n     = nccl();
+		const int each  = own[0].second - own[0].first;
+		bool      equal = true;
+		for (int k = 0; k < c->world; ++k) { equal = equal && own[k].first == k * each && own[k].second == (k + 1) * each; }
+		if (equal) {  // in place: this rank's planes already sit at full + rank * count
+			const size_t count = static_cast<size_t>(each) * static_cast<size_t>(plane_cells);
+			FI_NCCL(n.AllGather(full + static_cast<size_t>(c->rank) * count, full, count, ncclFloat, c->comm, s));
+		} else {  // ragged: one in-place broadcast per owner, grouped
+			FI_NCCL(n.GroupStart());
+			for (int k = 0; k < c->world; ++k) {
+				float*       at    = full + static_cast<size_t>(own[k].first) * static_cast<size_t>(plane_cells);
+				const size_t count = static_cast<size_t>(own[k].second - own[k].first) * static_cast<size_t>(plane_cells);
+				FI_NCCL(n.Broadcast(at, at, count, ncclFloat, k, c->comm, s));
+			}
+			FI_NCCL(n.GroupEnd());
+		}
+		count_launch();
+	}
 	int64_t peer_own_cells(int peer) override
 	{
 		int z0 = 0, z1 = 0;
@@ -319,6 +347,83 @@ void slab_solve_typed(fi_comm* c, const Geom& g, int halo, const ModelAccum& mod
 	}
 }
 
+
+// Multigrid-preconditioned CG on the slab (mg.cu: SlabMultigrid): the V-cycle always runs in fp32, the outer CG in T.
+template <typename T>
+void slab_mg_solve_typed(fi_comm* c, const Geom& g, const SlabMgPlan& plan, const ModelAccum& model, const PointStore& pts, const fi_solve_options& o,
+                         const float* d_guess_own, float* d_out_own, fi_solve_stats* st, cudaStream_t s)
+{
+	cudaEvent_t e0, e1;
+	FI_CUDA(cudaEventCreate(&e0));
+	FI_CUDA(cudaEventCreate(&e1));
+	FI_CUDA(cudaEventRecord(e0, s));
+	HostRows  none;
+	SlabHooks hooks(c, g, plan.halo);
+	auto      op32 = build_operator<float>(g, model, pts, none, s);
+	op32->dist     = &hooks;
+	op32->use_fast = kStencilAuto;
+	MgOptions mo;
+	if (o.mg_smoothing_steps > 0) { mo.nu = o.mg_smoothing_steps; }
+	if (o.mg_cheb_ratio > 1.0) { mo.cheb_ratio = o.mg_cheb_ratio; }
+	if (const char* e = getenv("FI_B200_MG_COARSEST")) {
+		if (atoi(e) > 0) { mo.coarsest_cells = atoi(e); }
+	}
+	auto mg = build_slab_multigrid(*op32, model, pts, mo, plan, s);
+	std::unique_ptr<Operator<T>> op_wide;  // the outer CG's operator when it is not the V-cycle's
+	Operator<T>*                 op = nullptr;
+	if constexpr (std::is_same<T, float>::value) {
+		op = op32.get();
+	} else {
+		op_wide           = build_operator<T>(g, model, pts, none, s);
+		op_wide->dist     = &hooks;
+		op_wide->use_fast = kStencilAuto;
+		op                = op_wide.get();
+	}
+	FI_CUDA(cudaEventRecord(e1, s));
+	const int64_t off = g.own_offset(), n = g.own_cells();
+	DevBuf<T>     x(g.N);
+	x.zero(s);
+	if (d_guess_own) {
+		if (std::is_same<T, float>::value) {
+			FI_CUDA(cudaMemcpyAsync(x.data() + off, d_guess_own, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+		} else {
+			convert(d_guess_own, reinterpret_cast<double*>(x.data()) + off, n, s);
+		}
+	}
+	const PcgResult r = slab_mgpcg_solve<T>(*op, *mg, nullptr, x.data(), o.tolerance, o.max_iterations, s);
+	if (std::is_same<T, float>::value) {
+		FI_CUDA(cudaMemcpyAsync(d_out_own, x.data() + off, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+	} else {
+		convert(reinterpret_cast<const double*>(x.data()) + off, d_out_own, n, s);
+	}
+	FI_CUDA(cudaStreamSynchronize(s));
+	float setup = 0;
+	FI_CUDA(cudaEventElapsedTime(&setup, e0, e1));
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	if (st) {
+		std::memset(st, 0, sizeof(*st));
+		st->iterations        = r.iterations;
+		st->relative_residual = r.rel_residual;
+		st->true_residual     = r.true_residual;
+		st->initial_residual  = r.initial_residual;
+		st->setup_ms          = setup;
+		st->solve_ms          = r.solve_ms;
+		st->converged         = r.converged ? 1 : 0;
+		st->occupied_cells    = op->data.nocc;
+		st->generic_rows      = op->data.nrows;
+	}
+}
+
+int64_t slab_mg_gather_cells()
+{
+	// levels with at most this many cells are replicated on every rank (default: up to 144^3)
+	if (const char* e = getenv("FI_B200_MG_GATHER_CELLS")) {
+		if (atoll(e) > 0) { return atoll(e); }
+	}
+	return 3000000;
+}
+
 }  // namespace
 
 // add_model_impl's arithmetic (abi.cu) for one Weights value
@@ -341,6 +446,12 @@ void slab_sdf_solve(fi_comm* c, const int32_t* sizes, const fi_weights& w, int64
 		if (model.on[k]) { halo = k; }
 	}
 	FI_REQUIRE(halo >= 1, FI_ERR_UNSUPPORTED, "slab solves need a smoothness order >= 1");
+	const bool multigrid = o.preconditioner == FI_PRECOND_MULTIGRID;
+	SlabMgPlan plan;
+	if (multigrid) {  // the V-cycle's transfers want at least two halo planes
+		plan = plan_slab_multigrid(sizes, c->world, halo, slab_mg_gather_cells());
+		halo = plan.halo;
+	}
 	int z0 = 0, z1 = 0;
 	slab_range(sizes[2], c->world, c->rank, &z0, &z1);
 	FI_REQUIRE(z1 - z0 >= halo, FI_ERR_INVALID, "slabs thinner than the stencil radius: use fewer ranks");
@@ -382,7 +493,11 @@ void slab_sdf_solve(fi_comm* c, const int32_t* sizes, const fi_weights& w, int64
 				gptr = d_guess.data();
 			}
 		}
-		if (o.precision == FI_F32) {
+		if (multigrid && o.precision == FI_F32) {
+			slab_mg_solve_typed<float>(c, g, plan, model, pts, o, gptr, optr, st, s);
+		} else if (multigrid) {
+			slab_mg_solve_typed<double>(c, g, plan, model, pts, o, gptr, optr, st, s);
+		} else if (o.precision == FI_F32) {
 			slab_solve_typed<float>(c, g, halo, model, pts, o, gptr, optr, st, s);
 		} else {
 			slab_solve_typed<double>(c, g, halo, model, pts, o, gptr, optr, st, s);

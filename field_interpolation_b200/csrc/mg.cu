@@ -156,11 +156,13 @@ __global__ void unit_vector_kernel(int n, int k, float* v)
 }
 
 // ---- power iteration helpers ----------------------------------------------------------------------------------------
-__global__ void hash_fill_kernel(int64_t n, float* v)
+// v[i] = pseudo-random in [-0.5, 0.5) from the lattice index i + first (a slab fills its planes with the values the
+// unsharded vector has there)
+__global__ void hash_fill_kernel(int64_t n, float* v, int64_t first)
 {
 	const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
 	for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-		uint64_t h = static_cast<uint64_t>(i) * 0x9E3779B97F4A7C15ull + 0x7F4A7C15ull;
+		uint64_t h = static_cast<uint64_t>(i + first) * 0x9E3779B97F4A7C15ull + 0x7F4A7C15ull;
 		h ^= h >> 31;
 		h *= 0xBF58476D1CE4E5B9ull;
 		h ^= h >> 29;
@@ -315,58 +317,112 @@ struct Multigrid::Level
 
 namespace {
 
-// Per-axis interpolation tables of the pair (lv = fine, gc = coarse); the arithmetic is upscale_field's position rule
-// evaluated in double.
-void build_xfer(Multigrid::Level& lv, const Geom& gc, cudaStream_t s)
+// Interpolation tables of one axis of a level pair (nf fine nodes, nc coarse nodes); the arithmetic is upscale_field's
+// position rule (field_interpolation.cpp:462) evaluated in double.
+struct AxisTables
 {
-	Xfer&            x = lv.to_coarser;
+	std::vector<int>   base, first, count;  // base[nf]; first[nc], count[nc]
+	std::vector<float> frac, weight;        // frac[nf]; weight[nc][kMaxFan]
+};
+
+AxisTables axis_tables(int nf, int nc)
+{
+	AxisTables t;
+	const double sc = nf > 1 ? static_cast<double>(nc - 1) / static_cast<double>(nf - 1) : 0.0;
+	t.base.assign(nf, 0);
+	t.first.assign(nc, 0);
+	t.count.assign(nc, 0);
+	t.frac.assign(nf, 0.0f);
+	t.weight.assign(static_cast<size_t>(nc) * kMaxFan, 0.0f);
+	for (int i = 0; i < nf; ++i) {
+		const double x = i * sc;
+		int          b = static_cast<int>(x);
+		if (b > nc - 1) { b = nc - 1; }
+		t.base[i] = b;
+		t.frac[i] = static_cast<float>(x - b);
+	}
+	for (int i = 0; i < nf; ++i) {  // transpose: scatter every fine node's two weights to its coarse nodes
+		const int   b = t.base[i];
+		const float w[2] = {1.0f - t.frac[i], t.frac[i]};
+		for (int k = 0; k < 2; ++k) {
+			const int C = b + k;
+			if (C >= nc || w[k] == 0.0f) { continue; }
+			if (t.count[C] == 0) { t.first[C] = i; }
+			const int at = i - t.first[C];
+			FI_REQUIRE(at < kMaxFan, FI_ERR_UNSUPPORTED, "multigrid: coarsening ratio too large for the transfer tables");
+			t.weight[static_cast<size_t>(C) * kMaxFan + at] = w[k];
+			t.count[C] = at + 1;
+		}
+	}
+	return t;
+}
+
+// Device copy of the tables of all axes of the pair (gf = fine, gc = coarse lattice sizes; unused axes have nf = nc = 1).
+void build_xfer(Xfer& x, DevBuf<int>& xfer_int, DevBuf<float>& xfer_float, const Geom& gf, const Geom& gc, cudaStream_t s)
+{
 	std::vector<int>   hi;
 	std::vector<float> hf;
 	size_t off_base[kMaxDim], off_first[kMaxDim], off_count[kMaxDim], off_frac[kMaxDim], off_weight[kMaxDim];
 	for (int d = 0; d < kMaxDim; ++d) {
-		const int nf = d < lv.g.ndim ? lv.g.size[d] : 1, nc = d < lv.g.ndim ? gc.size[d] : 1;
+		const int nf = d < gf.ndim ? gf.size[d] : 1, nc = d < gf.ndim ? gc.size[d] : 1;
 		x.nf[d] = nf;
 		x.nc[d] = nc;
-		const double sc = nf > 1 ? static_cast<double>(nc - 1) / static_cast<double>(nf - 1) : 0.0;
-		std::vector<int>   base(nf), first(nc, 0), count(nc, 0);
-		std::vector<float> frac(nf), weight(static_cast<size_t>(nc) * kMaxFan, 0.0f);
-		for (int i = 0; i < nf; ++i) {
-			const double t = i * sc;
-			int          b = static_cast<int>(t);
-			if (b > nc - 1) { b = nc - 1; }
-			base[i] = b;
-			frac[i] = static_cast<float>(t - b);
-		}
-		for (int i = 0; i < nf; ++i) {  // transpose: scatter every fine node's two weights to its coarse nodes
-			const int   b = base[i];
-			const float w[2] = {1.0f - frac[i], frac[i]};
-			for (int k = 0; k < 2; ++k) {
-				const int C = b + k;
-				if (C >= nc || w[k] == 0.0f) { continue; }
-				if (count[C] == 0) { first[C] = i; }
-				const int at = i - first[C];
-				FI_REQUIRE(at < kMaxFan, FI_ERR_UNSUPPORTED, "multigrid: coarsening ratio too large for the transfer tables");
-				weight[static_cast<size_t>(C) * kMaxFan + at] = w[k];
-				count[C] = at + 1;
-			}
-		}
-		off_base[d]  = hi.size(); hi.insert(hi.end(), base.begin(), base.end());
-		off_first[d] = hi.size(); hi.insert(hi.end(), first.begin(), first.end());
-		off_count[d] = hi.size(); hi.insert(hi.end(), count.begin(), count.end());
-		off_frac[d]   = hf.size(); hf.insert(hf.end(), frac.begin(), frac.end());
-		off_weight[d] = hf.size(); hf.insert(hf.end(), weight.begin(), weight.end());
+		const AxisTables t = axis_tables(nf, nc);
+		off_base[d]  = hi.size(); hi.insert(hi.end(), t.base.begin(), t.base.end());
+		off_first[d] = hi.size(); hi.insert(hi.end(), t.first.begin(), t.first.end());
+		off_count[d] = hi.size(); hi.insert(hi.end(), t.count.begin(), t.count.end());
+		off_frac[d]   = hf.size(); hf.insert(hf.end(), t.frac.begin(), t.frac.end());
+		off_weight[d] = hf.size(); hf.insert(hf.end(), t.weight.begin(), t.weight.end());
 	}
-	lv.xfer_int.resize(hi.size());
-	lv.xfer_float.resize(hf.size());
-	FI_CUDA(cudaMemcpyAsync(lv.xfer_int.data(), hi.data(), hi.size() * sizeof(int), cudaMemcpyHostToDevice, s));
-	FI_CUDA(cudaMemcpyAsync(lv.xfer_float.data(), hf.data(), hf.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+	xfer_int.resize(hi.size());
+	xfer_float.resize(hf.size());
+	FI_CUDA(cudaMemcpyAsync(xfer_int.data(), hi.data(), hi.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+	FI_CUDA(cudaMemcpyAsync(xfer_float.data(), hf.data(), hf.size() * sizeof(float), cudaMemcpyHostToDevice, s));
 	FI_CUDA(cudaStreamSynchronize(s));  // the host vectors go out of scope
 	for (int d = 0; d < kMaxDim; ++d) {
-		x.base[d]   = lv.xfer_int.data() + off_base[d];
-		x.first[d]  = lv.xfer_int.data() + off_first[d];
-		x.count[d]  = lv.xfer_int.data() + off_count[d];
-		x.frac[d]   = lv.xfer_float.data() + off_frac[d];
-		x.weight[d] = lv.xfer_float.data() + off_weight[d];
+		x.base[d]   = xfer_int.data() + off_base[d];
+		x.first[d]  = xfer_int.data() + off_first[d];
+		x.count[d]  = xfer_int.data() + off_count[d];
+		x.frac[d]   = xfer_float.data() + off_frac[d];
+		x.weight[d] = xfer_float.data() + off_weight[d];
+	}
+}
+
+void build_xfer(Multigrid::Level& lv, const Geom& gc, cudaStream_t s) { build_xfer(lv.to_coarser, lv.xfer_int, lv.xfer_float, lv.g, gc, s); }
+
+// Model and points of level `la` (>= 1) of the hierarchy whose level 0 is the lattice root_size with `model` and `pts`:
+// the same points in the coarse lattice's coordinates, gradient rows / 2 per level, order-k smoothness rows scaled by
+// 2^((D - 2k) / 2) per level (squared weights by 2^(D - 2k)).
+void level_inputs(int D, const int* root_size, const ModelAccum& model, const PointStore& pts, const Geom& gl, int la, ModelAccum& m, PointStore& out,
+                  cudaStream_t s)
+{
+	m = model;
+	for (int k = 0; k <= 4; ++k) {
+		const double f = std::pow(2.0, static_cast<double>(D - 2 * k) * la);
+		for (int a = 0; a < 5; ++a) {
+			for (int b = 0; b < 5; ++b) { m.cc[k][a][b] *= f; }
+		}
+	}
+	m.gs_sq *= std::pow(2.0, static_cast<double>(D - 4) * la);
+	const int64_t n = pts.count;
+	if (n > 0) {
+		out.pos.resize(static_cast<size_t>(n) * D);
+		out.grad.resize(static_cast<size_t>(n) * D);
+		out.value.resize(n);
+		out.vw.resize(n);
+		out.gw.resize(n);
+		out.kind.resize(n);
+		out.count = n;
+		float sc[kMaxDim] = {1, 1, 1};
+		for (int d = 0; d < D; ++d) {
+			sc[d] = root_size[d] > 1 ? static_cast<float>(static_cast<double>(gl.size[d] - 1) / static_cast<double>(root_size[d] - 1)) : 0.0f;
+		}
+		FI_LAUNCH(coarsen_points_kernel, div_up(n, kThreads), kThreads, 0, s, D, n, pts.pos.data(), pts.gw.data(), sc[0], sc[1], sc[2],
+		          static_cast<float>(std::pow(0.5, la)), out.pos.data(), out.gw.data());
+		FI_CUDA(cudaMemcpyAsync(out.grad.data(), pts.grad.data(), static_cast<size_t>(n) * D * sizeof(float), cudaMemcpyDeviceToDevice, s));
+		FI_CUDA(cudaMemcpyAsync(out.value.data(), pts.value.data(), n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+		FI_CUDA(cudaMemcpyAsync(out.vw.data(), pts.vw.data(), n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+		FI_CUDA(cudaMemcpyAsync(out.kind.data(), pts.kind.data(), n * sizeof(uint8_t), cudaMemcpyDeviceToDevice, s));
 	}
 }
 
@@ -378,10 +434,12 @@ Multigrid::~Multigrid()
 	if (exec) { cudaGraphExecDestroy(exec); }
 }
 
-std::unique_ptr<Multigrid> build_multigrid(Operator<float>& fine, const ModelAccum& model, const PointStore& pts, const MgOptions& opt, cudaStream_t s)
+std::unique_ptr<Multigrid> build_multigrid(Operator<float>& fine, const ModelAccum& model, const PointStore& pts, const MgOptions& opt, cudaStream_t s,
+                                           const int* root_size, int fine_level)
 {
 	TraceScope trace("build_multigrid");
-	FI_REQUIRE(!fine.g.sharded(), FI_ERR_UNSUPPORTED, "the multigrid preconditioner runs on one GPU");
+	FI_REQUIRE(!fine.g.sharded(), FI_ERR_UNSUPPORTED, "build_multigrid takes an unsharded lattice (slabs: build_slab_multigrid)");
+	if (!root_size) { root_size = fine.g.size; }
 	auto mg     = std::make_unique<Multigrid>();
 	mg->opt     = opt;
 	const int D = fine.g.ndim;
@@ -416,34 +474,8 @@ std::unique_ptr<Multigrid> build_multigrid(Operator<float>& fine, const ModelAcc
 	// coarse operators by re-discretisation
 	for (int l = 1; l < L; ++l) {
 		Multigrid::Level& lv = *mg->levels[l];
-		ModelAccum        m  = model;
-		for (int k = 0; k <= 4; ++k) {
-			const double f = std::pow(2.0, static_cast<double>(D - 2 * k) * l);  // squared weights scale by rho^(D-2k) per level
-			for (int a = 0; a < 5; ++a) {
-				for (int b = 0; b < 5; ++b) { m.cc[k][a][b] *= f; }
-			}
-		}
-		m.gs_sq *= std::pow(2.0, static_cast<double>(D - 4) * l);
-		const int64_t n = pts.count;
-		if (n > 0) {
-			lv.pts.pos.resize(static_cast<size_t>(n) * D);
-			lv.pts.grad.resize(static_cast<size_t>(n) * D);
-			lv.pts.value.resize(n);
-			lv.pts.vw.resize(n);
-			lv.pts.gw.resize(n);
-			lv.pts.kind.resize(n);
-			lv.pts.count = n;
-			float sc[kMaxDim] = {1, 1, 1};
-			for (int d = 0; d < D; ++d) {
-				sc[d] = fine.g.size[d] > 1 ? static_cast<float>(static_cast<double>(lv.g.size[d] - 1) / static_cast<double>(fine.g.size[d] - 1)) : 0.0f;
-			}
-			FI_LAUNCH(coarsen_points_kernel, div_up(n, kThreads), kThreads, 0, s, D, n, pts.pos.data(), pts.gw.data(), sc[0], sc[1], sc[2],
-			          static_cast<float>(std::pow(0.5, l)), lv.pts.pos.data(), lv.pts.gw.data());
-			FI_CUDA(cudaMemcpyAsync(lv.pts.grad.data(), pts.grad.data(), static_cast<size_t>(n) * D * sizeof(float), cudaMemcpyDeviceToDevice, s));
-			FI_CUDA(cudaMemcpyAsync(lv.pts.value.data(), pts.value.data(), n * sizeof(float), cudaMemcpyDeviceToDevice, s));
-			FI_CUDA(cudaMemcpyAsync(lv.pts.vw.data(), pts.vw.data(), n * sizeof(float), cudaMemcpyDeviceToDevice, s));
-			FI_CUDA(cudaMemcpyAsync(lv.pts.kind.data(), pts.kind.data(), n * sizeof(uint8_t), cudaMemcpyDeviceToDevice, s));
-		}
+		ModelAccum        m;
+		level_inputs(D, root_size, model, pts, lv.g, fine_level + l, m, lv.pts, s);
 		HostRows none;
 		lv.owned = build_operator<float>(lv.g, m, lv.pts, none, s);
 		lv.op    = lv.owned.get();
@@ -474,7 +506,7 @@ std::unique_ptr<Multigrid> build_multigrid(Operator<float>& fine, const ModelAcc
 			Multigrid::Level& lv = *mg->levels[l];
 			const int64_t     n  = lv.g.N;
 			float *           v = lv.d.data(), *w = lv.res.data();
-			FI_LAUNCH(hash_fill_kernel, vgrid(n), kThreads, 0, s, n, v);
+			FI_LAUNCH(hash_fill_kernel, vgrid(n), kThreads, 0, s, n, v, static_cast<int64_t>(0));
 			double lam = 1.0;
 			for (int it = 0; it < opt.power_iterations; ++it) {
 				lv.op->apply(v, lv.q.data(), nullptr, nullptr, s);
@@ -639,38 +671,329 @@ void Multigrid::vcycle(const float* r, float* z, cudaStream_t s)
 	count_launch(static_cast<int>(graph_launches));
 }
 
+// ---- the V-cycle with z-slab sharded fine levels ------------------------------------------------------------------------
+struct SlabMultigrid::DLevel
+{
+	Geom                             g;             // this rank's slab of the level (halo planes either side)
+	DistHooks*                       hooks = nullptr;  // level 0: the fine operator's; coarser: owned below
+	std::unique_ptr<DistHooks>       owned_hooks;
+	Operator<float>*                 op = nullptr;  // level 0: the caller's operator; coarser: owned below
+	std::unique_ptr<Operator<float>> owned;
+	PointStore                       pts;
+	DevBuf<float>                    r, e, res, d, q;  // slab-local; r / e of level 0 are the caller's vectors
+	double                           lmax = 0;
+	Xfer                             to_coarser;    // tables over the WHOLE axes of this level and the next
+	DevBuf<int>                      xfer_int;
+	DevBuf<float>                    xfer_float;
+	int                              c0 = 0, c1 = 0;  // planes of the next level this rank restricts into
+};
+
+SlabMultigrid::SlabMultigrid()  = default;
+SlabMultigrid::~SlabMultigrid() = default;
+
+SlabMgPlan plan_slab_multigrid(const int32_t* sizes, int world, int radius, int64_t gather_cells)
+{
+	FI_REQUIRE(sizes != nullptr && world >= 1 && radius >= 1 && radius <= 4, FI_ERR_INVALID, "bad slab multigrid request");
+	SlabMgPlan plan;
+	plan.world = world;
+	plan.halo  = std::max(radius, 2);  // restriction reads up to two planes below the middle one
+	auto tma_ok = [](const int* n) { return n[0] % 4 == 0 && n[0] >= 32 && n[1] >= 8; };  // stencil_tma.cu: eligible<float>()
+	for (int d = 0; d < kMaxDim; ++d) { plan.size[0][d] = sizes[d]; }
+	FI_REQUIRE(tma_ok(plan.size[0]), FI_ERR_UNSUPPORTED, "slab multigrid: the x size must be a multiple of 4 and >= 32, the y size >= 8");
+	plan.own[0].resize(world);
+	for (int k = 0; k < world; ++k) {
+		slab_range(sizes[2], world, k, &plan.own[0][k].first, &plan.own[0][k].second);
+		FI_REQUIRE(plan.own[0][k].second - plan.own[0][k].first >= plan.halo, FI_ERR_UNSUPPORTED, "slab multigrid: slabs thinner than the halo: use fewer ranks");
+	}
+	for (int l = 0;; ++l) {
+		// the next level and who restricts into which of its planes
+		int*       nc = plan.size[l + 1];
+		const int* nf = plan.size[l];
+		int        smallest = 1 << 30;
+		int64_t    cells = 1;
+		for (int d = 0; d < kMaxDim; ++d) {
+			nc[d] = (nf[d] + 1) / 2;
+			cells *= nc[d];
+			smallest = std::min(smallest, nc[d]);
+		}
+		FI_REQUIRE(smallest >= 4, FI_ERR_UNSUPPORTED, "slab multigrid: the lattice is too small to coarsen");
+		const AxisTables tz = axis_tables(nf[2], nc[2]);
+		auto owner_of_fine = [&](int z) {
+			for (int k = 0; k < world; ++k) {
+				if (z >= plan.own[l][k].first && z < plan.own[l][k].second) { return k; }
+			}
+			return -1;
+		};
+		std::vector<std::pair<int, int>>& oc = plan.own[l + 1];
+		oc.assign(world, std::make_pair(-1, -1));
+		int last_owner = 0;
+		for (int C = 0; C < nc[2]; ++C) {
+			FI_REQUIRE(tz.count[C] >= 1, FI_ERR_UNSUPPORTED, "slab multigrid: a coarse plane without fine planes");
+			const int mid = tz.first[C] + tz.count[C] / 2;  // the middle one of the fine planes restriction reads
+			const int k   = owner_of_fine(std::min(mid, tz.first[C] + tz.count[C] - 1));
+			FI_REQUIRE(k >= last_owner, FI_ERR_UNSUPPORTED, "slab multigrid: coarse plane owners are not monotone");
+			last_owner = k;
+			if (oc[k].first < 0) { oc[k].first = C; }
+			oc[k].second = C + 1;
+			// restriction of this plane stays inside the owner's stored window
+			FI_REQUIRE(tz.first[C] >= plan.own[l][k].first - plan.halo && tz.first[C] + tz.count[C] <= plan.own[l][k].second + plan.halo, FI_ERR_UNSUPPORTED,
+			           "slab multigrid: restriction reaches beyond the halo planes");
+		}
+		for (int k = 0; k < world; ++k) {
+			FI_REQUIRE(oc[k].first >= 0, FI_ERR_UNSUPPORTED, "slab multigrid: a rank owns no plane of a coarse level: use fewer ranks");
+			FI_REQUIRE(k == 0 ? oc[k].first == 0 : oc[k].first == oc[k - 1].second, FI_ERR_UNSUPPORTED, "slab multigrid: coarse planes are not partitioned");
+		}
+		FI_REQUIRE(oc[world - 1].second == nc[2], FI_ERR_UNSUPPORTED, "slab multigrid: coarse planes are not partitioned");
+		plan.nd = l + 1;
+		// is the next level sharded too?
+		bool shard = cells > gather_cells && tma_ok(nc) && l + 2 <= kMaxSlabLevels && (nc[2] + 1) / 2 >= 4;
+		for (int k = 0; shard && k < world; ++k) {
+			shard = oc[k].second - oc[k].first >= plan.halo;
+			// prolongation into this rank's planes of level l reads planes base, base + 1 of level l + 1: inside its window there
+			for (int z = plan.own[l][k].first; shard && z < plan.own[l][k].second; ++z) {
+				const int b0 = tz.base[z], b1 = std::min(tz.base[z] + 1, nc[2] - 1);
+				shard = b0 >= oc[k].first - plan.halo && b1 < oc[k].second + plan.halo;
+			}
+		}
+		if (!shard) { break; }
+	}
+	return plan;
+}
+
+std::unique_ptr<SlabMultigrid> build_slab_multigrid(Operator<float>& fine, const ModelAccum& model, const PointStore& pts, const MgOptions& opt,
+                                                    const SlabMgPlan& plan, cudaStream_t s)
+{
+	TraceScope trace("build_slab_multigrid");
+	FI_REQUIRE(fine.dist != nullptr && fine.g.ndim == 3, FI_ERR_INVALID, "build_slab_multigrid needs a 3D slab operator with its communicator hooks");
+	DistHooks& hooks0 = *fine.dist;
+	const int  rank = hooks0.rank(), world = hooks0.world();
+	FI_REQUIRE(world == plan.world && plan.nd >= 1, FI_ERR_INVALID, "slab multigrid: the plan is for another communicator");
+	FI_REQUIRE(fine.g.zown0 == plan.halo && fine.g.zoff == plan.own[0][rank].first - plan.halo && fine.g.zown1 - fine.g.zown0 == plan.own[0][rank].second - plan.own[0][rank].first,
+	           FI_ERR_INVALID, "slab multigrid: the fine operator's slab is not the plan's");
+	auto mg  = std::make_unique<SlabMultigrid>();
+	mg->opt  = opt;
+	mg->plan = plan;
+	mg->rank = rank;
+	const int D = 3;
+	HostRows  none;
+	// sharded levels
+	for (int l = 0; l < plan.nd; ++l) {
+		auto lv = std::make_unique<SlabMultigrid::DLevel>();
+		if (l == 0) {
+			lv->g     = fine.g;
+			lv->op    = &fine;
+			lv->hooks = &hooks0;
+		} else {
+			lv->g           = make_slab_geom(plan.size[l], plan.own[l][rank].first, plan.own[l][rank].second, plan.halo);
+			lv->owned_hooks = hooks0.for_geom(lv->g, plan.halo);
+			FI_REQUIRE(lv->owned_hooks != nullptr, FI_ERR_UNSUPPORTED, "slab multigrid: the communicator cannot serve another level");
+			lv->hooks = lv->owned_hooks.get();
+			ModelAccum m;
+			level_inputs(D, plan.size[0], model, pts, lv->g, l, m, lv->pts, s);
+			lv->owned       = build_operator<float>(lv->g, m, lv->pts, none, s);
+			lv->op          = lv->owned.get();
+			lv->op->dist    = lv->hooks;
+			lv->op->use_fast = kStencilAuto;
+		}
+		lv->c0 = plan.own[l + 1][rank].first;
+		lv->c1 = plan.own[l + 1][rank].second;
+		const size_t n = static_cast<size_t>(lv->g.N);
+		if (l > 0) {
+			lv->r.resize(n);
+			lv->e.resize(n);
+			lv->r.zero(s);
+			lv->e.zero(s);
+		}
+		lv->res.resize(n);
+		lv->d.resize(n);
+		lv->q.resize(n);
+		lv->res.zero(s);  // halo planes and planes beyond the lattice must be finite (zero) before anything reads them
+		lv->d.zero(s);
+		lv->q.zero(s);
+		const Geom gf = make_geom(D, plan.size[l]), gc = make_geom(D, plan.size[l + 1]);
+		build_xfer(lv->to_coarser, lv->xfer_int, lv->xfer_float, gf, gc, s);
+		mg->dl.push_back(std::move(lv));
+	}
+	// the first replicated level and everything below it
+	{
+		const Geom gt = make_geom(D, plan.size[plan.nd]);
+		ModelAccum m;
+		level_inputs(D, plan.size[0], model, pts, gt, plan.nd, m, mg->tail_pts, s);
+		mg->tail_op           = build_operator<float>(gt, m, mg->tail_pts, none, s);
+		mg->tail_op->use_fast = kStencilAuto;
+		mg->tail              = build_multigrid(*mg->tail_op, model, pts, opt, s, plan.size[0], plan.nd);
+		mg->tail_r.resize(static_cast<size_t>(gt.N));
+		mg->tail_e.resize(static_cast<size_t>(gt.N));
+		mg->tail_r.zero(s);
+		mg->tail_e.zero(s);
+	}
+	// largest eigenvalue of D^-1 A per sharded level: power iteration from the start vector the unsharded hierarchy uses
+	{
+		DevBuf<double>   out(2), partial(static_cast<size_t>(2) * (static_cast<size_t>(sm_count()) * 8 + 8));
+		DevBuf<unsigned> ticket(1);
+		ticket.zero(s);
+		for (int l = 0; l < plan.nd; ++l) {
+			SlabMultigrid::DLevel& lv  = *mg->dl[l];
+			const int64_t          off = lv.g.own_offset(), n = lv.g.own_cells();
+			float *                v = lv.d.data(), *w = lv.res.data();
+			FI_LAUNCH(hash_fill_kernel, vgrid(n), kThreads, 0, s, n, v + off, static_cast<int64_t>(plan.own[l][rank].first) * lv.g.stride[2]);
+			double lam = 1.0;
+			for (int it = 0; it < opt.power_iterations; ++it) {
+				lv.hooks->exchange_halo(v, sizeof(float), s);
+				lv.op->apply(v, lv.q.data(), nullptr, nullptr, s);
+				FI_LAUNCH(power_step_kernel, vgrid(n), kThreads, 0, s, n, v + off, lv.q.data() + off, lv.op->minv.data() + off, w + off, out.data(), partial.data(),
+				          ticket.data());
+				lv.hooks->allreduce(out.data(), 2, s);
+				double h[2];
+				FI_CUDA(cudaMemcpyAsync(h, out.data(), sizeof(h), cudaMemcpyDeviceToHost, s));
+				FI_CUDA(cudaStreamSynchronize(s));
+				const double nw = std::sqrt(h[0]);
+				FI_REQUIRE(nw > 0 && std::isfinite(nw), FI_ERR_INVALID, "slab multigrid: power iteration broke down");
+				lam = nw;
+				FI_LAUNCH(scale_kernel, vgrid(n), kThreads, 0, s, n, w + off, static_cast<float>(1.0 / nw));
+				std::swap(v, w);
+			}
+			lv.lmax = lam * 1.1;
+			// the smoother expects clean work vectors: halo planes are refilled by exchanges, owned planes overwritten
+		}
+	}
+	return mg;
+}
+
+namespace {
+
+// q = A v on the slab's owned rows, after refreshing v's halo planes from the neighbours
+void slab_apply(SlabMultigrid::DLevel& lv, float* v, cudaStream_t s)
+{
+	lv.hooks->exchange_halo(v, sizeof(float), s);
+	lv.op->apply(v, lv.q.data(), nullptr, nullptr, s);
+}
+
+// nu Chebyshev steps on A e = r over the slab's owned planes (the unfused form of smooth()).  Returns the residual
+// before the last correction and the last correction, like smooth().
+Smoothed slab_smooth(SlabMultigrid::DLevel& lv, const MgOptions& opt, const float* r, float* e, bool e_zero, cudaStream_t s)
+{
+	const int64_t off = lv.g.own_offset(), n = lv.g.own_cells();
+	const double  lmax  = lv.lmax, lmin = lmax / opt.cheb_ratio;
+	const double  theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
+	float *       d = lv.d.data(), *res = lv.res.data();
+	const float*  minv = lv.op->minv.data();
+	const float*  res_src = r;
+	const float   b0 = static_cast<float>(1.0 / theta);
+	if (e_zero) {  // res = r: d = b0 M^-1 r, e = d
+		FI_LAUNCH(cheb_step_kernel, vgrid(n), kThreads, 0, s, n, r + off, res + off, static_cast<const float*>(nullptr), d + off, minv + off, e + off, 0.0f, b0, 1);
+	} else {  // res = r - A e, then the first step from it
+		slab_apply(lv, e, s);
+		FI_LAUNCH(cheb_step_kernel, vgrid(n), kThreads, 0, s, n, r + off, res + off, static_cast<const float*>(lv.q.data() + off), d + off, minv + off, e + off, 0.0f,
+		          b0, 0);
+		res_src = res;
+	}
+	double rho = 1.0 / sigma;
+	for (int k = 1; k < opt.nu; ++k) {
+		const double rho_new = 1.0 / (2.0 * sigma - rho);
+		const float  a = static_cast<float>(rho_new * rho), b = static_cast<float>(2.0 * rho_new / delta);
+		slab_apply(lv, d, s);
+		FI_LAUNCH(cheb_step_kernel, vgrid(n), kThreads, 0, s, n, res_src + off, res + off, static_cast<const float*>(lv.q.data() + off), d + off, minv + off, e + off,
+		          a, b, 0);
+		res_src = res;
+		rho     = rho_new;
+	}
+	return Smoothed{res_src, d};
+}
+
+void slab_vcycle_level(SlabMultigrid& mg, int l, const float* r, float* e, cudaStream_t s)
+{
+	SlabMultigrid::DLevel& lv  = *mg.dl[l];
+	const int64_t          off = lv.g.own_offset(), n = lv.g.own_cells();
+	const int              z0 = mg.plan.own[l][mg.rank].first, z1 = mg.plan.own[l][mg.rank].second;
+	const bool             last = l + 1 == mg.plan.nd;
+	const Smoothed         sm = slab_smooth(lv, mg.opt, r, e, true, s);
+	// residual after the last correction
+	slab_apply(lv, sm.d, s);
+	FI_LAUNCH(residual_sub_kernel, vgrid(n), kThreads, 0, s, n, sm.res + off, static_cast<const float*>(lv.q.data() + off), lv.res.data() + off);
+	lv.hooks->exchange_halo(lv.res.data(), sizeof(float), s);
+	// restriction into the planes [c0, c1) of the next level: the kernel indexes fine planes by their lattice z, so the
+	// slab pointer is moved back by the slab's first stored plane; the z tables start at c0
+	const int64_t plane_f = lv.g.stride[2];
+	const int64_t plane_c = static_cast<int64_t>(lv.to_coarser.nc[0]) * lv.to_coarser.nc[1];
+	{
+		Xfer x = lv.to_coarser;
+		x.first[2] += lv.c0;
+		x.count[2] += lv.c0;
+		x.weight[2] += static_cast<size_t>(lv.c0) * kMaxFan;
+		const float* rf = lv.res.data() - static_cast<int64_t>(lv.g.zoff) * plane_f;
+		float*       rc = last ? mg.tail_r.data() + static_cast<int64_t>(lv.c0) * plane_c : mg.dl[l + 1]->r.data() + mg.dl[l + 1]->g.own_offset();
+		FI_LAUNCH(restrict_kernel, dim3(div_up(x.nc[0], 128), x.nc[1], lv.c1 - lv.c0), 128, 0, s, x, rf, rc);
+	}
+	const float* ec = nullptr;  // the coarse correction, indexable by the lattice z of the next level
+	if (last) {
+		lv.hooks->allgather_planes(mg.tail_r.data(), plane_c, mg.plan.own[l + 1], s);
+		mg.tail->vcycle(mg.tail_r.data(), mg.tail_e.data(), s);
+		ec = mg.tail_e.data();
+	} else {
+		SlabMultigrid::DLevel& lc = *mg.dl[l + 1];
+		slab_vcycle_level(mg, l + 1, lc.r.data(), lc.e.data(), s);
+		lc.hooks->exchange_halo(lc.e.data(), sizeof(float), s);
+		ec = lc.e.data() - static_cast<int64_t>(lc.g.zoff) * plane_c;
+	}
+	{
+		Xfer x = lv.to_coarser;
+		x.base[2] += z0;
+		x.frac[2] += z0;
+		FI_LAUNCH(prolong_add_kernel, dim3(div_up(x.nf[0], 128), x.nf[1], z1 - z0), 128, 0, s, x, ec, e + off);
+	}
+	slab_smooth(lv, mg.opt, r, e, false, s);
+}
+
+}  // namespace
+
+void SlabMultigrid::vcycle(const float* r, float* z, cudaStream_t s) { slab_vcycle_level(*this, 0, r, z, s); }
+
 // CG on A x = b preconditioned by one V-cycle per iteration.  Scalars travel through the host (three small reads
-// per iteration against several milliseconds of device work).  Same stopping rule as pcg_solve.
-template <typename T>
-PcgResult mgpcg_solve(Operator<T>& op, Multigrid& mg, const T* b, T* x, double tol, long long max_iter, cudaStream_t s)
+// per iteration against several milliseconds of device work).  Same stopping rule as pcg_solve.  With op.dist set
+// the vectors are slab-local: the vector kernels run over the owned planes, the halo planes of whatever the operator
+// is applied to are exchanged first, and every sum is all-reduced before the host reads it.
+namespace {
+
+template <typename T, typename Precond>
+PcgResult mgpcg_impl(Operator<T>& op, Precond& mg, const T* b, T* x, double tol, long long max_iter, cudaStream_t s)
 {
 	TraceScope    trace("mgpcg_solve");
-	const int64_t n   = op.g.N;
+	DistHooks*    dist = op.dist;
+	const int64_t N = op.g.N, off = op.g.own_offset(), n = op.g.own_cells();
 	const T*      rhs = b ? b : op.atb.data();
-	if (max_iter <= 0) { max_iter = 2 * n; }
+	if (max_iter <= 0) { max_iter = 2 * static_cast<long long>(op.g.size[0]) * op.g.size[1] * op.g.size[2]; }
 	if (!(tol > 0)) { tol = std::is_same<T, float>::value ? 1.1920929e-07 : 2.220446049250313e-16; }
-	DevBuf<T>        r(n), p(n), q(n);
-	DevBuf<float>    r32(n), z(n);
+	DevBuf<T>        r(N), p(N), q(N);
+	DevBuf<float>    r32(N), z(N);
 	DevBuf<double>   out(2), partial(static_cast<size_t>(2) * (static_cast<size_t>(sm_count()) * 8 + 8));
 	DevBuf<unsigned> ticket(1);
 	ticket.zero(s);
+	if (dist) {  // halo planes and planes beyond the lattice are read by the stencil kernels: start finite
+		r.zero(s);
+		q.zero(s);
+		r32.zero(s);
+		z.zero(s);
+	}
 	cudaEvent_t e0, e1;
 	FI_CUDA(cudaEventCreate(&e0));
 	FI_CUDA(cudaEventCreate(&e1));
 	FI_CUDA(cudaEventRecord(e0, s));
-	auto read2 = [&](double* h) {
-		FI_CUDA(cudaMemcpyAsync(h, out.data(), 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+	auto read = [&](double* h, int count) {
+		if (dist) { dist->allreduce(out.data(), count, s); }
+		FI_CUDA(cudaMemcpyAsync(h, out.data(), count * sizeof(double), cudaMemcpyDeviceToHost, s));
 		FI_CUDA(cudaStreamSynchronize(s));
 	};
 	const int grid = vgrid(n);
 	PcgResult res;
 	double    h[2] = {0, 0};
+	if (dist) { dist->exchange_halo(x, sizeof(T), s); }
 	op.apply(x, q.data(), nullptr, nullptr, s);
 	{
 		auto k = mg_residual_kernel<T>;
-		FI_LAUNCH(k, grid, kThreads, 0, s, n, rhs, q.data(), r.data(), r32.data(), out.data(), partial.data(), ticket.data());
+		FI_LAUNCH(k, grid, kThreads, 0, s, n, rhs + off, q.data() + off, r.data() + off, r32.data() + off, out.data(), partial.data(), ticket.data());
 	}
-	read2(h);
+	read(h, 2);
 	double       rr = h[0];
 	const double bb = h[1];
 	res.zero_rhs         = bb == 0.0;
@@ -678,7 +1001,7 @@ PcgResult mgpcg_solve(Operator<T>& op, Multigrid& mg, const T* b, T* x, double t
 	const double target  = tol * tol * bb;
 	long long    it      = 0;
 	if (res.zero_rhs) {
-		FI_CUDA(cudaMemsetAsync(x, 0, n * sizeof(T), s));
+		FI_CUDA(cudaMemsetAsync(x + off, 0, n * sizeof(T), s));
 		rr = 0;
 	} else if (rr > target) {
 		double rz = 0;
@@ -687,28 +1010,29 @@ PcgResult mgpcg_solve(Operator<T>& op, Multigrid& mg, const T* b, T* x, double t
 			mg.vcycle(r32.data(), z.data(), s);
 			{
 				auto k = mg_dot_kernel<T>;
-				FI_LAUNCH(k, grid, kThreads, 0, s, n, r.data(), z.data(), out.data(), partial.data(), ticket.data());
+				FI_LAUNCH(k, grid, kThreads, 0, s, n, r.data() + off, z.data() + off, out.data(), partial.data(), ticket.data());
 			}
-			read2(h);
+			read(h, 1);
 			const double rz_new = h[0];
 			if (!(rz_new > 0.0) || !std::isfinite(rz_new)) { break; }  // breakdown: keep the last iterate
 			const double beta = it == 0 ? 0.0 : rz_new / rz;
 			rz                = rz_new;
 			{
 				auto k = mg_direction_kernel<T>;
-				FI_LAUNCH(k, grid, kThreads, 0, s, n, z.data(), p.data(), static_cast<T>(beta));
+				FI_LAUNCH(k, grid, kThreads, 0, s, n, z.data() + off, p.data() + off, static_cast<T>(beta));
 			}
+			if (dist) { dist->exchange_halo(p.data(), sizeof(T), s); }
 			op.apply(p.data(), q.data(), out.data(), nullptr, s);
-			read2(h);
+			read(h, 1);
 			const double pq = h[0];
 			if (!(pq > 0.0) || !std::isfinite(pq)) { break; }
 			const double alpha = rz / pq;
 			{
 				auto k = mg_update_kernel<T>;
-				FI_LAUNCH(k, grid, kThreads, 0, s, n, x, r.data(), p.data(), q.data(), r32.data(), static_cast<T>(alpha), out.data(), partial.data(),
-				          ticket.data());
+				FI_LAUNCH(k, grid, kThreads, 0, s, n, x + off, r.data() + off, p.data() + off, q.data() + off, r32.data() + off, static_cast<T>(alpha), out.data(),
+				          partial.data(), ticket.data());
 			}
-			read2(h);
+			read(h, 1);
 			rr = h[0];
 			++it;
 			if (rr <= target) { break; }
@@ -734,7 +1058,25 @@ PcgResult mgpcg_solve(Operator<T>& op, Multigrid& mg, const T* b, T* x, double t
 	return res;
 }
 
+}  // namespace
+
+template <typename T>
+PcgResult mgpcg_solve(Operator<T>& op, Multigrid& mg, const T* b, T* x, double tol, long long max_iter, cudaStream_t s)
+{
+	FI_REQUIRE(op.dist == nullptr && !op.g.sharded(), FI_ERR_UNSUPPORTED, "mgpcg_solve takes an unsharded lattice (slabs: slab_mgpcg_solve)");
+	return mgpcg_impl<T, Multigrid>(op, mg, b, x, tol, max_iter, s);
+}
+
+template <typename T>
+PcgResult slab_mgpcg_solve(Operator<T>& op, SlabMultigrid& mg, const T* b, T* x, double tol, long long max_iter, cudaStream_t s)
+{
+	FI_REQUIRE(op.dist != nullptr, FI_ERR_INVALID, "slab_mgpcg_solve needs the slab's communicator hooks");
+	return mgpcg_impl<T, SlabMultigrid>(op, mg, b, x, tol, max_iter, s);
+}
+
 template PcgResult mgpcg_solve<float>(Operator<float>&, Multigrid&, const float*, float*, double, long long, cudaStream_t);
 template PcgResult mgpcg_solve<double>(Operator<double>&, Multigrid&, const double*, double*, double, long long, cudaStream_t);
+template PcgResult slab_mgpcg_solve<float>(Operator<float>&, SlabMultigrid&, const float*, float*, double, long long, cudaStream_t);
+template PcgResult slab_mgpcg_solve<double>(Operator<double>&, SlabMultigrid&, const double*, double*, double, long long, cudaStream_t);
 
 }  // namespace fi

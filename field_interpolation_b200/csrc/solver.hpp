@@ -1,6 +1,7 @@
 // Normal-equation operator and the preconditioned conjugate-gradient driver (solver.cu).
 #pragma once
 
+#include <utility>
 #include <vector>
 
 #include "internal.hpp"
@@ -81,6 +82,20 @@ struct DistHooks
 	virtual void allreduce(double* d_ptr, int count, cudaStream_t s) = 0;
 	// fills the halo planes of a local lattice vector from the neighbouring slabs' owned planes
 	virtual void exchange_halo(void* d_vec, size_t elem_size, cudaStream_t s) = 0;
+	virtual int rank() const { return 0; }
+	virtual int world() const { return 1; }
+	// hooks on the same communicator for another slab geometry (a coarser multigrid level); NCCL path only
+	virtual std::unique_ptr<DistHooks> for_geom(const Geom& g, int halo)
+	{
+		(void)g; (void)halo;
+		return nullptr;
+	}
+	// `full` is a whole (unsharded) lattice vector of planes of `plane_cells` floats of which rank k has filled planes
+	// [own[k].first, own[k].second); afterwards every rank holds every plane (all-gather with ragged counts)
+	virtual void allgather_planes(float* full, int64_t plane_cells, const std::vector<std::pair<int, int>>& own, cudaStream_t s)
+	{
+		(void)full; (void)plane_cells; (void)own; (void)s;
+	}
 };
 
 template <typename T>
@@ -193,12 +208,64 @@ struct Multigrid
 };
 
 // Builds the hierarchy under `fine` (which must outlive it): re-discretised coarse operators from the same points
-// and the same smoothness model, Chebyshev bounds, dense coarsest inverse.
-std::unique_ptr<Multigrid> build_multigrid(Operator<float>& fine, const ModelAccum& model, const PointStore& pts, const MgOptions& opt, cudaStream_t s);
+// and the same smoothness model, Chebyshev bounds, dense coarsest inverse.  `model` / `pts` describe the ROOT lattice
+// of the hierarchy (sizes root_size; null: fine.g.size) and `fine` is its level `fine_level` (0: the root itself) —
+// the slab-sharded V-cycle hands the levels below its last sharded one to a hierarchy built this way, so that every
+// level's operator is the one the single-GPU hierarchy would have.
+std::unique_ptr<Multigrid> build_multigrid(Operator<float>& fine, const ModelAccum& model, const PointStore& pts, const MgOptions& opt, cudaStream_t s,
+                                           const int* root_size = nullptr, int fine_level = 0);
+
+// ---- mg.cu: the same V-cycle with the finest levels z-slab sharded over the ranks of a communicator -------------
+// Levels 0 .. nd-1 are sharded (each rank smooths its slab; halo planes of the smoothed vector are exchanged before
+// every operator application), level nd and everything below it is replicated: the restricted residual is
+// all-gathered and every rank runs the rest of the V-cycle (a plain `Multigrid`, one CUDA graph) redundantly, then
+// prolongs into its own planes.  Coarse plane C of a level pair belongs to the rank that owns the middle one of the
+// fine planes restriction reads for it, so restriction needs at most `halo` (>= 2) planes from a neighbour.
+constexpr int kMaxSlabLevels = 8;
+
+struct SlabMgPlan  // pure host arithmetic, identical on every rank
+{
+	int nd   = 0;                    // sharded levels (>= 1)
+	int halo = 2;                    // halo planes stored per side on every sharded level
+	int world = 1;
+	int size[kMaxSlabLevels + 1][kMaxDim] = {};             // lattice sizes of levels 0 .. nd
+	std::vector<std::pair<int, int>> own[kMaxSlabLevels + 1];  // own[l][rank]: planes [z0, z1) of level l (for level nd: the planes the rank restricts into)
+};
+
+// Throws FI_ERR_UNSUPPORTED when level 0 cannot be sharded this way (slabs thinner than the halo, sizes the TMA stencil
+// kernel does not take, a restriction that would reach beyond the halo).  gather_cells: levels with at most this many
+// cells are replicated.
+SlabMgPlan plan_slab_multigrid(const int32_t* sizes, int world, int radius, int64_t gather_cells);
+
+struct SlabMultigrid
+{
+	struct DLevel;
+	MgOptions                             opt;
+	SlabMgPlan                            plan;
+	int                                   rank = 0;
+	std::vector<std::unique_ptr<DLevel>>  dl;       // sharded levels, 0 = finest
+	std::unique_ptr<Operator<float>>      tail_op;  // first replicated level (unsharded lattice)
+	PointStore                            tail_pts;
+	std::unique_ptr<Multigrid>            tail;
+	DevBuf<float>                         tail_r, tail_e;
+
+	SlabMultigrid();
+	~SlabMultigrid();
+	// z = V-cycle(r) on slab-local vectors of the finest level (owned planes are read / written)
+	void vcycle(const float* r, float* z, cudaStream_t s);
+};
+
+// fine: this rank's slab operator of the finest level with fine.dist set (it must outlive the hierarchy); model / pts:
+// the whole problem (every rank holds all points).
+std::unique_ptr<SlabMultigrid> build_slab_multigrid(Operator<float>& fine, const ModelAccum& model, const PointStore& pts, const MgOptions& opt,
+                                                    const SlabMgPlan& plan, cudaStream_t s);
 
 // CG preconditioned by one V-cycle per iteration; same contract as pcg_solve.
 template <typename T>
 PcgResult mgpcg_solve(Operator<T>& op, Multigrid& mg, const T* b, T* x, double tol, long long max_iter, cudaStream_t s);
+// The same on a slab (op.dist set; x / b are slab-local vectors, every rank calls this together).
+template <typename T>
+PcgResult slab_mgpcg_solve(Operator<T>& op, SlabMultigrid& mg, const T* b, T* x, double tol, long long max_iter, cudaStream_t s);
 
 // Tile phase of solve_tiled_with_guess (reference sparse_linear.cpp:246-390): x holds the guess on entry and the
 // tile-by-tile solution on exit.  The returned statistics are those of the block-diagonal solve.

@@ -201,6 +201,8 @@ void stencil_apply(const Geom& g, const StencilTables& t, const T* p, T* q, doub
 	if (g.tile) { mode = kStencilGeneric; }  // only the generic kernel knows the tile mask
 	if (mode == kStencilAuto && stencil_tma_3d<T>(g, t, p, q, d_dot_out, d_partial, d_ticket, d_done, s)) { return; }
 	if (mode != kStencilGeneric && stencil_fast_3d<T>(g, t, p, q, d_dot_out, d_partial, d_ticket, d_done, s)) { return; }
+	// the generic kernel runs over every stored node and would read beyond a slab's halo planes
+	FI_REQUIRE(!g.sharded(), FI_ERR_UNSUPPORTED, "a slab-sharded lattice needs the TMA-staged 3D stencil kernel (x size a multiple of 16 bytes and >= 32, y size >= 8)");
 	auto kern = stencil_generic_kernel<T>;
 	FI_LAUNCH(kern, div_up(g.N, kThreads), kThreads, 0, s, g, to_dev<T>(t), p, q, d_dot_out, d_partial, d_ticket, d_done);
 }

@@ -21,6 +21,21 @@ def slab_range(nz: int, world: int, rank: int):
     return int(z0.value), int(z1.value)
 
 
+def slab_mg_plan(sizes, world: int, stencil_radius: int = 2, gather_cells: int = 0):
+    """How a multigrid-preconditioned slab solve shards its V-cycle (fi_slab_mg_plan, host only): a dict with
+    `halo`, `sharded_levels`, `sizes[l]` and `own[l][rank] = (z0, z1)` for l = 0 .. sharded_levels (the last level
+    listed is the first replicated one; its ranges say who restricts into which planes)."""
+    sz = (C.c_int32 * 3)(*[int(v) for v in sizes])
+    nd, halo = C.c_int32(0), C.c_int32(0)
+    lsz = (C.c_int32 * 27)()
+    rng = (C.c_int32 * (18 * int(world)))()
+    L.check(L.lib().fi_slab_mg_plan(sz, int(world), int(stencil_radius), int(gather_cells), C.byref(nd), C.byref(halo), lsz, rng))
+    levels = nd.value + 1
+    return {"halo": int(halo.value), "sharded_levels": int(nd.value),
+            "sizes": [[int(lsz[3 * l + d]) for d in range(3)] for l in range(levels)],
+            "own": [[(int(rng[2 * (l * world + k)]), int(rng[2 * (l * world + k) + 1])) for k in range(world)] for l in range(levels)]}
+
+
 def broadcast_unique_id(dist, rank: int, device=None) -> bytes:
     """Rank 0 asks the library for an NCCL id; everyone receives it through torch.distributed."""
     import torch

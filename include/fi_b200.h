@@ -56,7 +56,8 @@ enum fi_precision { FI_F32 = 0, FI_F64 = 1, FI_MIXED = 2 };
  * reference's BiCGSTAB uses).  FI_PRECOND_MULTIGRID = one geometric-multigrid V-cycle per iteration: the reference's
  * coarse-to-fine idea (the same problem re-assembled on coarser lattices, src/sdf_field.cpp:251-304) applied to the
  * error on every level; iteration counts stop growing with the lattice size.  The V-cycle runs in fp32; with FI_F64
- * (or FI_MIXED, the same thing here) the outer CG and its residual are fp64.  One GPU. */
+ * (or FI_MIXED, the same thing here) the outer CG and its residual are fp64.  One GPU through fi_field_solve, z-slab
+ * sharded through fi_slab_sdf_solve. */
 enum fi_preconditioner { FI_PRECOND_JACOBI = 0, FI_PRECOND_MULTIGRID = 1 };
 
 /* Weights, field_interpolation.hpp:75-95 (same field order and defaults; see fi_weights_default) */
@@ -230,11 +231,22 @@ FI_API int fi_comm_create(int32_t rank, int32_t world, const void* id, fi_comm**
 FI_API int fi_comm_destroy(fi_comm* c);
 /* Planes [z0, z1) of an nz-plane lattice owned by `rank` (contiguous, balanced to one plane).  Pure host code. */
 FI_API int fi_slab_range(int32_t nz, int32_t world, int32_t rank, int32_t* z0, int32_t* z1);
+/* How a FI_PRECOND_MULTIGRID slab solve shards its V-cycle over `world` ranks (pure host code, the same on every
+ * rank): levels 0 .. *sharded_levels - 1 are z-slab sharded, level *sharded_levels and everything below it is
+ * replicated (its restricted residual is all-gathered).  stencil_radius = highest active model order (1..4);
+ * gather_cells: levels with at most this many cells are replicated (<= 0: 3,000,000).  Outputs for levels
+ * l = 0 .. *sharded_levels: level_sizes[3 l + d] (room for 27 ints) and plane_ranges[2 (l world + rank) + {0, 1}] = the
+ * planes [z0, z1) of level l that `rank` owns / restricts into (room for 18 * world ints).  *halo = planes stored
+ * per side.  FI_ERR_UNSUPPORTED when the lattice cannot be sharded this way. */
+FI_API int fi_slab_mg_plan(const int32_t* sizes /* 3 */, int32_t world, int32_t stencil_radius, int64_t gather_cells, int32_t* sharded_levels,
+                    int32_t* halo, int32_t* level_sizes, int32_t* plane_ranges);
 /* sdf_from_points + PCG on the slab of this rank: every rank passes the whole point cloud (positions in lattice
  * coordinates of the full lattice) and receives its owned planes, (z1 - z0) * nx * ny floats, in solution_own.
  * Collective: all ranks of the communicator call it together with the same arguments except the buffers.
  * guess_own (nullable) is this rank's part of the starting guess.  FI_F32 or FI_F64; star-shaped smoothness
- * (gradient_smoothness = 0), nearest / cell-edge gradient kernels. */
+ * (gradient_smoothness = 0), nearest / cell-edge gradient kernels.  opt->preconditioner = FI_PRECOND_MULTIGRID runs
+ * the V-cycle sharded the way fi_slab_mg_plan says (halo planes by ncclSend/ncclRecv before every operator
+ * application of the smoother, one all-gather of the restricted residual per V-cycle). */
 FI_API int fi_slab_sdf_solve(fi_comm* c, const int32_t* sizes /* 3 */, const fi_weights* w, int64_t num_points,
                       const float* positions, const float* normals, const float* point_weights, int32_t loc,
                       const fi_solve_options* opt, const float* guess_own, float* solution_own, int32_t solution_loc,

@@ -1,7 +1,10 @@
 """Multi-GPU parity check (run under torchrun on >= 2 GPUs): the z-slab sharded solve against the single-GPU
 solve of the same system, iterate for iterate.
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 scripts/slab_check.py
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 scripts/slab_check.py [--mg-only]
+
+Second half: multigrid-preconditioned CG through the sharded V-cycle against the single-GPU V-cycle (same iteration
+count within rounding, same field).
 """
 import json
 import os
@@ -20,8 +23,9 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ok = True
-for sizes, npts, orders in (([64, 48, 40], 4000, {}), ([128, 64, 37], 20000, dict(model_1=0.3)), ([96, 40, 64], 8000, dict(model_2=0.0, model_4=0.2)),
-                            ([256, 256, 256], 1000000, {})):
+PCG_CASES = () if "--mg-only" in sys.argv else (([64, 48, 40], 4000, {}), ([128, 64, 37], 20000, dict(model_1=0.3)), ([96, 40, 64], 8000, dict(model_2=0.0, model_4=0.2)),
+                            ([256, 256, 256], 1000000, {}))
+for sizes, npts, orders in PCG_CASES:
     cloud = W.sphere_torus_3d(npts, seed=1)
     pos = W.to_lattice(cloud["unit_pos"], sizes)
     weights = fi.Weights(**orders)
@@ -47,6 +51,53 @@ for sizes, npts, orders in (([64, 48, 40], 4000, {}), ([128, 64, 37], 20000, dic
                                   "relres_single": st1["relative_residual"], "true_slab": st["true_residual"], "true_single": st1["true_residual"], "ok": bool(good)}), flush=True)
                 f.close()
     runner.close()
+
+# ---- multigrid-preconditioned CG: the sharded V-cycle against the single-GPU V-cycle (the same linear operator) --------
+def gather_own(out, sizes):
+    parts = [torch.zeros((fid.slab_range(sizes[2], world, r)[1] - fid.slab_range(sizes[2], world, r)[0]) * sizes[0] * sizes[1], device="cuda")
+             for r in range(world)]
+    dist.all_gather(parts, out)
+    return torch.cat(parts).cpu().numpy()
+
+
+for sizes, npts, orders, gather in (([64, 48, 40], 5000, {}, 1000), ([128, 64, 72], 20000, dict(model_1=0.2), 0), ([128, 128, 128], 200000, {}, 100000),
+                                    ([256, 256, 256], 1000000, {}, 0), ([256, 256, 256], 1000000, {}, 300000)):
+    if gather:
+        os.environ["FI_B200_MG_GATHER_CELLS"] = str(gather)
+    else:
+        os.environ.pop("FI_B200_MG_GATHER_CELLS", None)
+    radius = 2
+    try:
+        plan = fid.slab_mg_plan(sizes, world, radius, gather)
+    except Exception as e:  # slabs too thin for this many ranks: every rank skips alike
+        if rank == 0:
+            print(json.dumps({"mg": True, "sizes": sizes, "skipped": str(e)}), flush=True)
+        continue
+    cloud = W.sphere_torus_3d(npts, seed=2)
+    pos = W.to_lattice(cloud["unit_pos"], sizes)
+    weights = fi.Weights(**orders)
+    runner = fid.SlabRunner(sizes, weights, rank, world, dist)
+    d_pos, d_nrm = torch.from_numpy(pos).cuda(), torch.from_numpy(cloud["normals"]).cuda()
+    for prec, name, tol, close in ((fi.FI_F64, "f64", 1e-8, 1e-5), (fi.FI_F32, "f32", 1e-6, 2e-3)):
+        opt = fi.solve_options(prec, 300, tol, preconditioner=fi.FI_PRECOND_MULTIGRID)
+        out = torch.zeros(runner.local_cells, device="cuda")
+        st = runner.step(d_pos, d_nrm, opt, out)
+        st = runner.step(d_pos, d_nrm, opt, out)  # warm (allocations, NCCL channels)
+        full = gather_own(out, sizes)
+        if rank == 0:
+            f = fi.sdf_from_points(sizes, weights, d_pos, d_nrm)
+            ref, st1 = f.solve(opt, out=torch.zeros(int(np.prod(sizes)), device="cuda"))
+            ref = ref.cpu().numpy()
+            err = float(np.linalg.norm(full - ref) / max(np.linalg.norm(ref), 1e-300))
+            good = bool(st["converged"]) and abs(st["iterations"] - st1["iterations"]) <= 2 and err <= close
+            ok = ok and good
+            print(json.dumps({"mg": True, "sizes": sizes, "prec": name, "sharded_levels": plan["sharded_levels"], "iters_slab": st["iterations"],
+                              "iters_single": st1["iterations"], "rel_diff_vs_single": err, "true_slab": st["true_residual"], "true_single": st1["true_residual"],
+                              "solve_ms_slab": st["solve_ms"], "setup_ms_slab": st["setup_ms"], "solve_ms_single": st1["solve_ms"], "ok": good}), flush=True)
+            f.close()
+    runner.close()
+os.environ.pop("FI_B200_MG_GATHER_CELLS", None)
+
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.broadcast(flag, src=0)
 dist.destroy_process_group()

@@ -32,6 +32,65 @@ def test_slab_ranges_partition_the_lattice(nz):
         assert min(sizes) >= 1 and max(sizes) - min(sizes) <= 1
 
 
+def _axis_tables(nf, nc):
+    """Independent restatement of the transfer geometry along one axis (upscale_field's align-corners rule,
+    reference field_interpolation.cpp:462): base coarse node of every fine node, and for every coarse node the
+    fine nodes that interpolate from it with a non-zero weight."""
+    sc = (nc - 1) / (nf - 1) if nf > 1 else 0.0
+    base = np.minimum(np.floor(np.arange(nf) * sc).astype(int), nc - 1)
+    frac = (np.arange(nf) * sc - base).astype(np.float32)
+    touch = [[] for _ in range(nc)]
+    for i in range(nf):
+        if np.float32(1) - frac[i] != 0:
+            touch[base[i]].append(i)
+        if frac[i] != 0 and base[i] + 1 < nc:
+            touch[base[i] + 1].append(i)
+    return base, touch
+
+
+@pytest.mark.parametrize("sizes,world,radius,gather", [
+    ([512, 512, 512], 8, 2, 0), ([512, 512, 512], 2, 2, 0), ([1024, 1024, 1024], 8, 2, 0), ([256, 256, 256], 8, 2, 0),
+    ([256, 256, 256], 4, 1, 1000), ([128, 64, 37], 2, 2, 1000), ([96, 40, 64], 3, 4, 1000), ([64, 48, 40], 1, 2, 1000),
+    ([512, 256, 1000], 7, 3, 0), ([320, 200, 129], 5, 2, 100)])
+def test_slab_multigrid_plan_windows(sizes, world, radius, gather):
+    """fi_slab_mg_plan: every level's planes are partitioned over the ranks, restriction into a rank's coarse planes
+    and prolongation into its fine planes read only planes inside its stored window (owned + halo)."""
+    from field_interpolation_b200 import dist as fid
+    plan = fid.slab_mg_plan(sizes, world, radius, gather)
+    nd, halo = plan["sharded_levels"], plan["halo"]
+    assert nd >= 1 and halo == max(radius, 2)
+    assert plan["sizes"][0] == sizes
+    assert plan["own"][0] == [fid.slab_range(sizes[2], world, k) for k in range(world)]
+    for l in range(nd + 1):
+        own = plan["own"][l]
+        assert own[0][0] == 0 and own[-1][1] == plan["sizes"][l][2]
+        assert all(own[k][1] == own[k + 1][0] for k in range(world - 1))
+        if l > 0:
+            assert plan["sizes"][l] == [(v + 1) // 2 for v in plan["sizes"][l - 1]]
+        if l < nd:  # sharded: thick enough for the halo exchange, sizes the TMA stencil kernel takes
+            assert all(b - a >= halo for a, b in own)
+            assert plan["sizes"][l][0] % 4 == 0 and plan["sizes"][l][0] >= 32 and plan["sizes"][l][1] >= 8
+    for l in range(nd):
+        base, touch = _axis_tables(plan["sizes"][l][2], plan["sizes"][l + 1][2])
+        for k in range(world):
+            z0, z1 = plan["own"][l][k]
+            c0, c1 = plan["own"][l + 1][k]
+            for C in range(c0, c1):  # restriction reads the fine planes that touch C
+                assert touch[C] and min(touch[C]) >= z0 - halo and max(touch[C]) < z1 + halo
+            if l + 1 < nd:  # prolongation from a sharded level reads its planes base, base + 1
+                for z in range(z0, z1):
+                    assert base[z] >= c0 - halo and min(base[z] + 1, plan["sizes"][l + 1][2] - 1) < c1 + halo
+
+
+def test_slab_multigrid_plan_refuses_thin_slabs():
+    from field_interpolation_b200 import dist as fid
+    from field_interpolation_b200 import _lib as L
+    with pytest.raises(L.FiError):
+        fid.slab_mg_plan([64, 64, 8], 8, 2)       # one plane per rank
+    with pytest.raises(L.FiError):
+        fid.slab_mg_plan([30, 64, 64], 2, 2)      # x size the TMA stencil kernel does not take
+
+
 def _bootstrap_worker(rank, world, port, out):
     import torch.distributed as dist
     from field_interpolation_b200 import dist as fid
@@ -101,4 +160,44 @@ def test_one_rank_slab_matches_plain_solve(orders):
     st = runner.step(d_pos, d_nrm, fi.solve_options(fi.FI_F32, 5, 1e-30), out, guess=guess)
     ref2, _ = f.solve(fi.solve_options(fi.FI_F32, 5, 1e-30), guess=ref)
     assert np.linalg.norm(out.cpu().numpy() - ref2) <= 1e-5 * np.linalg.norm(ref2)
+    runner.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gather", [0, 1000])
+def test_one_rank_slab_multigrid_matches_plain_multigrid(gather, monkeypatch):
+    """FI_PRECOND_MULTIGRID through the slab path on a 1-rank communicator: the sharded V-cycle (unfused smoother over
+    the owned planes, transfers through shifted slab pointers, replicated tail hierarchy) is the same linear operator
+    as the single-GPU V-cycle, so the CG takes the same number of iterations (within rounding) to the same field.
+    gather = 1000 forces two sharded levels at this size."""
+    import field_interpolation_b200 as fi
+    from field_interpolation_b200 import dist as fid
+
+    class OneRank:
+        @staticmethod
+        def get_backend():
+            return "gloo"
+
+        @staticmethod
+        def broadcast(t, src=0):
+            return None
+
+    if gather:
+        monkeypatch.setenv("FI_B200_MG_GATHER_CELLS", str(gather))
+    sizes = [64, 48, 40]
+    assert fid.slab_mg_plan(sizes, 1, 2, gather)["sharded_levels"] == (2 if gather else 1)
+    cloud = W.sphere_torus_3d(5000, seed=5)
+    pos = W.to_lattice(cloud["unit_pos"], sizes)
+    weights = fi.Weights()
+    runner = fid.SlabRunner(sizes, weights, 0, 1, OneRank)
+    f = fi.sdf_from_points(sizes, weights, pos, cloud["normals"])
+    for prec, tol, close in ((fi.FI_F64, 1e-9, 1e-6), (fi.FI_F32, 1e-5, 2e-3)):
+        opt = fi.solve_options(prec, 200, tol, preconditioner=fi.FI_PRECOND_MULTIGRID)
+        out = np.zeros(runner.local_cells, np.float32)
+        st = runner.step(pos, cloud["normals"], opt, out)
+        ref, st1 = f.solve(opt)
+        assert st["converged"] and st1["converged"]
+        assert abs(st["iterations"] - st1["iterations"]) <= 2, (st, st1)
+        assert st["true_residual"] <= 30 * max(tol, st1["true_residual"])
+        assert np.linalg.norm(out - ref) <= close * np.linalg.norm(ref)
     runner.close()
