@@ -157,6 +157,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--time-to-tol", action="store_true", help="also time the Jacobi-PCG coarse-to-fine cascade to 1e-6 (slow)")
     ap.add_argument("--no-time-to-tol", action="store_true", help="skip the multigrid time-to-1e-6 measurement")
+    ap.add_argument("--mg-timeout", type=float, default=240.0, help="N>1: deadline in seconds for the sharded multigrid time-to-1e-6 section")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -317,7 +318,36 @@ def main():
                           "halo_GBps_per_interior_rank_averaged_over_iteration": halo_bytes / max(it_ms, 1e-9) / 1e6,
                           "path": "peer stores over NVLink inside pcg_update_peer_kernel" if os.environ.get("FI_B200_P2P", "1") != "0" else "ncclSend/ncclRecv"}}
 
+    def emit(ttt, base=None):
+        line = {
+            "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": desc, "lattice": sizes, "points": npts, "weights": "default (model_2=0.5, trilinear value rows, cell-edge gradient rows)",
+                       "pcg_iterations_per_step": args.iters, "step": "assemble normal equations from device-resident points + PCG iterations",
+                       "l2": "working set (>= 6 lattice vectors) exceeds L2; no flush needed" if N * 4 * 6 > 126e6 else "flush not applied",
+                       "parallelism": "single GPU" if world == 1 else f"z-slab x{world}"},
+            "roofline": roof, "cpu_baseline": base,
+            "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": clock_summary, "kernels": extra, "time_to_1e-6": ttt,
+        }
+        print(json.dumps(line), flush=True)
+
     ttt = None
+    watchdog = None
+    if runner is not None and not args.no_time_to_tol:
+        # The sharded V-cycle is the one part of this file that exchanges halos through NCCL point-to-point calls between
+        # the timed steps' barriers; a rank that fails alone would leave its peers waiting for ever.  The headline numbers
+        # above are complete by now, so every rank arms the same deadline: when it passes, rank 0 prints the line without
+        # the multigrid figures and all ranks leave.
+        def bail():
+            if rank == 0:
+                emit({"error": f"sharded multigrid time-to-1e-6 did not finish within {args.mg_timeout} s; skipped"})
+            sys.stdout.flush()
+            os._exit(0)
+        watchdog = threading.Timer(args.mg_timeout, bail)
+        watchdog.daemon = True
+        watchdog.start()
     if runner is not None and not args.no_time_to_tol:
         # metric (ii) on the slabs: every rank passes the whole cloud from HOST arrays and receives its owned planes in host
         # memory; the V-cycle is sharded (fi_slab_mg_plan).  Wall time between barriers, max over ranks.
@@ -380,20 +410,13 @@ def main():
         v, sec, base = cpu_reference_arm(sn, snpts, args.cpu_iters, 1, 0)
         base["value"], base["unit"] = v, unit
 
+    if watchdog is not None:
+        watchdog.cancel()
     if rank == 0:
-        line = {
-            "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": desc, "lattice": sizes, "points": npts, "weights": "default (model_2=0.5, trilinear value rows, cell-edge gradient rows)",
-                       "pcg_iterations_per_step": args.iters, "step": "assemble normal equations from device-resident points + PCG iterations",
-                       "l2": "working set (>= 6 lattice vectors) exceeds L2; no flush needed" if N * 4 * 6 > 126e6 else "flush not applied",
-                       "parallelism": "single GPU" if world == 1 else f"z-slab x{world}"},
-            "roofline": roof, "cpu_baseline": base,
-            "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches), "clocks": clock_summary, "kernels": extra, "time_to_1e-6": ttt,
-        }
-        print(json.dumps(line))
+        emit(ttt, base)
+    if runner is not None and isinstance(ttt, dict) and "error" in ttt:
+        sys.stdout.flush()
+        os._exit(0)  # a rank that failed alone must not wait for its peers in destroy_process_group
     if dist is not None:
         dist.destroy_process_group()
 
