@@ -318,6 +318,69 @@ def upscale_field(small_field, small_sizes: Sequence[int], large_sizes: Sequence
     return out
 
 
+# ---- iso-surface helpers of the callers (emilib/marching_squares.cpp, src/sdf_field.cpp:555-614) -------------------
+def _field_2d(values):
+    """(height, width) field as a _Buf; row-major like the reference's `width * height` arrays."""
+    shape = tuple(values.shape)
+    if len(shape) != 2:
+        raise ValueError("a 2D (height, width) field is expected")
+    if _is_device(values):
+        values = values.contiguous()
+    return _Buf(values, shape[0] * shape[1]), int(shape[0]), int(shape[1])
+
+
+def iso_surface(values, iso: float = 0.0, want_area: bool = False):
+    """iso_surface, src/sdf_field.cpp:605-614 = emilib::marching_squares (marching_squares.cpp:11-134) of `values - iso`.
+    values: (height, width) numpy array or CUDA tensor.  Returns the (num_segments, 4) segments x0 y0 x1 y1 in the
+    reference's order, living where `values` lives; with want_area also emilib::calc_area of them (:136-150)."""
+    buf, h, w = _field_2d(values)
+    n = C.c_int64(0)
+    L.check(L.lib().fi_marching_squares(w, h, buf.ptr, float(iso), buf.loc, None, 0, C.byref(n), None))
+    ns = int(n.value)
+    area = C.c_float(0.0)
+    if buf.loc == FI_DEVICE:
+        import torch
+        out = torch.empty((ns, 4), dtype=torch.float32, device=values.device)
+        dst = C.c_void_p(out.data_ptr()) if ns else None
+    else:
+        out = np.empty((ns, 4), np.float32)
+        dst = C.c_void_p(out.ctypes.data) if ns else None
+    if ns:
+        L.check(L.lib().fi_marching_squares(w, h, buf.ptr, float(iso), buf.loc, dst, ns, C.byref(n), C.byref(area) if want_area else None))
+    return (out, float(area.value)) if want_area else out
+
+
+def marching_squares(iso_field):
+    """emilib::marching_squares, third_party/emilib/emilib/marching_squares.cpp:11-134: the contour at 0."""
+    return iso_surface(iso_field, 0.0)
+
+
+def calc_area(lines) -> float:
+    """emilib::calc_area, marching_squares.cpp:136-150."""
+    if _is_device(lines):
+        lines = lines.contiguous()
+    buf = _Buf(lines)
+    n = (buf.keep.numel() if buf.loc == FI_DEVICE else buf.keep.size) // 4 if buf.keep is not None else 0
+    area = C.c_float(0.0)
+    L.check(L.lib().fi_calc_area(n, buf.ptr if n else None, buf.loc if buf.loc is not None else FI_HOST, C.byref(area)))
+    return float(area.value)
+
+
+def bicubic_upsample(values, upsample: int):
+    """bicubic_upsample, src/sdf_field.cpp:555-603: (height, width) -> (upsample*height - upsample + 1, upsample*width - upsample + 1)."""
+    buf, h, w = _field_2d(values)
+    lh, lw = upsample * h - upsample + 1, upsample * w - upsample + 1
+    if buf.loc == FI_DEVICE:
+        import torch
+        out = torch.empty((lh, lw), dtype=torch.float32, device=values.device)
+        dst = C.c_void_p(out.data_ptr())
+    else:
+        out = np.empty((lh, lw), np.float32)
+        dst = C.c_void_p(out.ctypes.data)
+    L.check(L.lib().fi_bicubic_upsample(w, h, buf.ptr, int(upsample), dst, buf.loc))
+    return out
+
+
 # ---- solvers (sparse_linear.hpp:44-80), on a LatticeField ---------------------------------------------
 # The reference passes field.eq; here the field itself carries the structure (a bare triplet list has lost the
 # lattice).  A failed solve returns an empty array like the reference returns {}.

@@ -15,9 +15,9 @@ OBJ = os.path.join(HERE, "_build")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 COMMON = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "--extended-lambda",
           "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-I", os.path.join(HERE, "..", "include")]
-# assembly.cu restates the reference's scalar fp32 arithmetic bit for bit: no FMA contraction there.
-PER_FILE = {"assembly.cu": ["-fmad=false"]}
-SOURCES = ["abi.cu", "assembly.cu", "sort_scan.cu", "stencil.cu", "stencil_fast.cu", "stencil_tma.cu", "solver.cu", "mg.cu", "errormap.cu", "dist.cu"]
+# assembly.cu and isosurface.cu restate the reference's scalar fp32 arithmetic bit for bit: no FMA contraction there.
+PER_FILE = {"assembly.cu": ["-fmad=false"], "isosurface.cu": ["-fmad=false"]}
+SOURCES = ["abi.cu", "assembly.cu", "sort_scan.cu", "stencil.cu", "stencil_fast.cu", "stencil_tma.cu", "solver.cu", "mg.cu", "errormap.cu", "isosurface.cu", "dist.cu"]
 
 
 def _stale(src, obj):
@@ -62,7 +62,7 @@ def build(verbose: bool = False, force: bool = False) -> str:
     return OUT
 
 
-HOST_SRC = [os.path.join(HERE, "host", f) for f in ("field_interpolation.cpp", "sparse_linear.cpp")]
+HOST_SRC = [os.path.join(HERE, "host", f) for f in ("field_interpolation.cpp", "sparse_linear.cpp", "iso_surface.cpp")]
 HOST_OUT = os.path.join(HERE, "libfield_interpolation.so")
 CXX = os.environ.get("CXX", "g++")
 
@@ -72,7 +72,9 @@ def build_host(force: bool = False) -> str:
     deps = HOST_SRC + [os.path.join(HERE, "host", "structured.hpp"), OUT,
                        os.path.join(HERE, "..", "include", "fi_b200.h"),
                        os.path.join(HERE, "..", "include", "field_interpolation", "field_interpolation.hpp"),
-                       os.path.join(HERE, "..", "include", "field_interpolation", "sparse_linear.hpp")]
+                       os.path.join(HERE, "..", "include", "field_interpolation", "sparse_linear.hpp"),
+                       os.path.join(HERE, "..", "include", "field_interpolation", "iso_surface.hpp"),
+                       os.path.join(HERE, "..", "include", "emilib", "marching_squares.hpp")]
     if not force and os.path.exists(HOST_OUT) and all(os.path.getmtime(d) <= os.path.getmtime(HOST_OUT) for d in deps):
         return HOST_OUT
     cmd = [CXX, "-std=c++14", "-O2", "-fPIC", "-shared", "-Wall", "-Wextra", "-o", HOST_OUT, *HOST_SRC,

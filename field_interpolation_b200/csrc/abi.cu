@@ -944,6 +944,62 @@ int fi_error_map(int64_t num_triplets, const fi_triplet* triplets, int64_t num_c
 	});
 }
 
+int fi_marching_squares(int32_t width, int32_t height, const float* values, float iso, int32_t loc, float* lines, int64_t capacity_segments,
+                        int64_t* num_segments, float* area)
+{
+	return guarded([&] {
+		FI_REQUIRE(width >= 1 && height >= 1 && values && num_segments, FI_ERR_INVALID, "marching squares: bad argument");
+		FI_REQUIRE(lines == nullptr || capacity_segments >= 0, FI_ERR_INVALID, "marching squares: negative capacity");
+		*num_segments = 0;
+		if (area) { *area = 0.0f; }
+		cudaStream_t  s = nullptr;
+		Staged<float> v(values, static_cast<size_t>(width) * height, loc, s);
+		// the count decides how many segments exist; they are materialised on the device when the caller wants them or the area
+		const int64_t n = marching_squares_device(width, height, v.ptr, iso, nullptr, 0, s);
+		*num_segments   = n;
+		FI_REQUIRE(lines == nullptr || n <= capacity_segments, FI_ERR_RANGE, "marching squares: segment buffer too small");
+		if (n == 0 || (lines == nullptr && area == nullptr)) { return; }
+		DevBuf<float> own;
+		float*        d_lines = lines;
+		if (lines == nullptr || loc != FI_DEVICE) {
+			own.resize(static_cast<size_t>(n) * 4);
+			d_lines = own.data();
+		}
+		marching_squares_device(width, height, v.ptr, iso, d_lines, n, s);
+		if (area) { *area = static_cast<float>(area_twice_device(n, d_lines, s) / 2); }
+		if (lines && loc != FI_DEVICE) { FI_CUDA(cudaMemcpy(lines, d_lines, static_cast<size_t>(n) * 4 * sizeof(float), cudaMemcpyDeviceToHost)); }
+	});
+}
+
+int fi_calc_area(int64_t num_segments, const float* lines, int32_t loc, float* area)
+{
+	return guarded([&] {
+		FI_REQUIRE(num_segments >= 0 && area && (lines || num_segments == 0), FI_ERR_INVALID, "calc_area: bad argument");
+		cudaStream_t  s = nullptr;
+		Staged<float> l(lines, static_cast<size_t>(num_segments) * 4, loc, s);
+		*area = static_cast<float>(area_twice_device(num_segments, l.ptr, s) / 2);
+	});
+}
+
+int fi_bicubic_upsample(int32_t width, int32_t height, const float* values, int32_t upsample, float* large, int32_t loc)
+{
+	return guarded([&] {
+		FI_REQUIRE(width >= 1 && height >= 1 && values && large, FI_ERR_INVALID, "bicubic_upsample: bad argument");
+		FI_REQUIRE(upsample > 1, FI_ERR_INVALID, "bicubic_upsample: upsample must be > 1 (src/sdf_field.cpp:557)");
+		cudaStream_t  s = nullptr;
+		const int64_t lw = static_cast<int64_t>(upsample) * width - upsample + 1, lh = static_cast<int64_t>(upsample) * height - upsample + 1;
+		Staged<float> v(values, static_cast<size_t>(width) * height, loc, s);
+		if (loc == FI_DEVICE) {
+			bicubic_upsample_device(width, height, v.ptr, upsample, large, s);
+			FI_CUDA(cudaStreamSynchronize(s));
+		} else {
+			DevBuf<float> out(static_cast<size_t>(lw * lh));
+			bicubic_upsample_device(width, height, v.ptr, upsample, out.data(), s);
+			FI_CUDA(cudaMemcpy(large, out.data(), static_cast<size_t>(lw * lh) * sizeof(float), cudaMemcpyDeviceToHost));
+		}
+	});
+}
+
 int fi_sdf_solve_cascade(int32_t ndim, const int32_t* sizes, const fi_weights* w, int64_t num_points, const float* unit_positions,
                          const float* normals, const float* point_weights, const fi_cascade_options* opt, float* solution,
                          int32_t loc, fi_cascade_stats* stats)

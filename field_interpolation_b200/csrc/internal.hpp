@@ -166,6 +166,11 @@ bool apply_data_term_epilogue(const Geom& g, const DataTerm<T>& dt, const T* in,
 // ---- errormap.cu ------------------------------------------------------------------------------------------
 void error_map(int64_t nt, const fi_triplet* h_trips, int64_t n, const float* h_x, int64_t nrows, const float* h_rhs, float* h_out);
 
+// ---- isosurface.cu (compiled with -fmad=false) ----------------------------------------------------------------
+int64_t marching_squares_device(int width, int height, const float* d_values, float iso, float* d_lines, int64_t capacity, cudaStream_t s);
+double  area_twice_device(int64_t nseg, const float* d_lines, cudaStream_t s);
+void    bicubic_upsample_device(int width, int height, const float* d_values, int upsample, float* d_large, cudaStream_t s);
+
 // ---- stencil.cu ------------------------------------------------------------------------------------------
 // Per-axis banded operator T_d = sum_k w_k^2 D_k^T D_k (rows that stick out dropped), 9 row classes x 9 taps,
 // plus the tri-diagonal D_1^T D_1 used by the gradient-smoothness cross terms.  See DESIGN.md §3.

@@ -193,6 +193,23 @@ FI_API int fi_upscale_field(int32_t ndim, const int32_t* small_sizes, const int3
 FI_API int fi_error_map(int64_t num_triplets, const fi_triplet* triplets, int64_t num_columns, const float* solution,
                  int64_t num_rows, const float* rhs, float* heatmap);
 
+/* ---- iso-surface helpers of the callers: what the demo runs on every solved 2D field -------- */
+/* emilib::marching_squares (third_party/emilib/emilib/marching_squares.cpp:11-134) of `values - iso` — iso_surface,
+ * src/sdf_field.cpp:605-614; iso = 0 is marching_squares itself.  values: row-major width x height floats, >= 0 means
+ * "outside".  Segments come out in the reference's order (cells y-major, one or two directed segments x0 y0 x1 y1 per
+ * crossed cell) and are bit-identical to the reference's.  *num_segments always receives the count.  lines (nullable:
+ * count only) must hold capacity_segments * 4 floats; when the count exceeds the capacity nothing is written and the
+ * call returns FI_ERR_RANGE.  area (nullable) receives emilib::calc_area of the segments (:136-150).  values and lines
+ * live where `loc` says (a device `lines` buffer must be 16-byte aligned). */
+FI_API int fi_marching_squares(int32_t width, int32_t height, const float* values, float iso, int32_t loc, float* lines,
+                        int64_t capacity_segments, int64_t* num_segments, float* area);
+/* emilib::calc_area, marching_squares.cpp:136-150: half the shoelace sum over the segments (double accumulation). */
+FI_API int fi_calc_area(int64_t num_segments, const float* lines, int32_t loc, float* area);
+/* bicubic_upsample, src/sdf_field.cpp:555-603: Catmull-Rom upsampling of a width x height field to
+ * (upsample * width - upsample + 1) x (upsample * height - upsample + 1), clamped reads at the border; upsample >= 2
+ * (the reference CHECKs > 1).  Bit-identical fp32 arithmetic. */
+FI_API int fi_bicubic_upsample(int32_t width, int32_t height, const float* values, int32_t upsample, float* large, int32_t loc);
+
 /* Coarse-to-fine solve mirroring the demo's recipe (src/sdf_field.cpp:251-304) applied recursively:
  * positions are in UNIT coordinates and are scaled per level by (size-1) as on_lattice does (:198-210);
  * each level re-assembles sdf_from_points with the same weights and unscaled normals, the coarser solution

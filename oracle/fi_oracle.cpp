@@ -765,6 +765,97 @@ void ora_generate_error_map(int64_t num_triplets, const int* rows, const int* co
 	}
 }
 
+// ---- iso-surface helpers the demo runs right after every solve ------------------
+// emilib::marching_squares, third_party/emilib/emilib/marching_squares.cpp:11-134.  `iso` is row-major
+// width x height; a corner is "outside" when its value is >= 0 (:21-24); cells are visited y-major (:15-16) and
+// emit 0, 1 or 2 directed segments x0 y0 x1 y1.  The reference is one switch over 14 cases (:36-129); here the
+// same cases are a table of directed edge pairs over the four crossing points
+//   L = (x, y + tl/(tl-bl))  T = (x + tl/(tl-tr), y)  R = (x+1, y + tr/(tr-br))  B = (x + bl/(bl-br), y+1)   (:31-34).
+// Returns the number of floats; writes them when out != nullptr.
+int64_t ora_marching_squares(int64_t width, int64_t height, const float* iso, float* out)
+{
+	enum { L, T, R, B };
+	// config = br<<3 | bl<<2 | tr<<1 | tl (:26); up to two (from, to) pairs, -1 terminated
+	static const int kSeg[16][4] = {
+		{-1, -1, -1, -1}, {L, T, -1, -1}, {T, R, -1, -1}, {L, R, -1, -1}, {B, L, -1, -1}, {B, T, -1, -1}, {T, L, B, R}, {B, R, -1, -1},
+		{R, B, -1, -1},   {L, T, R, B},   {T, B, -1, -1}, {L, B, -1, -1}, {R, L, -1, -1}, {R, T, -1, -1}, {T, L, -1, -1}, {-1, -1, -1, -1}};
+	int64_t n = 0;
+	for (int64_t y = 0; y + 1 < height; ++y) {
+		for (int64_t x = 0; x + 1 < width; ++x) {
+			const float tl = iso[x + width * y], tr = iso[x + 1 + width * y];
+			const float bl = iso[x + width * (y + 1)], br = iso[x + 1 + width * (y + 1)];
+			const int config = (br >= 0.0f ? 8 : 0) | (bl >= 0.0f ? 4 : 0) | (tr >= 0.0f ? 2 : 0) | (tl >= 0.0f ? 1 : 0);
+			const int* seg = kSeg[config];
+			if (seg[0] < 0) { continue; }
+			const float fx = static_cast<float>(x), fy = static_cast<float>(y);
+			const float px[4] = {fx + 0.0f, fx + tl / (tl - tr), fx + 1.0f, fx + bl / (bl - br)};
+			const float py[4] = {fy + tl / (tl - bl), fy + 0.0f, fy + tr / (tr - br), fy + 1.0f};
+			for (int k = 0; k < 4 && seg[k] >= 0; k += 2) {
+				if (out) {
+					out[n + 0] = px[seg[k]];
+					out[n + 1] = py[seg[k]];
+					out[n + 2] = px[seg[k + 1]];
+					out[n + 3] = py[seg[k + 1]];
+				}
+				n += 4;
+			}
+		}
+	}
+	return n;
+}
+
+// emilib::calc_area, marching_squares.cpp:136-150: shoelace sum in double over the segments in order, halved, as float.
+float ora_calc_area(int64_t num_segments, const float* xy)
+{
+	double twice = 0;
+	for (int64_t i = 0; i < num_segments; ++i) {
+		const double ax = xy[4 * i], ay = xy[4 * i + 1], bx = xy[4 * i + 2], by = xy[4 * i + 3];
+		twice += ax * by - bx * ay;
+	}
+	return static_cast<float>(twice / 2);
+}
+
+// emath::catmull_rom, third_party/emath/emath/math.hpp:308-316, in the reference's fp32 evaluation order.
+static float catmull_rom_f32(float t, float p0, float p1, float p2, float p3)
+{
+	const float a = p0 * t * ((2.0f - t) * t - 1.0f);
+	const float b = p1 * (t * t * (3.0f * t - 5.0f) + 2.0f);
+	const float c = p2 * t * ((4.0f - 3.0f * t) * t + 1.0f);
+	const float d = p3 * (t - 1.0f) * t * t;
+	return 0.5f * (a + b + c + d);
+}
+
+// bicubic_upsample, src/sdf_field.cpp:555-603: large = upsample * small - upsample + 1 per axis; sample (lx, ly) sits at
+// cell (lx / upsample, ly / upsample) with t = (l % upsample) / upsample; 4 x 4 neighbourhood with clamped reads (:565-570),
+// Catmull-Rom along x for each of the four rows, then along y (:587-594).  out: large_width * large_height floats.
+void ora_bicubic_upsample(int width, int height, const float* values, int upsample, float* out)
+{
+	const int64_t lw = static_cast<int64_t>(upsample) * width - upsample + 1, lh = static_cast<int64_t>(upsample) * height - upsample + 1;
+	auto at = [&](int x, int y) {
+		x = std::min(std::max(x, 0), width - 1);
+		y = std::min(std::max(y, 0), height - 1);
+		return values[static_cast<int64_t>(y) * width + x];
+	};
+	for (int64_t ly = 0; ly < lh; ++ly) {
+		for (int64_t lx = 0; lx < lw; ++lx) {
+			const float tx = static_cast<float>(lx % upsample) / static_cast<float>(upsample);
+			const float ty = static_cast<float>(ly % upsample) / static_cast<float>(upsample);
+			const int   sx = static_cast<int>(lx / upsample), sy = static_cast<int>(ly / upsample);
+			float row[4];
+			for (int j = 0; j < 4; ++j) { row[j] = catmull_rom_f32(tx, at(sx - 1, sy - 1 + j), at(sx, sy - 1 + j), at(sx + 1, sy - 1 + j), at(sx + 2, sy - 1 + j)); }
+			out[ly * lw + lx] = catmull_rom_f32(ty, row[0], row[1], row[2], row[3]);
+		}
+	}
+}
+
+// iso_surface, src/sdf_field.cpp:605-614: marching squares of (values - iso).
+int64_t ora_iso_surface(int width, int height, const float* values, float iso, float* out)
+{
+	std::vector<float> shifted(static_cast<size_t>(width) * height);
+	for (size_t i = 0; i < shifted.size(); ++i) { shifted[i] = values[i] - iso; }
+	return ora_marching_squares(width, height, shifted.data(), out);
+}
+
 // ---- solve half -------------------------------------------------------------------------------
 // precision: 0 = float (as_sparse_matrix_float, keeps explicit zeros), 1 = double (drops them).
 void* ora_normal_create(int64_t nt, const int* rows, const int* cols, const float* values, int64_t num_rows,

@@ -140,6 +140,8 @@ class CpuLib:
             "copy_system": (None, [vp, pi, pi, pf, pf]),
             "upscale_field": (None, [pf, i, pi, pi, pf]),
             "generate_error_map": (None, [i64, pi, pi, pf, i64, pf, i64, pf, pf]),
+            "marching_squares": (i64, [i64, i64, pf, pf]), "calc_area": (f, [i64, pf]),
+            "bicubic_upsample": (None, [i, i, pf, i, pf]), "iso_surface": (i64, [i, i, pf, f, pf]),
         }
         for name, (res, args) in S.items():
             fn = self.fn(name)
@@ -188,6 +190,35 @@ class CpuLib:
         out = np.empty(sol.size, np.float32)
         self.fn("generate_error_map")(sys.num_triplets, _ptr(sys.rows, C.c_int), _ptr(sys.cols, C.c_int),
                                       _ptr(sys.vals), sol.size, _ptr(sol), sys.num_rows, _ptr(sys.rhs), _ptr(out))
+        return out
+
+    # ---- iso-surface helpers (emilib/marching_squares.cpp, src/sdf_field.cpp:555-614) ----------------
+    def marching_squares(self, iso) -> np.ndarray:
+        """`iso`: (height, width) float32, row-major.  Returns (num_segments, 4) float32: x0 y0 x1 y1."""
+        a = np.ascontiguousarray(iso, dtype=np.float32)
+        h, w = a.shape
+        n = int(self.fn("marching_squares")(w, h, _ptr(a), None))
+        out = np.empty(max(n, 1), np.float32)
+        self.fn("marching_squares")(w, h, _ptr(a), _ptr(out))
+        return out[:n].reshape(-1, 4)
+
+    def iso_surface(self, values, iso: float) -> np.ndarray:
+        a = np.ascontiguousarray(values, dtype=np.float32)
+        h, w = a.shape
+        n = int(self.fn("iso_surface")(w, h, _ptr(a), float(iso), None))
+        out = np.empty(max(n, 1), np.float32)
+        self.fn("iso_surface")(w, h, _ptr(a), float(iso), _ptr(out))
+        return out[:n].reshape(-1, 4)
+
+    def calc_area(self, lines) -> float:
+        a = np.ascontiguousarray(lines, dtype=np.float32).reshape(-1, 4)
+        return float(self.fn("calc_area")(a.shape[0], _ptr(a) if a.size else None))
+
+    def bicubic_upsample(self, values, upsample: int) -> np.ndarray:
+        a = np.ascontiguousarray(values, dtype=np.float32)
+        h, w = a.shape
+        out = np.empty((upsample * h - upsample + 1, upsample * w - upsample + 1), np.float32)
+        self.fn("bicubic_upsample")(w, h, _ptr(a), int(upsample), _ptr(out))
         return out
 
     # ---- solve half (port only) -----------------------------------------------------------------

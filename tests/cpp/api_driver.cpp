@@ -15,7 +15,9 @@
 #include <string>
 #include <vector>
 
+#include <emilib/marching_squares.hpp>
 #include <field_interpolation/field_interpolation.hpp>
+#include <field_interpolation/iso_surface.hpp>
 
 namespace fi = field_interpolation;
 
@@ -247,6 +249,37 @@ static int scenario_deferred_3d()
 	return 0;
 }
 
+// reference src/sdf_field.cpp:660-670 — what the demo does with a solved 2D field: optional bicubic upsampling, the zero
+// contour by marching squares, its area relative to the lattice; plus one off-zero iso line (:701).
+static int scenario_iso_2d(const char* in_path)
+{
+	FILE* in = std::fopen(in_path, "rb");
+	if (!in) { return 3; }
+	const std::vector<float> dims = read_floats(in);  // width, height, upsampling, iso
+	const std::vector<float> sdf  = read_floats(in);
+	std::fclose(in);
+	int       iso_width = static_cast<int>(dims[0]), iso_height = static_cast<int>(dims[1]);
+	const int upsampling = static_cast<int>(dims[2]);
+	if (sdf.size() != static_cast<size_t>(iso_width) * iso_height) { return 4; }
+
+	const std::vector<float> plain = emilib::marching_squares(iso_width, iso_height, sdf.data());
+	put_f("plain_lines", plain);
+	put_f("plain_area", {emilib::calc_area(plain.size() / 4, plain.data())});
+
+	std::vector<float> iso_source = sdf;
+	if (upsampling > 1) { iso_source = fi::bicubic_upsample(&iso_width, &iso_height, iso_source.data(), upsampling); }
+	put_i("up_size", {iso_width, iso_height});
+	put_f("upsampled", iso_source);
+	const std::vector<float> zero_lines = fi::iso_surface(iso_width, iso_height, iso_source.data(), 0.0f);
+	put_f("zero_lines", zero_lines);
+	const float side = static_cast<float>(iso_width - 1);
+	put_f("lines_area", {emilib::calc_area(zero_lines.size() / 4, zero_lines.data()) / (side * side)});
+	put_f("iso_lines", fi::iso_surface(iso_width, iso_height, iso_source.data(), dims[3]));
+	int w1 = 3, h1 = 3;
+	put_f("bad_upsample", fi::bicubic_upsample(&w1, &h1, sdf.data(), 1));  // the reference CHECKs upsample > 1: {} here
+	return 0;
+}
+
 int main(int argc, char** argv)
 {
 	if (argc < 3) {
@@ -262,6 +295,7 @@ int main(int argc, char** argv)
 	else if (sc == "readme") { rc = scenario_readme(); }
 	else if (sc == "interpolate_2d") { rc = scenario_interpolate_2d(24); }
 	else if (sc == "sdf_2d" && argc > 3) { rc = scenario_sdf_2d(argv[3]); }
+	else if (sc == "iso_2d" && argc > 3) { rc = scenario_iso_2d(argv[3]); }
 	else if (sc == "hand_rows") { rc = scenario_hand_rows(); }
 	else if (sc == "deferred_3d") { rc = scenario_deferred_3d(); }
 	std::fclose(g_out);

@@ -110,6 +110,34 @@ def main():
     sol = rng.normal(size=42).astype(np.float32)
     save("error_map_2d", s, 42, solve=False, sol_in=sol, heat=ref.generate_error_map(s, sol))
 
+    # iso-surface helpers: emilib::marching_squares / calc_area from the reference's own
+    # marching_squares.cpp, bicubic_upsample / iso_surface (src/sdf_field.cpp:555-614) around the reference's emath.
+    def iso_case(name, field, upsample, iso):
+        field = np.ascontiguousarray(field, np.float32)
+        lines = ref.marching_squares(field)
+        up = ref.bicubic_upsample(field, upsample)
+        zero_up = ref.iso_surface(up, 0.0)
+        np.savez_compressed(os.path.join(OUT, name), field=field, lines=lines, area=np.float32(ref.calc_area(lines)),
+                            upsample=np.int32(upsample), upsampled=up, zero_lines_up=zero_up, area_up=np.float32(ref.calc_area(zero_up)),
+                            iso=np.float32(iso), iso_lines_up=ref.iso_surface(up, iso), iso_lines=ref.iso_surface(field, iso))
+        print(f"{name}: {field.shape} -> {len(lines)} segments, x{upsample}: {up.shape} -> {len(zero_up)} segments")
+
+    sizes = [44, 37]
+    cloud = W.circles_2d(600, seed=5)
+    pos = W.to_lattice(cloud["unit_pos"], sizes)
+    s = ref.sdf_from_points(sizes, O.make_weights(), pos, cloud["normals"]).system()
+    iso_case("iso_sdf_2d_44x37", O.exact_solve(s, 44 * 37).astype(np.float32).reshape(37, 44), 3, 0.7)
+    rng = np.random.default_rng(11)
+    noise = rng.standard_normal((33, 20)).astype(np.float32)
+    noise[rng.random((33, 20)) < 0.15] = 0.0      # exact zeros: corners sitting on the contour (>= 0 counts as outside)
+    noise[5:9, 3:8] = np.float32(-0.0)
+    iso_case("iso_random_33x20", noise, 2, -0.25)
+    yy, xx = np.mgrid[0:75, 0:61].astype(np.float32)
+    iso_case("iso_saddles_61x75", (np.sin(xx * np.float32(0.9)) * np.sin(yy * np.float32(1.1)) + np.float32(0.05)).astype(np.float32), 3, 0.3)
+    iso_case("iso_2x2", np.array([[-1.0, 1.0], [1.0, -2.0]], np.float32), 5, 0.5)
+    iso_case("iso_1x7", np.linspace(-1, 1, 7, dtype=np.float32).reshape(1, 7), 2, 0.0)   # no cells at all
+    iso_case("iso_9x2", np.linspace(-1, 1, 18, dtype=np.float32).reshape(9, 2), 3, 0.1)
+
 
 if __name__ == "__main__":
     main()

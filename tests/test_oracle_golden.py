@@ -123,3 +123,35 @@ def test_solve_half_restatement(port):
     f.add_field_constraints(O.make_weights())
     xz, it, err = port.normal(f.system(), 8, "f32").bicgstab(guess=np.ones(8, np.float32))
     assert it == 0 and not xz.any()
+
+
+# ---- iso-surface helpers --------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_names("iso_"))
+def test_iso_surface_helpers_match_reference_fixtures(port, name):
+    """marching_squares / calc_area (third_party/emilib/emilib/marching_squares.cpp), bicubic_upsample / iso_surface
+    (src/sdf_field.cpp:555-614): the port against outputs frozen from the reference's own code, bit for bit."""
+    g = load_golden(name)
+    field, up = g["field"], int(g["upsample"])
+    lines = port.marching_squares(field)
+    assert lines.shape == g["lines"].shape and np.array_equal(bits(lines), bits(g["lines"]))
+    assert np.float32(port.calc_area(lines)) == g["area"]
+    big = port.bicubic_upsample(field, up)
+    assert big.shape == g["upsampled"].shape and np.array_equal(bits(big), bits(g["upsampled"]))
+    zl = port.iso_surface(big, 0.0)
+    assert zl.shape == g["zero_lines_up"].shape and np.array_equal(bits(zl), bits(g["zero_lines_up"]))
+    assert np.float32(port.calc_area(zl)) == g["area_up"]
+    for src, key in ((big, "iso_lines_up"), (field, "iso_lines")):
+        il = port.iso_surface(src, float(g["iso"]))
+        assert il.shape == g[key].shape and np.array_equal(bits(il), bits(g[key]))
+
+
+def test_marching_squares_contour_of_a_disc(port):
+    """Known answer independent of the reference: the contour of a radius-40 disc SDF is closed, clockwise in a
+    y-down system (negative shoelace sign convention of calc_area gives +area), and encloses ~pi r^2."""
+    yy, xx = np.mgrid[0:129, 0:129].astype(np.float32)
+    sdf = (np.hypot(xx - 64, yy - 64) - 40).astype(np.float32)
+    lines = port.marching_squares(sdf)
+    assert abs(port.calc_area(lines) - np.pi * 1600) / (np.pi * 1600) < 2e-3
+    starts = {tuple(p) for p in lines[:, :2].view(np.uint32).reshape(-1, 2).tolist()}
+    ends = {tuple(p) for p in lines[:, 2:].copy().view(np.uint32).reshape(-1, 2).tolist()}
+    assert starts == ends  # every segment end is another segment's start: closed loops

@@ -49,3 +49,19 @@ def test_upscale_and_error_map_match_reference(port, ref):
     s = ref.sdf_from_points([8, 9], O.make_weights(), *W.random_cloud(2, 100, [8, 9], 3)).system()
     sol = rng.normal(size=72).astype(np.float32)
     assert np.array_equal(bits(port.generate_error_map(s, sol)), bits(ref.generate_error_map(s, sol)))
+
+
+def test_iso_surface_helpers_match_reference(port, ref):
+    """Randomised: fields with exact zeros, negative zeros, saddles and 1-wide shapes."""
+    rng = np.random.default_rng(21)
+    for h, w in ((2, 2), (5, 7), (33, 20), (1, 5), (6, 1), (64, 64), (3, 200)):
+        a = rng.standard_normal((h, w)).astype(np.float32)
+        a[rng.random((h, w)) < 0.1] = 0.0
+        a[rng.random((h, w)) < 0.05] = np.float32(-0.0)
+        for iso in (0.0, 0.3, -1.5):
+            r, p = ref.iso_surface(a, iso), port.iso_surface(a, iso)
+            assert r.shape == p.shape and np.array_equal(bits(r), bits(p))
+            assert ref.calc_area(r) == port.calc_area(p)
+        assert np.array_equal(bits(ref.marching_squares(a)), bits(port.marching_squares(a)))
+        for up in (2, 3, 7):
+            assert np.array_equal(bits(ref.bicubic_upsample(a, up)), bits(port.bicubic_upsample(a, up)))
