@@ -43,12 +43,14 @@ void set_last_error(const std::string& s);
 extern int64_t g_launches;
 inline void count_launch(int n = 1) { g_launches += n; }
 
+#ifndef FI_LAUNCH  // tests/emu/cuda_emu.hpp (the CPU functional emulator of the build container) supplies its own
 #define FI_LAUNCH(kernel, grid, block, smem, stream, ...)                 \
 	do {                                                                  \
 		kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);       \
 		::fi::count_launch();                                             \
 		FI_CUDA(cudaGetLastError());                                      \
 	} while (0)
+#endif
 
 // ---- tracing (the reference logs the wall time of each phase with loguru scopes, sparse_linear.cpp:62-198) ----
 // FI_B200_TRACE=1 prints one line per phase to stderr.
@@ -173,7 +175,7 @@ inline int div_up(int64_t a, int64_t b) { return static_cast<int>((a + b - 1) / 
 int sm_count();  // cached multiprocessor count of the current device (148 on B200)
 
 // ---- device-side reductions --------------------------------------------------------------------------
-#ifdef __CUDACC__
+#if defined(__CUDACC__) || defined(FI_B200_EMU)
 
 __device__ __forceinline__ double warp_sum(double v)
 {
@@ -231,6 +233,6 @@ __device__ __forceinline__ void grid_sum(const double (&mine)[K], double* partia
 	}
 }
 
-#endif  // __CUDACC__
+#endif  // __CUDACC__ || FI_B200_EMU
 
 }  // namespace fi

@@ -114,13 +114,21 @@ __global__ void __launch_bounds__(kThreads) pcg_init_kernel(int64_t n, const T* 
 // ---- peer-memory all-reduce (see solver.hpp) ----------------------------------------------------------------
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
 {
+#ifdef FI_B200_EMU  // tests/emu: no PTX on the CPU functional emulator
+	return *reinterpret_cast<const volatile unsigned long long*>(p);
+#else
 	unsigned long long v;
 	asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
 	return v;
+#endif
 }
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
 {
+#ifdef FI_B200_EMU
+	*reinterpret_cast<volatile unsigned long long*>(p) = v;
+#else
 	asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+#endif
 }
 
 // The first warp of a block, all 32 lanes: lane j stores this rank's `count` (<= 2) partial sums and then the sequence
@@ -181,9 +189,13 @@ __device__ __forceinline__ unsigned long long seq_of(unsigned long long base, co
 
 __device__ __forceinline__ unsigned long long global_ns()
 {
+#ifdef FI_B200_EMU
+	return 0;
+#else
 	unsigned long long t;
 	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
 	return t;
+#endif
 }
 
 __global__ void peer_publish_kernel(PeerLink L, int which, int par, unsigned long long base, const PcgState* st, const double* src, int count,

@@ -73,6 +73,25 @@ struct EpiArgs
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------
+#ifdef FI_B200_EMU
+// tests/emu (CPU functional emulator of the build container): a TMA load is a box copy with zero fill outside the
+// tensor, performed when it is issued; the mbarrier is a word holding {bytes still expected, completed phases}, so a
+// consumer that gets ahead of the producer thread still waits, as on the hardware.  Everything else runs as is.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(reinterpret_cast<uintptr_t>(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t) { *bar = 0; }
+__device__ __forceinline__ void fence_barrier_init() {}
+__device__ __forceinline__ void fence_proxy_async() {}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { *bar += static_cast<uint64_t>(bytes) << 32; }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+	while ((*reinterpret_cast<volatile uint64_t*>(bar) & 1u) == parity) { ::cuda_emu::spin_yield(); }
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int z)
+{
+	*bar -= static_cast<uint64_t>(::cuda_emu::tma_load_3d(dst, map, x, y, z)) << 32;
+	if ((*bar >> 32) == 0) { *bar += 1; }  // all expected bytes have landed: the phase completes
+}
+#else
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
@@ -107,6 +126,7 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 	    "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
 	    : "memory");
 }
+#endif  // FI_B200_EMU
 
 // ---- geometry of one block -----------------------------------------------------------------------------------
 template <typename T, int R>
@@ -151,7 +171,11 @@ __global__ void __launch_bounds__(256, MINB)
 
 	if (done && *done) { return; }
 
+#ifdef FI_B200_EMU
+	unsigned char* smem_raw = ::cuda_emu::dynamic_smem();
+#else
 	extern __shared__ unsigned char smem_raw[];
+#endif
 	unsigned char* base = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
 	auto stage_ptr = [&](int s, int a) { return reinterpret_cast<Pack*>(base + (static_cast<size_t>(s) * NA + a) * G::TILE_BYTES); };
 	unsigned char* ring_base = base + static_cast<size_t>(S) * NA * G::TILE_BYTES;

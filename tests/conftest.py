@@ -15,6 +15,31 @@ WKEYS = ["data_pos", "data_gradient", "model_0", "model_1", "model_2", "model_3"
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    if os.environ.get("FI_B200_TEST_EMU") == "1":
+        # Developer switch for the GPU-less build container, never set by the driver: run `-m gpu` tests against the CPU
+        # functional emulator build of the library (tests/emu/) to debug kernel LOGIC before a GPU box is available.
+        # Passing this way is not parity evidence; only a run on the B200 is.
+        use_emulated_library()
+
+
+def use_emulated_library():
+    """Swaps field_interpolation_b200._lib's handle for tests/emu/_build/libfi_emu.so in this process; returns a
+    function that undoes it."""
+    import ctypes
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+    import build_emu
+    from field_interpolation_b200 import _lib
+    dll = ctypes.CDLL(build_emu.build())
+    assert dll.fi_emu_marker() == 1
+    for name, (res, args) in _lib.SIGNATURES.items():
+        fn = getattr(dll, name)
+        fn.restype, fn.argtypes = res, args
+    before = _lib._dll
+    _lib._dll = dll
+
+    def undo():
+        _lib._dll = before
+    return undo
 
 
 def load_golden(name):
@@ -57,3 +82,14 @@ def ref():
     if r is None:
         pytest.skip("oracle/_ref not built (needs /root/reference)")
     return r
+
+
+@pytest.fixture
+def emu():
+    """The package bound to the CPU functional emulator build of the library (tests/emu/) for one test."""
+    undo = use_emulated_library()
+    import field_interpolation_b200 as m
+    try:
+        yield m
+    finally:
+        undo()

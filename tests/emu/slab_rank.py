@@ -1,0 +1,75 @@
+"""TEST INFRASTRUCTURE.  One emulated rank of a z-slab sharded solve (run by tests/test_emu_slab.py, `world` of these in
+parallel): loads the CPU functional emulator build of the library (tests/emu/_build/libfi_emu.so) in place of
+libfi_b200.so — in THIS process only —, joins a communicator through the fake NCCL on LD_LIBRARY_PATH, runs
+fi_slab_sdf_solve on the case named on the command line and saves its owned planes and solve statistics.
+
+    python slab_rank.py <rank> <world> <workdir> <case-json>
+"""
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+
+def load_emulated_library():
+    from field_interpolation_b200 import _lib
+    dll = C.CDLL(os.path.join(HERE, "_build", "libfi_emu.so"))
+    assert dll.fi_emu_marker() == 1
+    for name, (res, args) in _lib.SIGNATURES.items():
+        fn = getattr(dll, name)
+        fn.restype, fn.argtypes = res, args
+    _lib._dll = dll
+    return _lib
+
+
+def main():
+    rank, world, work = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3]
+    case = json.loads(sys.argv[4])
+    L = load_emulated_library()
+    import field_interpolation_b200 as fi
+    from field_interpolation_b200 import dist as fid
+    from field_interpolation_b200 import workloads as W
+
+    id_path = os.path.join(work, "nccl_id.bin")
+    if rank == 0:
+        buf = (C.c_ubyte * 128)()
+        L.check(L.lib().fi_comm_unique_id(buf, 128))
+        with open(id_path + ".tmp", "wb") as f:
+            f.write(bytes(buf))
+        os.replace(id_path + ".tmp", id_path)
+    t0 = time.time()
+    while not os.path.exists(id_path):
+        assert time.time() - t0 < 60, "rank 0 never published the communicator id"
+        time.sleep(0.01)
+    comm = fid.SlabComm(rank, world, open(id_path, "rb").read())
+
+    sizes = case["sizes"]
+    cloud = W.sphere_torus_3d(case["points"], seed=case.get("seed", 1))
+    pos = W.to_lattice(cloud["unit_pos"], sizes)
+    weights = fi.Weights(**case.get("weights", {}))
+    runner = fid.SlabRunner.__new__(fid.SlabRunner)
+    runner.sizes, runner.weights, runner.rank, runner.world, runner.comm = sizes, weights, rank, world, comm
+    runner.z0, runner.z1 = fid.slab_range(sizes[2], world, rank)
+    runner.local_cells = (runner.z1 - runner.z0) * sizes[0] * sizes[1]
+    results = {}
+    for name, o in case["solves"].items():
+        opt = fi.solve_options(fi.FI_F64 if o["precision"] == "f64" else fi.FI_F32, o["max_iterations"], o["tolerance"],
+                               preconditioner=fi.FI_PRECOND_MULTIGRID if o.get("multigrid") else fi.FI_PRECOND_JACOBI)
+        out = np.zeros(runner.local_cells, np.float32)
+        st = runner.step(pos, cloud["normals"], opt, out)
+        np.save(os.path.join(work, f"{name}_rank{rank}.npy"), out)
+        results[name] = st
+    with open(os.path.join(work, f"stats_rank{rank}.json"), "w") as f:
+        json.dump(results, f)
+    runner.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,120 @@
+"""CPU: kernel LOGIC of the CUDA sources on the functional emulator of tests/emu/ (the library's own .cu files compiled
+with g++; every thread of a block is a fiber, so __syncthreads, warp collectives, the TMA/mbarrier pipeline of
+stencil_tma.cu and the reduction protocols run with their real semantics, block after block on the host).
+
+These tests exist because the build container has no GPU: they catch indexing / protocol errors before a B200 box is
+available.  They are NOT the parity evidence for the CUDA build (floating-point contraction, memory model and the real
+TMA unit are out of their reach) — the `-m gpu` tests are — and nothing in the product ever loads the emulated library.
+"""
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, assert_system_bit_exact, bits, golden_names, load_golden
+from field_interpolation_b200 import workloads as W
+from oracle import oracle as O
+
+
+@pytest.mark.parametrize("name", golden_names("iso_"))
+def test_isosurface_kernels_on_reference_fixtures(emu, name):
+    """csrc/isosurface.cu: count -> scan -> emit marching squares, area, Catmull-Rom upsampling against outputs frozen
+    from the reference's own code (bit for bit; compiled like the CUDA build without fp contraction)."""
+    g = load_golden(name)
+    field, up = g["field"], int(g["upsample"])
+    lines, area = emu.iso_surface(field, 0.0, want_area=True)
+    assert lines.shape == g["lines"].shape and np.array_equal(bits(lines), bits(g["lines"]))
+    assert abs(np.float32(area) - g["area"]) <= np.spacing(np.abs(g["area"]))
+    big = emu.bicubic_upsample(field, up)
+    assert np.array_equal(bits(big), bits(g["upsampled"]))
+    il = emu.iso_surface(big, float(g["iso"]))
+    assert il.shape == g["iso_lines_up"].shape and np.array_equal(bits(il), bits(g["iso_lines_up"]))
+
+
+@pytest.mark.parametrize("shape", [(31, 1025), (300, 257)])
+def test_isosurface_blocks_spanning_rows(emu, port, shape):
+    rng = np.random.default_rng(shape[0])
+    a = rng.standard_normal(shape).astype(np.float32)
+    a[rng.random(shape) < 0.1] = 0.0
+    want = port.iso_surface(a, 0.25)
+    got, area = emu.iso_surface(a, 0.25, want_area=True)
+    assert got.shape == want.shape and np.array_equal(bits(got), bits(want))
+    assert abs(np.float32(area) - np.float32(port.calc_area(want))) <= np.spacing(np.abs(np.float32(port.calc_area(want))))
+
+
+def test_assembly_and_solves_small_3d(emu, port):
+    """Scatter / sort / triplet export, the TMA-staged fused PCG iteration and the multigrid V-cycle on a lattice the
+    emulator finishes in seconds: triplet view bit for bit against the port, solved fields against the exact solve."""
+    sizes = [32, 8, 12]
+    cloud = W.sphere_torus_3d(400, seed=3)
+    pos = W.to_lattice(cloud["unit_pos"], sizes)
+    f = emu.sdf_from_points(sizes, emu.Weights(), pos, cloud["normals"])
+    want = port.sdf_from_points(sizes, O.make_weights(), pos, cloud["normals"]).system()
+    assert_system_bit_exact(f.eq, want.rows, want.cols, want.vals, want.rhs)
+    exact = O.exact_solve(want, f.num_unknowns)
+    x, st = f.solve(emu.solve_options(emu.FI_F64, 0, 1e-10, check_every=64))
+    assert st["converged"] and np.linalg.norm(x - exact) <= 1e-5 * np.linalg.norm(exact)
+    # the three stencil kernels agree on the operator
+    v = np.random.default_rng(0).normal(size=f.num_unknowns)
+    ys = []
+    for mode in (1, 2, 0):
+        f.use_fast_stencil(mode)
+        ys.append(f.apply(v, emu.FI_F64))
+    assert np.allclose(ys[0], ys[2], rtol=0, atol=1e-11 * np.abs(ys[2]).max()) and np.allclose(ys[1], ys[2], rtol=0, atol=1e-11 * np.abs(ys[2]).max())
+    f.use_fast_stencil(1)
+    xm, stm = f.solve(emu.solve_options(emu.FI_F64, 200, 1e-10, preconditioner=emu.FI_PRECOND_MULTIGRID))
+    assert stm["converged"] and stm["iterations"] < st["iterations"] and np.linalg.norm(xm - exact) <= 1e-5 * np.linalg.norm(exact)
+
+
+# ---- world_size > 1: the z-slab sharded solves over the fake NCCL (processes + shared memory) ---------------------------
+def _run_ranks(world, case, gather=None):
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+    import build_emu
+    build_emu.build()
+    nccl_dir = build_emu.build_fake_nccl()
+    with tempfile.TemporaryDirectory() as work:
+        env = dict(os.environ, LD_LIBRARY_PATH=nccl_dir + ":" + os.environ.get("LD_LIBRARY_PATH", ""), FI_B200_P2P="0")
+        env.pop("FI_B200_MG_GATHER_CELLS", None)
+        if gather:
+            env["FI_B200_MG_GATHER_CELLS"] = str(gather)
+        procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "emu", "slab_rank.py"), str(r), str(world), work, json.dumps(case)],
+                                  env=env, stderr=subprocess.PIPE, text=True) for r in range(world)]
+        try:
+            errs = [p.communicate(timeout=600)[1] for p in procs]
+        finally:
+            for p in procs:
+                if p.poll() is None:
+                    p.kill()
+        assert [p.returncode for p in procs] == [0] * world, "\n".join(e[-800:] for e in errs)
+        stats = json.load(open(os.path.join(work, "stats_rank0.json")))
+        fields = {k: np.concatenate([np.load(os.path.join(work, f"{k}_rank{r}.npy")) for r in range(world)]) for k in case["solves"]}
+    return fields, stats
+
+
+SLAB_SOLVES = {"pcg64": {"precision": "f64", "max_iterations": 10, "tolerance": 1e-30},
+               "pcg32": {"precision": "f32", "max_iterations": 10, "tolerance": 1e-30},
+               "mg64": {"precision": "f64", "max_iterations": 100, "tolerance": 1e-9, "multigrid": True}}
+
+
+@pytest.mark.parametrize("sizes,weights,gather", [([32, 24, 24], {}, 1000), ([32, 16, 37], {"model_1": 0.3}, None)])
+def test_slab_sharded_solves_match_one_rank(sizes, weights, gather):
+    """fi_slab_sdf_solve with 2 and 3 emulated ranks against the same call on 1 rank: Jacobi-PCG iterate for iterate
+    (the halo planes of r travel by ncclSend/ncclRecv, the fused kernel recomputes the direction on the halo planes), and
+    the sharded multigrid V-cycle (halo exchange before every smoother application, restriction ownership, all-gather of
+    the restricted residual, replicated tail) — the same linear operator whatever the number of ranks: same iteration
+    count, same field.  gather = 1000 forces two sharded levels; nz = 37 gives ragged slabs."""
+    case = {"sizes": sizes, "points": 2500, "seed": 5, "weights": weights, "solves": SLAB_SOLVES}
+    base, st1 = _run_ranks(1, case, gather)
+    assert st1["mg64"]["converged"]
+    for world in (2, 3):
+        out, st = _run_ranks(world, case, gather)
+        assert st["pcg64"]["iterations"] == st["pcg32"]["iterations"] == 10
+        assert np.linalg.norm(out["pcg64"] - base["pcg64"]) <= 1e-7 * np.linalg.norm(base["pcg64"])  # fp64 iterates, stored as float
+        assert np.linalg.norm(out["pcg32"] - base["pcg32"]) <= 2e-4 * np.linalg.norm(base["pcg32"])
+        assert st["mg64"]["converged"] and abs(st["mg64"]["iterations"] - st1["mg64"]["iterations"]) <= 1
+        assert abs(st["mg64"]["relative_residual"] - st1["mg64"]["relative_residual"]) <= 0.05 * st1["mg64"]["relative_residual"]
+        assert np.linalg.norm(out["mg64"] - base["mg64"]) <= 1e-6 * np.linalg.norm(base["mg64"])
