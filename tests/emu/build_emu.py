@@ -10,7 +10,7 @@ CSRC = os.path.join(ROOT, "field_interpolation_b200", "csrc")
 OUT = os.path.join(HERE, "_build", "libfi_emu.so")
 # every source of the library (stencil_tma.cu: TMA loads become synchronous box copies, see its FI_B200_EMU hooks)
 CU = ["abi.cu", "assembly.cu", "sort_scan.cu", "stencil.cu", "stencil_fast.cu", "stencil_tma.cu", "solver.cu", "mg.cu", "errormap.cu", "isosurface.cu", "dist.cu"]
-CPP = ["cuda_emu.cpp", "emu_glue.cpp", "emu_stubs.cpp"]
+CPP = ["cuda_emu.cpp", "emu_glue.cpp"]
 
 
 def build(force: bool = False) -> str:
@@ -42,7 +42,7 @@ def build(force: bool = False) -> str:
                 sys.stderr.write(r.stdout + r.stderr)
                 raise RuntimeError("emulator build failed")
             objs.append(obj)
-    r = subprocess.run([base[0], "-shared", "-Wl,-Bsymbolic", "-o", OUT, *objs, "-ldl", "-lpthread"], capture_output=True, text=True)
+    r = subprocess.run([base[0], "-shared", "-Wl,-Bsymbolic", "-o", OUT, *objs, "-ldl", "-lpthread", "-lrt"], capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("emulator link failed")

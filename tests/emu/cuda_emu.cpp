@@ -2,9 +2,14 @@
 // library's host code calls, over plain host memory.
 #include "cuda_emu.hpp"
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <unistd.h>
+
 #include <cstdio>
 #include <cstdlib>
 #include <map>
+#include <string>
 #include <memory>
 #include <vector>
 
@@ -326,14 +331,99 @@ using cuda_emu::Graph;
 
 extern "C" {
 
+// Device memory is host memory.  With CUDA_EMU_IPC=1 (the emulated ranks of a multi-process test) every allocation is a
+// named shared-memory mapping, so that cudaIpcGetMemHandle / cudaIpcOpenMemHandle can hand it to another process the
+// way CUDA IPC hands device memory to a peer GPU's process.
+struct Mapping
+{
+	std::string name;  // empty: opened from a peer (not ours to unlink)
+	size_t      bytes;
+};
+static std::map<void*, Mapping> g_mappings;
+static bool ipc_enabled()
+{
+	static const bool on = std::getenv("CUDA_EMU_IPC") != nullptr;
+	return on;
+}
+static void unlink_all_mappings()
+{
+	for (auto& m : g_mappings) {
+		if (!m.second.name.empty()) { shm_unlink(m.second.name.c_str()); }
+	}
+}
+
 cudaError_t cudaMalloc(void** p, size_t n)
 {
-	*p = std::malloc(n ? n : 1);
-	return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+	if (!ipc_enabled()) {
+		*p = std::malloc(n ? n : 1);
+		return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+	}
+	static int  counter = 0;
+	static bool hooked  = false;
+	if (!hooked) {
+		std::atexit(unlink_all_mappings);
+		hooked = true;
+	}
+	char name[48];
+	std::snprintf(name, sizeof(name), "/fi_emu_%d_%d", static_cast<int>(getpid()), counter++);
+	const size_t bytes = (std::max<size_t>(n, 1) + 4095) & ~size_t{4095};
+	const int    fd    = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+	if (fd < 0 || ftruncate(fd, static_cast<off_t>(bytes)) != 0) { return cudaErrorMemoryAllocation; }
+	void* q = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+	close(fd);
+	if (q == MAP_FAILED) { return cudaErrorMemoryAllocation; }
+	g_mappings[q] = Mapping{name, bytes};
+	*p            = q;
+	return cudaSuccess;
 }
 cudaError_t cudaFree(void* p)
 {
-	std::free(p);
+	auto it = g_mappings.find(p);
+	if (it == g_mappings.end()) {
+		std::free(p);
+		return cudaSuccess;
+	}
+	munmap(p, it->second.bytes);
+	if (!it->second.name.empty()) { shm_unlink(it->second.name.c_str()); }
+	g_mappings.erase(it);
+	return cudaSuccess;
+}
+struct EmuIpcHandle
+{
+	char               name[48];
+	unsigned long long bytes;
+};
+static_assert(sizeof(EmuIpcHandle) <= sizeof(cudaIpcMemHandle_t), "emulated IPC handle must fit the opaque one");
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p)
+{
+	auto it = g_mappings.find(p);
+	if (it == g_mappings.end() || it->second.name.empty()) { return cudaErrorNotSupported; }
+	EmuIpcHandle e{};
+	std::snprintf(e.name, sizeof(e.name), "%s", it->second.name.c_str());
+	e.bytes = it->second.bytes;
+	std::memset(h, 0, sizeof(*h));
+	std::memcpy(h, &e, sizeof(e));
+	return cudaSuccess;
+}
+cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned)
+{
+	EmuIpcHandle e;
+	std::memcpy(&e, &h, sizeof(e));
+	const int fd = shm_open(e.name, O_RDWR, 0600);
+	if (fd < 0) { return cudaErrorInvalidValue; }
+	void* q = mmap(nullptr, e.bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+	close(fd);
+	if (q == MAP_FAILED) { return cudaErrorInvalidValue; }
+	g_mappings[q] = Mapping{"", static_cast<size_t>(e.bytes)};
+	*p            = q;
+	return cudaSuccess;
+}
+cudaError_t cudaIpcCloseMemHandle(void* p)
+{
+	auto it = g_mappings.find(p);
+	if (it == g_mappings.end()) { return cudaErrorInvalidValue; }
+	munmap(p, it->second.bytes);
+	g_mappings.erase(it);
 	return cudaSuccess;
 }
 cudaError_t cudaMallocHost(void** p, size_t n) { return cudaMalloc(p, n); }

@@ -1,7 +1,7 @@
 // TEST INFRASTRUCTURE — NOT PRODUCT CODE.  A functional emulator of the CUDA execution model for the build container,
 // which has nvcc but no GPU: the library's .cu sources are compiled a second time with g++ (this header is
 // force-included) into tests/emu/_build/libfi_emu.so, where every kernel launch runs block after block on the CPU, each
-// thread of a block as a cooperatively scheduled fiber (ucontext) so that __syncthreads and the warp collectives
+// thread of a block as a cooperatively scheduled fiber so that __syncthreads and the warp collectives
 // (__shfl_*_sync, __ballot_sync, __match_any_sync, ...) have their real semantics.  "Device" memory is host memory.
 //
 // What it is for: catching LOGIC errors in kernels (indexing, scan offsets, reduction protocols, barriers that not every
@@ -102,9 +102,9 @@ inline size_t __cvta_generic_to_shared(const void* p) { return reinterpret_cast<
 
 inline void __syncthreads() { ::cuda_emu::block_barrier(); }
 inline void __syncwarp(unsigned mask = 0xffffffffu) { ::cuda_emu::warp_barrier(mask); }
-inline void __threadfence() {}
-inline void __threadfence_system() {}
-inline void __threadfence_block() {}
+inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }  // peers are other processes of this machine
+inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 
 template <typename T>
 inline T __shfl_sync(unsigned mask, T v, int src, int width = 32)

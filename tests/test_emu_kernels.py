@@ -71,14 +71,19 @@ def test_assembly_and_solves_small_3d(emu, port):
 
 
 # ---- world_size > 1: the z-slab sharded solves over the fake NCCL (processes + shared memory) ---------------------------
-def _run_ranks(world, case, gather=None):
+def _run_ranks(world, case, gather=None, p2p=False):
     sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
     import build_emu
     build_emu.build()
     nccl_dir = build_emu.build_fake_nccl()
     with tempfile.TemporaryDirectory() as work:
-        env = dict(os.environ, LD_LIBRARY_PATH=nccl_dir + ":" + os.environ.get("LD_LIBRARY_PATH", ""), FI_B200_P2P="0")
+        env = dict(os.environ, LD_LIBRARY_PATH=nccl_dir + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
         env.pop("FI_B200_MG_GATHER_CELLS", None)
+        if p2p:  # emulated CUDA IPC (shared-memory allocations): mailboxes + halo push by peer stores, graph-captured iterations
+            env["CUDA_EMU_IPC"] = "1"
+            env.pop("FI_B200_P2P", None)
+        else:    # ncclSend / ncclRecv + ncclAllReduce inside the iteration
+            env["FI_B200_P2P"] = "0"
         if gather:
             env["FI_B200_MG_GATHER_CELLS"] = str(gather)
         procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "emu", "slab_rank.py"), str(r), str(world), work, json.dumps(case)],
@@ -118,3 +123,23 @@ def test_slab_sharded_solves_match_one_rank(sizes, weights, gather):
         assert st["mg64"]["converged"] and abs(st["mg64"]["iterations"] - st1["mg64"]["iterations"]) <= 1
         assert abs(st["mg64"]["relative_residual"] - st1["mg64"]["relative_residual"]) <= 0.05 * st1["mg64"]["relative_residual"]
         assert np.linalg.norm(out["mg64"] - base["mg64"]) <= 1e-6 * np.linalg.norm(base["mg64"])
+
+
+def test_slab_peer_memory_path_matches_one_rank():
+    """The default multi-GPU iteration — r in a CUDA-IPC-mapped vector, boundary planes stored straight into the
+    neighbours' halos by pcg_update_peer_kernel, scalar sums through the per-rank mailboxes, no NCCL inside the CUDA
+    graph — with 2 and 3 emulated ranks (processes sharing memory) against 1 rank: iterate for iterate in fp64, and the
+    same iteration count to a tolerance (the device-side stop and the leftover replays of a finished solve included)."""
+    solves = {"pcg64": {"precision": "f64", "max_iterations": 12, "tolerance": 1e-30},
+              "pcg32": {"precision": "f32", "max_iterations": 12, "tolerance": 1e-30},
+              "conv64": {"precision": "f64", "max_iterations": 2000, "tolerance": 1e-3}}
+    case = {"sizes": [32, 16, 24], "points": 2500, "seed": 5, "weights": {}, "solves": solves}
+    base, st1 = _run_ranks(1, case)
+    assert st1["conv64"]["converged"]
+    for world in (2, 3):
+        out, st = _run_ranks(world, case, p2p=True)
+        assert st["pcg64"]["iterations"] == st["pcg32"]["iterations"] == 12
+        assert np.linalg.norm(out["pcg64"] - base["pcg64"]) <= 1e-7 * np.linalg.norm(base["pcg64"])
+        assert np.linalg.norm(out["pcg32"] - base["pcg32"]) <= 2e-4 * np.linalg.norm(base["pcg32"])
+        assert st["conv64"]["converged"] and abs(st["conv64"]["iterations"] - st1["conv64"]["iterations"]) <= 2
+        assert np.linalg.norm(out["conv64"] - base["conv64"]) <= 1e-4 * np.linalg.norm(base["conv64"])
