@@ -1,0 +1,13 @@
+#!/bin/bash
+# Multi-GPU visit (gpurun --gpus 2, then --gpus 8 when the pod has room): parity of the z-slab solves against the
+# single-GPU solve (Jacobi-PCG over peer memory, sharded multigrid V-cycle: validated so far only on the CPU emulator
+# of tests/emu with 2-3 ranks), then the bench line with the sharded time-to-1e-6.
+# Usage: gpurun --gpus N --timeout 900 -- 'bash scripts/gpu_round12_multi.sh N'
+N=${1:-2}
+set -x
+mkdir -p gpurun_out
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 scripts/slab_check.py \
+    > gpurun_out/slab_check12_n$N.jsonl 2> gpurun_out/slab_check12_n$N.err; echo "exit $?" >> gpurun_out/slab_check12_n$N.jsonl
+grep -v "^\[fi" gpurun_out/slab_check12_n$N.jsonl | tail -30
+FI_B200_TRACE=1 timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N \
+    > gpurun_out/bench12_n$N.json 2> gpurun_out/bench12_n$N.err; tail -c 2500 gpurun_out/bench12_n$N.json; grep "per-iteration us" gpurun_out/bench12_n$N.err | tail -8
