@@ -1087,7 +1087,8 @@ template <typename T>
 bool apply_data_term_epilogue(const Geom& g, const DataTerm<T>& dt, const T* in, T* res_out, const T* minv, T* e, T* d_new, T b,
                               cudaStream_t s)
 {
-	if (dt.nrows > 0 || g.tile || g.sharded()) { return false; }
+	// (a slab applies the rows of the nodes it owns: cell_mask bits 8..15, as in apply_blocks_kernel)
+	if (dt.nrows > 0 || g.tile) { return false; }
 	if (dt.nocc > 0) {
 		by_dim(g.ndim, [&](auto dim) {
 			auto kern = apply_blocks_epilogue_kernel<T, decltype(dim)::value>;

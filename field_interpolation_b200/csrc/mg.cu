@@ -680,7 +680,7 @@ struct SlabMultigrid::DLevel
 	Operator<float>*                 op = nullptr;  // level 0: the caller's operator; coarser: owned below
 	std::unique_ptr<Operator<float>> owned;
 	PointStore                       pts;
-	DevBuf<float>                    r, e, res, d, q;  // slab-local; r / e of level 0 are the caller's vectors
+	DevBuf<float>                    r, e, res, d, d2, q;  // slab-local; r / e of level 0 are the caller's vectors (d2: ping-pong partner of d)
 	double                           lmax = 0;
 	Xfer                             to_coarser;    // tables over the WHOLE axes of this level and the next
 	DevBuf<int>                      xfer_int;
@@ -806,9 +806,11 @@ std::unique_ptr<SlabMultigrid> build_slab_multigrid(Operator<float>& fine, const
 		}
 		lv->res.resize(n);
 		lv->d.resize(n);
+		lv->d2.resize(n);
 		lv->q.resize(n);
 		lv->res.zero(s);  // halo planes and planes beyond the lattice must be finite (zero) before anything reads them
 		lv->d.zero(s);
+		lv->d2.zero(s);
 		lv->q.zero(s);
 		const Geom gf = make_geom(D, plan.size[l]), gc = make_geom(D, plan.size[l + 1]);
 		build_xfer(lv->to_coarser, lv->xfer_int, lv->xfer_float, gf, gc, s);
@@ -862,39 +864,56 @@ std::unique_ptr<SlabMultigrid> build_slab_multigrid(Operator<float>& fine, const
 
 namespace {
 
-// q = A v on the slab's owned rows, after refreshing v's halo planes from the neighbours
-void slab_apply(SlabMultigrid::DLevel& lv, float* v, cudaStream_t s)
+// One pass over the slab's owned planes after refreshing the halo planes of `in` from the neighbours:
+//     res_out = res_in - A in   and, with d_new,   d_new = a in + b M^-1 res_out,   e += d_new
+// — the TMA stencil kernel in epilogue mode plus the data term's fix-up when they apply (28 B/cell), else the plain
+// operator and a vector kernel (8 + 32 B/cell).  Without d_new only the residual is formed.  d_new must not alias in.
+void slab_step(SlabMultigrid::DLevel& lv, float* in, const float* res_in, float* res_out, float* e, float* d_new, float a, float b, cudaStream_t s)
 {
-	lv.hooks->exchange_halo(v, sizeof(float), s);
-	lv.op->apply(v, lv.q.data(), nullptr, nullptr, s);
+	const int64_t    off = lv.g.own_offset(), n = lv.g.own_cells();
+	Operator<float>& op  = *lv.op;
+	lv.hooks->exchange_halo(in, sizeof(float), s);
+	if (op.data.nrows == 0 && op.use_fast == kStencilAuto &&
+	    stencil_tma_3d_epilogue<float>(op.g, op.tabs, in, res_in, res_out, op.minv.data(), e, d_new, a, b, s)) {
+		const bool ok = apply_data_term_epilogue<float>(op.g, op.data, in, res_out, op.minv.data(), e, d_new, b, s);
+		FI_REQUIRE(ok, FI_ERR_UNSUPPORTED, "slab multigrid: data-term epilogue refused after the stencil epilogue ran");
+		return;
+	}
+	op.apply(in, lv.q.data(), nullptr, nullptr, s);
+	if (d_new == nullptr) {
+		FI_LAUNCH(residual_sub_kernel, vgrid(n), kThreads, 0, s, n, res_in + off, static_cast<const float*>(lv.q.data() + off), res_out + off);
+		return;
+	}
+	// the vector kernel updates the direction in place: bring it to d_new first
+	FI_CUDA(cudaMemcpyAsync(d_new + off, in + off, static_cast<size_t>(n) * sizeof(float), cudaMemcpyDeviceToDevice, s));
+	FI_LAUNCH(cheb_step_kernel, vgrid(n), kThreads, 0, s, n, res_in + off, res_out + off, static_cast<const float*>(lv.q.data() + off), d_new + off,
+	          op.minv.data() + off, e + off, a, b, 0);
 }
 
-// nu Chebyshev steps on A e = r over the slab's owned planes (the unfused form of smooth()).  Returns the residual
-// before the last correction and the last correction, like smooth().
+// nu Chebyshev steps on A e = r over the slab's owned planes (smooth() on a slab).  Returns the residual before the last
+// correction and the last correction, like smooth().
 Smoothed slab_smooth(SlabMultigrid::DLevel& lv, const MgOptions& opt, const float* r, float* e, bool e_zero, cudaStream_t s)
 {
 	const int64_t off = lv.g.own_offset(), n = lv.g.own_cells();
 	const double  lmax  = lv.lmax, lmin = lmax / opt.cheb_ratio;
 	const double  theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
-	float *       d = lv.d.data(), *res = lv.res.data();
+	float *       d = lv.d.data(), *d_other = lv.d2.data(), *res = lv.res.data();
 	const float*  minv = lv.op->minv.data();
 	const float*  res_src = r;
 	const float   b0 = static_cast<float>(1.0 / theta);
 	if (e_zero) {  // res = r: d = b0 M^-1 r, e = d
 		FI_LAUNCH(cheb_step_kernel, vgrid(n), kThreads, 0, s, n, r + off, res + off, static_cast<const float*>(nullptr), d + off, minv + off, e + off, 0.0f, b0, 1);
 	} else {  // res = r - A e, then the first step from it
-		slab_apply(lv, e, s);
-		FI_LAUNCH(cheb_step_kernel, vgrid(n), kThreads, 0, s, n, r + off, res + off, static_cast<const float*>(lv.q.data() + off), d + off, minv + off, e + off, 0.0f,
-		          b0, 0);
+		slab_step(lv, e, r, res, nullptr, nullptr, 0.0f, 0.0f, s);
+		FI_LAUNCH(cheb_step_kernel, vgrid(n), kThreads, 0, s, n, res + off, res + off, static_cast<const float*>(nullptr), d + off, minv + off, e + off, 0.0f, b0, 0);
 		res_src = res;
 	}
 	double rho = 1.0 / sigma;
 	for (int k = 1; k < opt.nu; ++k) {
 		const double rho_new = 1.0 / (2.0 * sigma - rho);
 		const float  a = static_cast<float>(rho_new * rho), b = static_cast<float>(2.0 * rho_new / delta);
-		slab_apply(lv, d, s);
-		FI_LAUNCH(cheb_step_kernel, vgrid(n), kThreads, 0, s, n, res_src + off, res + off, static_cast<const float*>(lv.q.data() + off), d + off, minv + off, e + off,
-		          a, b, 0);
+		slab_step(lv, d, res_src, res, e, d_other, a, b, s);
+		std::swap(d, d_other);
 		res_src = res;
 		rho     = rho_new;
 	}
@@ -909,8 +928,7 @@ void slab_vcycle_level(SlabMultigrid& mg, int l, const float* r, float* e, cudaS
 	const bool             last = l + 1 == mg.plan.nd;
 	const Smoothed         sm = slab_smooth(lv, mg.opt, r, e, true, s);
 	// residual after the last correction
-	slab_apply(lv, sm.d, s);
-	FI_LAUNCH(residual_sub_kernel, vgrid(n), kThreads, 0, s, n, sm.res + off, static_cast<const float*>(lv.q.data() + off), lv.res.data() + off);
+	slab_step(lv, sm.d, sm.res, lv.res.data(), nullptr, nullptr, 0.0f, 0.0f, s);
 	lv.hooks->exchange_halo(lv.res.data(), sizeof(float), s);
 	// restriction into the planes [c0, c1) of the next level: the kernel indexes fine planes by their lattice z, so the
 	// slab pointer is moved back by the slab's first stored plane; the z tables start at c0

@@ -519,7 +519,9 @@ template <typename T>
 bool stencil_tma_3d_epilogue(const Geom& g, const StencilTables& t, const T* in, const T* res_in, T* res_out, const T* minv, T* e, T* d_new,
                              T a, T b, cudaStream_t s)
 {
-	if (!eligible<T>(g, t) || g.sharded()) { return false; }
+	// On a slab (g.sharded()) the owned planes are updated; the halo planes of `in` must be current, those of the outputs
+	// are the caller's business.
+	if (!eligible<T>(g, t)) { return false; }
 	EpiArgs<T> epi;
 	epi.res_in  = res_in;
 	epi.res_out = res_out;
