@@ -143,3 +143,19 @@ def test_slab_peer_memory_path_matches_one_rank():
         assert np.linalg.norm(out["pcg32"] - base["pcg32"]) <= 2e-4 * np.linalg.norm(base["pcg32"])
         assert st["conv64"]["converged"] and abs(st["conv64"]["iterations"] - st1["conv64"]["iterations"]) <= 2
         assert np.linalg.norm(out["conv64"] - base["conv64"]) <= 1e-4 * np.linalg.norm(base["conv64"])
+
+
+@pytest.mark.parametrize("target,select", [
+    ("tests/test_gpu_assembly.py", "not device_resident"),
+    ("tests/test_gpu_solve.py", "operator_matches or 1d_known or generic_rows or jacobi or randomised_golden"),
+])
+def test_gpu_test_bodies_pass_on_the_emulator(target, select):
+    """The bodies of the `-m gpu` parity tests (triplet view bit for bit against the reference's fixtures and the port;
+    the operator against the explicit normal equations; 1D/2D/3D golden solutions; generic rows; Jacobi sweeps), run in
+    a child pytest whose library handle is the emulator build (FI_B200_TEST_EMU=1, tests/conftest.py).  Selections are
+    the cases the emulator finishes in seconds and that need no torch CUDA tensor."""
+    env = dict(os.environ, FI_B200_TEST_EMU="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, target), "-m", "gpu", "-q", "-x", "-k", select, "-p", "no:cacheprovider"],
+                       env=env, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+    assert " passed" in r.stdout and " failed" not in r.stdout
