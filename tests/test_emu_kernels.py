@@ -159,3 +159,18 @@ def test_gpu_test_bodies_pass_on_the_emulator(target, select):
                        env=env, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
     assert " passed" in r.stdout and " failed" not in r.stdout
+
+
+def test_cpp_drop_in_callers_pass_on_the_emulator(tmp_path):
+    """tests/cpp/api_driver.cpp (the reference's own callers replayed against the drop-in headers, iso-surface sequence
+    included) with libfi_b200.so resolved to the emulator build: exercises the C++ host layer end to end on the CPU."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+    import build_emu
+    os.symlink(build_emu.build(), tmp_path / "libfi_b200.so")
+    env = dict(os.environ, LD_LIBRARY_PATH=str(tmp_path) + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_cpp_api.py"),
+                        os.path.join(ROOT, "tests", "test_gpu_zz_isosurface.py"), "-m", "gpu", "-q", "-x", "-k",
+                        "readme or field_1d or interpolate_2d or hand_written or cpp_drop_in", "-p", "no:cacheprovider"],
+                       env=env, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+    assert " passed" in r.stdout and " failed" not in r.stdout
