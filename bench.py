@@ -205,7 +205,12 @@ def main():
 
     if world > 1:
         from field_interpolation_b200 import dist as fid
-        runner = fid.SlabRunner(sizes, weights, rank, world, dist)
+        # The occupied cells of the cloud cluster in the middle slabs, and the slowest rank sets the pace of every
+        # iteration: partition by cost (lattice planes + data points, fi_slab_balanced_cuts) instead of by plane count.
+        # One histogram kernel over the resident points, computed once for the cloud (it fixes the size of every rank's
+        # output buffer); FI_B200_BENCH_UNIFORM=1 keeps the uniform partition.
+        cuts = None if os.environ.get("FI_B200_BENCH_UNIFORM") == "1" else fid.balanced_cuts(sizes, world, d_pos, 0.0, 8)
+        runner = fid.SlabRunner(sizes, weights, rank, world, dist, cuts=cuts)
     else:
         runner = None
 
@@ -275,7 +280,7 @@ def main():
     ms_e2e, its_e2e = timed(step_e2e, args.steps)
     e2e_value = N * its_e2e / (ms_e2e * 1e-3)
     h2d = h_pos.numel() * 4 + h_nrm.numel() * 4
-    d2h = h_out.numel() * 4 * (world if runner is not None else 1)
+    d2h = N * 4  # every rank reads back its owned planes: the whole field over all ranks
 
     # roofline of the dominant kernel, measured live with CUDA events on the solver stream
     peak, peak_src = peaks()
@@ -313,7 +318,8 @@ def main():
         R = 2  # default Weights: model_2 -> radius-2 star
         it_ms = last_stats.get("solve_ms", 0.0) / max(1, last_stats.get("iterations", 1))
         halo_bytes = 2 * R * n * n * (4 if args.precision == "f32" else 8)  # an interior rank: both neighbours
-        extra = {"slab": {"planes_per_rank": n // world, "setup_ms": last_stats.get("setup_ms"), "solve_ms": last_stats.get("solve_ms"),
+        extra = {"slab": {"planes_per_rank": [b - a for a, b in zip(runner.cuts, runner.cuts[1:])] if runner.cuts else n // world,
+                          "partition": "cost-balanced (fi_slab_balanced_cuts)" if runner.cuts else "uniform", "setup_ms": last_stats.get("setup_ms"), "solve_ms": last_stats.get("solve_ms"),
                           "ms_per_iteration": it_ms, "halo_bytes_per_iteration_per_interior_rank": halo_bytes,
                           "halo_GBps_per_interior_rank_averaged_over_iteration": halo_bytes / max(it_ms, 1e-9) / 1e6,
                           "path": "peer stores over NVLink inside pcg_update_peer_kernel" if os.environ.get("FI_B200_P2P", "1") != "0" else "ncclSend/ncclRecv"}}
@@ -370,7 +376,7 @@ def main():
                                 "recurrence_residual": st["relative_residual"], "converged": bool(st["converged"]),
                                 "solve_ms": st["solve_ms"], "setup_ms": st["setup_ms"]}
                 ttt[pname] = best
-            plan = fid.slab_mg_plan(sizes, world, 2)
+            plan = fid.slab_mg_plan(sizes, world, 2)  # level sizes (the plane ranges it lists are those of the uniform partition)
             ttt["method"] = (f"fi_slab_sdf_solve (host arrays) + multigrid-preconditioned CG, V-cycle z-slab sharded on {plan['sharded_levels']} level(s) "
                              f"({'/'.join('x'.join(map(str, s_)) for s_ in plan['sizes'][:-1])}), replicated from {'x'.join(map(str, plan['sizes'][-1]))}; best of 2 after one warm pass")
         except Exception as e:  # deterministic refusals (lattice not shardable this way) hit every rank alike

@@ -102,6 +102,8 @@ SIGNATURES = {
     "fi_comm_unique_id": (C.c_int, [_vp, _i64]),
     "fi_comm_create": (C.c_int, [_i32, _i32, _vp, _p(_vp)]),
     "fi_comm_destroy": (C.c_int, [_vp]),
+    "fi_slab_balanced_cuts": (C.c_int, [_pi32, _i32, _i64, _vp, _i32, _d, _i32, _pi32]),
+    "fi_comm_set_slab_cuts": (C.c_int, [_vp, _i32, _pi32]),
     "fi_slab_range": (C.c_int, [_i32, _i32, _i32, _pi32, _pi32]),
     "fi_slab_mg_plan": (C.c_int, [_pi32, _i32, _i32, _i64, _pi32, _pi32, _pi32, _pi32]),
     "fi_slab_sdf_solve": (C.c_int, [_vp, _pi32, _p(fi_weights), _i64, _vp, _vp, _vp, _i32, _p(fi_solve_options), _vp, _vp, _i32,

@@ -1125,6 +1125,21 @@ int fi_slab_mg_plan(const int32_t* sizes, int32_t world, int32_t stencil_radius,
 	});
 }
 
+int fi_slab_balanced_cuts(const int32_t* sizes, int32_t world, int64_t num_points, const float* positions, int32_t loc, double point_weight,
+                          int32_t min_planes, int32_t* cuts)
+{
+	return guarded([&] {
+		FI_REQUIRE(sizes && cuts && world >= 1 && world <= 64 && num_points >= 0 && (positions || num_points == 0), FI_ERR_INVALID, "bad argument");
+		for (int d = 0; d < 3; ++d) { FI_REQUIRE(sizes[d] >= 1, FI_ERR_INVALID, "lattice size must be >= 1"); }
+		balanced_cuts(sizes, world, num_points, positions, loc, point_weight > 0 ? point_weight : 9.0, min_planes, cuts);
+	});
+}
+
+int fi_comm_set_slab_cuts(fi_comm* c, int32_t nz, const int32_t* cuts)
+{
+	return guarded([&] { comm_set_cuts(c, nz, cuts); });
+}
+
 int fi_slab_range(int32_t nz, int32_t world, int32_t rank, int32_t* z0, int32_t* z1)
 {
 	return guarded([&] {

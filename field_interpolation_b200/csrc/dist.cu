@@ -110,6 +110,9 @@ struct fi_comm
 	void*              shared_lo    = nullptr;  // rank - 1's vector, mapped here
 	void*              shared_hi    = nullptr;  // rank + 1's vector, mapped here
 	unsigned long long seq          = 0;
+	// non-uniform z partition of an nz = cuts_nz lattice (fi_comm_set_slab_cuts); empty: slab_range
+	std::vector<int>   cuts;
+	int                cuts_nz      = 0;
 
 	void close_shared()
 	{
@@ -241,7 +244,7 @@ struct SlabHooks final : DistHooks
 	int64_t peer_own_cells(int peer) override
 	{
 		int z0 = 0, z1 = 0;
-		slab_range(g.size[2], c->world, peer, &z0, &z1);
+		comm_slab_range(c, g.size[2], peer, &z0, &z1);
 		return static_cast<int64_t>(z1 - z0) * g.stride[2];
 	}
 
@@ -449,11 +452,11 @@ void slab_sdf_solve(fi_comm* c, const int32_t* sizes, const fi_weights& w, int64
 	const bool multigrid = o.preconditioner == FI_PRECOND_MULTIGRID;
 	SlabMgPlan plan;
 	if (multigrid) {  // the V-cycle's transfers want at least two halo planes
-		plan = plan_slab_multigrid(sizes, c->world, halo, slab_mg_gather_cells());
+		plan = plan_slab_multigrid(sizes, c->world, halo, slab_mg_gather_cells(), comm_cuts(c, sizes[2]));
 		halo = plan.halo;
 	}
 	int z0 = 0, z1 = 0;
-	slab_range(sizes[2], c->world, c->rank, &z0, &z1);
+	comm_slab_range(c, sizes[2], c->rank, &z0, &z1);
 	FI_REQUIRE(z1 - z0 >= halo, FI_ERR_INVALID, "slabs thinner than the stencil radius: use fewer ranks");
 	const Geom g = make_slab_geom(sizes, z0, z1, halo);
 
@@ -522,6 +525,85 @@ void comm_unique_id(void* id, int64_t capacity)
 }
 
 void comm_destroy(fi_comm* c) { delete c; }
+
+const int* comm_cuts(const fi_comm* c, int nz) { return (c && !c->cuts.empty() && c->cuts_nz == nz) ? c->cuts.data() : nullptr; }
+
+void comm_slab_range(const fi_comm* c, int nz, int rank, int* z0, int* z1)
+{
+	if (const int* cuts = comm_cuts(c, nz)) {
+		*z0 = cuts[rank];
+		*z1 = cuts[rank + 1];
+	} else {
+		slab_range(nz, c->world, rank, z0, z1);
+	}
+}
+
+void comm_set_cuts(fi_comm* c, int nz, const int32_t* cuts)
+{
+	FI_REQUIRE(c != nullptr, FI_ERR_INVALID, "communicator is null");
+	if (cuts == nullptr) {
+		c->cuts.clear();
+		c->cuts_nz = 0;
+		return;
+	}
+	FI_REQUIRE(nz >= c->world && cuts[0] == 0 && cuts[c->world] == nz, FI_ERR_INVALID, "slab cuts must run from 0 to nz");
+	for (int k = 0; k < c->world; ++k) { FI_REQUIRE(cuts[k + 1] > cuts[k], FI_ERR_INVALID, "slab cuts must increase: every rank owns at least one plane"); }
+	c->cuts.assign(cuts, cuts + c->world + 1);
+	c->cuts_nz = nz;
+}
+
+namespace {
+
+// points whose containing cell starts in plane z (the planes that pay for their cell block in the data-term kernels)
+__global__ void plane_histogram_kernel(int64_t n, const float* __restrict__ pos, int nz, unsigned long long* __restrict__ hist)
+{
+	const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+	for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+		const float z = floorf(pos[3 * i + 2]);
+		if (z >= 0.0f && z < static_cast<float>(nz)) { atomicAdd(&hist[static_cast<int>(z)], 1ull); }
+	}
+}
+
+}  // namespace
+
+void balanced_cuts(const int32_t* sizes, int world, int64_t num_points, const float* positions, int loc, double point_weight, int min_planes,
+                   int32_t* cuts)
+{
+	const int nz = sizes[2];
+	min_planes   = std::max(1, min_planes);
+	FI_REQUIRE(world >= 1 && nz >= world * min_planes, FI_ERR_INVALID, "balanced cuts: fewer planes than ranks x min_planes");
+	std::vector<unsigned long long> hist(nz, 0ull);
+	if (num_points > 0 && point_weight > 0) {
+		cudaStream_t                 s = nullptr;
+		DevBuf<unsigned long long>   d_hist(nz);
+		DevBuf<float>                staged;
+		const float*                 d_pos = positions;
+		d_hist.zero(s);
+		if (loc == FI_HOST) {
+			staged.resize(static_cast<size_t>(num_points) * 3);
+			FI_CUDA(cudaMemcpyAsync(staged.data(), positions, static_cast<size_t>(num_points) * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+			d_pos = staged.data();
+		}
+		const int grid = static_cast<int>(std::min<int64_t>((num_points + 255) / 256, static_cast<int64_t>(sm_count()) * 8));
+		FI_LAUNCH(plane_histogram_kernel, grid, 256, 0, s, num_points, d_pos, nz, d_hist.data());
+		FI_CUDA(cudaMemcpyAsync(hist.data(), d_hist.data(), static_cast<size_t>(nz) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+		FI_CUDA(cudaStreamSynchronize(s));
+	}
+	// prefix of the per-plane cost in units of one lattice cell's share of an iteration
+	const double        plane = static_cast<double>(sizes[0]) * sizes[1];
+	std::vector<double> cum(nz + 1, 0.0);
+	for (int z = 0; z < nz; ++z) { cum[z + 1] = cum[z] + plane + point_weight * static_cast<double>(hist[z]); }
+	cuts[0] = 0;
+	for (int k = 1; k < world; ++k) {
+		const double target = cum[nz] * k / world;
+		int z = static_cast<int>(std::lower_bound(cum.begin(), cum.end(), target) - cum.begin());
+		if (z > 0 && target - cum[z - 1] < cum[z] - target) { --z; }  // the nearer of the two plane boundaries
+		z       = std::max(z, cuts[k - 1] + min_planes);           // slabs at least min_planes thick ...
+		z       = std::min(z, nz - (world - k) * min_planes);      // ... and room for the ranks still to come
+		cuts[k] = z;
+	}
+	cuts[world] = nz;
+}
 
 fi_comm* comm_create(int rank, int world, const void* id)
 {

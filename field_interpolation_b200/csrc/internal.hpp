@@ -210,6 +210,14 @@ int stencil_partial_slots(const Geom& g);  // upper bound of blocks any stencil 
 
 // ---- dist.cu ------------------------------------------------------------------------------------------------
 void     slab_range(int nz, int world, int rank, int* z0, int* z1);
+// Planes [z0, z1) of `rank` on this communicator: its custom cuts when they were set for an nz-plane lattice, else slab_range.
+void     comm_slab_range(const fi_comm* c, int nz, int rank, int* z0, int* z1);
+const int* comm_cuts(const fi_comm* c, int nz);  // world + 1 plane numbers, or nullptr (uniform partition)
+void     comm_set_cuts(fi_comm* c, int nz, const int32_t* cuts);
+// Cuts that balance  planes * nx * ny + point_weight * (points whose cell starts in the plane)  over the ranks, every slab at
+// least min_planes thick.  Deterministic: every rank computes the same cuts from the same cloud.
+void     balanced_cuts(const int32_t* sizes, int world, int64_t num_points, const float* positions, int loc, double point_weight, int min_planes,
+                       int32_t* cuts);
 void     comm_unique_id(void* id, int64_t capacity);
 fi_comm* comm_create(int rank, int world, const void* id);
 void     comm_destroy(fi_comm* c);

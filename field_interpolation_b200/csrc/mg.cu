@@ -691,7 +691,7 @@ struct SlabMultigrid::DLevel
 SlabMultigrid::SlabMultigrid()  = default;
 SlabMultigrid::~SlabMultigrid() = default;
 
-SlabMgPlan plan_slab_multigrid(const int32_t* sizes, int world, int radius, int64_t gather_cells)
+SlabMgPlan plan_slab_multigrid(const int32_t* sizes, int world, int radius, int64_t gather_cells, const int* cuts)
 {
 	FI_REQUIRE(sizes != nullptr && world >= 1 && radius >= 1 && radius <= 4, FI_ERR_INVALID, "bad slab multigrid request");
 	SlabMgPlan plan;
@@ -702,7 +702,11 @@ SlabMgPlan plan_slab_multigrid(const int32_t* sizes, int world, int radius, int6
 	FI_REQUIRE(tma_ok(plan.size[0]), FI_ERR_UNSUPPORTED, "slab multigrid: the x size must be a multiple of 4 and >= 32, the y size >= 8");
 	plan.own[0].resize(world);
 	for (int k = 0; k < world; ++k) {
-		slab_range(sizes[2], world, k, &plan.own[0][k].first, &plan.own[0][k].second);
+		if (cuts) {
+			plan.own[0][k] = std::make_pair(cuts[k], cuts[k + 1]);
+		} else {
+			slab_range(sizes[2], world, k, &plan.own[0][k].first, &plan.own[0][k].second);
+		}
 		FI_REQUIRE(plan.own[0][k].second - plan.own[0][k].first >= plan.halo, FI_ERR_UNSUPPORTED, "slab multigrid: slabs thinner than the halo: use fewer ranks");
 	}
 	for (int l = 0;; ++l) {

@@ -235,7 +235,8 @@ struct SlabMgPlan  // pure host arithmetic, identical on every rank
 // Throws FI_ERR_UNSUPPORTED when level 0 cannot be sharded this way (slabs thinner than the halo, sizes the TMA stencil
 // kernel does not take, a restriction that would reach beyond the halo).  gather_cells: levels with at most this many
 // cells are replicated.
-SlabMgPlan plan_slab_multigrid(const int32_t* sizes, int world, int radius, int64_t gather_cells);
+// cuts (nullable): world + 1 plane numbers of a non-uniform level-0 partition (fi_comm_set_slab_cuts); else slab_range.
+SlabMgPlan plan_slab_multigrid(const int32_t* sizes, int world, int radius, int64_t gather_cells, const int* cuts = nullptr);
 
 struct SlabMultigrid
 {

@@ -21,6 +21,17 @@ def slab_range(nz: int, world: int, rank: int):
     return int(z0.value), int(z1.value)
 
 
+def balanced_cuts(sizes, world: int, positions, point_weight: float = 0.0, min_planes: int = 4):
+    """fi_slab_balanced_cuts: world + 1 plane numbers that balance lattice planes plus data points over the ranks
+    (positions: lattice coordinates, numpy or CUDA tensor).  The same on every rank for the same cloud."""
+    p = _Buf(positions)
+    n = (p.keep.numel() if p.loc == L.FI_DEVICE else p.keep.size) // 3 if p.keep is not None else 0
+    sz = (C.c_int32 * 3)(*[int(v) for v in sizes])
+    cuts = (C.c_int32 * (int(world) + 1))()
+    L.check(L.lib().fi_slab_balanced_cuts(sz, int(world), n, p.ptr, p.loc if p.loc is not None else L.FI_HOST, float(point_weight), int(min_planes), cuts))
+    return [int(v) for v in cuts]
+
+
 def slab_mg_plan(sizes, world: int, stencil_radius: int = 2, gather_cells: int = 0):
     """How a multigrid-preconditioned slab solve shards its V-cycle (fi_slab_mg_plan, host only): a dict with
     `halo`, `sharded_levels`, `sizes[l]` and `own[l][rank] = (z0, z1)` for l = 0 .. sharded_levels (the last level
@@ -57,6 +68,11 @@ class SlabComm:
         L.check(L.lib().fi_comm_create(self.rank, self.world, idbuf, C.byref(h)))
         self._h = h
 
+    def set_cuts(self, nz: int, cuts=None):
+        """fi_comm_set_slab_cuts: a non-uniform partition for later solves on nz-plane lattices (None: uniform again)."""
+        arr = None if cuts is None else (C.c_int32 * (self.world + 1))(*[int(v) for v in cuts])
+        L.check(L.lib().fi_comm_set_slab_cuts(self._h, int(nz), arr))
+
     def close(self):
         if getattr(self, "_h", None):
             L.lib().fi_comm_destroy(self._h)
@@ -72,14 +88,20 @@ class SlabComm:
 class SlabRunner:
     """sdf_from_points + PCG with the lattice sharded over the ranks of a torch.distributed group."""
 
-    def __init__(self, sizes, weights: Weights, rank: int, world: int, dist):
+    def __init__(self, sizes, weights: Weights, rank: int, world: int, dist, cuts=None):
         import torch
         assert len(sizes) == 3, "slab sharding is for 3D lattices"
         self.sizes, self.weights, self.rank, self.world = [int(s) for s in sizes], weights, rank, world
-        self.z0, self.z1 = slab_range(self.sizes[2], world, rank)
-        self.local_cells = (self.z1 - self.z0) * self.sizes[0] * self.sizes[1]
         dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else None
         self.comm = SlabComm(rank, world, broadcast_unique_id(dist, rank, dev))
+        self.set_cuts(cuts)
+
+    def set_cuts(self, cuts=None):
+        """cuts: world + 1 plane numbers (balanced_cuts) or None for the uniform partition; fixes this rank's planes."""
+        self.comm.set_cuts(self.sizes[2], cuts)
+        self.cuts = None if cuts is None else [int(v) for v in cuts]
+        self.z0, self.z1 = (self.cuts[self.rank], self.cuts[self.rank + 1]) if cuts is not None else slab_range(self.sizes[2], self.world, self.rank)
+        self.local_cells = (self.z1 - self.z0) * self.sizes[0] * self.sizes[1]
 
     def step(self, positions, normals, options=None, out=None, guess=None, point_weights=None):
         """Every rank passes the whole cloud (lattice coordinates); returns this rank's solve stats, `out` holds

@@ -248,6 +248,17 @@ FI_API int fi_comm_create(int32_t rank, int32_t world, const void* id, fi_comm**
 FI_API int fi_comm_destroy(fi_comm* c);
 /* Planes [z0, z1) of an nz-plane lattice owned by `rank` (contiguous, balanced to one plane).  Pure host code. */
 FI_API int fi_slab_range(int32_t nz, int32_t world, int32_t rank, int32_t* z0, int32_t* z1);
+/* A non-uniform partition for this communicator: cuts[0] = 0 < cuts[1] < ... < cuts[world] = nz, rank k owns planes
+ * [cuts[k], cuts[k+1]) of every later fi_slab_sdf_solve on an nz-plane lattice (collective in effect: every rank must set
+ * the same cuts).  cuts = null: back to fi_slab_range.  The data term makes slabs unequal in cost — the occupied cells of an
+ * SDF cloud cluster in a few slabs, and the slowest rank sets the pace of every iteration — so fi_slab_balanced_cuts
+ * balances  planes * nx * ny + point_weight * (points whose cell starts in the plane)  instead of the plane count:
+ * point_weight = the cost of one data point in units of one lattice cell of an iteration (<= 0: 9, measured on B200:
+ * profiles/r1c_trace_n8_before.txt), min_planes = thinnest slab allowed (>= the stencil radius; 2 x radius for multigrid).
+ * Pure function of its arguments (one histogram kernel over the points): every rank computes the same cuts. */
+FI_API int fi_slab_balanced_cuts(const int32_t* sizes /* 3 */, int32_t world, int64_t num_points, const float* positions, int32_t loc,
+                          double point_weight, int32_t min_planes, int32_t* cuts /* world + 1 */);
+FI_API int fi_comm_set_slab_cuts(fi_comm* c, int32_t nz, const int32_t* cuts /* world + 1, or null */);
 /* How a FI_PRECOND_MULTIGRID slab solve shards its V-cycle over `world` ranks (pure host code, the same on every
  * rank): levels 0 .. *sharded_levels - 1 are z-slab sharded, level *sharded_levels and everything below it is
  * replicated (its restricted residual is all-gathered).  stencil_radius = highest active model order (1..4);
@@ -258,7 +269,8 @@ FI_API int fi_slab_range(int32_t nz, int32_t world, int32_t rank, int32_t* z0, i
 FI_API int fi_slab_mg_plan(const int32_t* sizes /* 3 */, int32_t world, int32_t stencil_radius, int64_t gather_cells, int32_t* sharded_levels,
                     int32_t* halo, int32_t* level_sizes, int32_t* plane_ranges);
 /* sdf_from_points + PCG on the slab of this rank: every rank passes the whole point cloud (positions in lattice
- * coordinates of the full lattice) and receives its owned planes, (z1 - z0) * nx * ny floats, in solution_own.
+ * coordinates of the full lattice) and receives its owned planes ([z0, z1) of fi_slab_range, or of the cuts set with
+ * fi_comm_set_slab_cuts), (z1 - z0) * nx * ny floats, in solution_own.
  * Collective: all ranks of the communicator call it together with the same arguments except the buffers.
  * guess_own (nullable) is this rank's part of the starting guess.  FI_F32 or FI_F64; star-shaped smoothness
  * (gradient_smoothness = 0), nearest / cell-edge gradient kernels.  opt->preconditioner = FI_PRECOND_MULTIGRID runs

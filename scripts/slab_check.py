@@ -29,15 +29,17 @@ for sizes, npts, orders in PCG_CASES:
     cloud = W.sphere_torus_3d(npts, seed=1)
     pos = W.to_lattice(cloud["unit_pos"], sizes)
     weights = fi.Weights(**orders)
-    runner = fid.SlabRunner(sizes, weights, rank, world, dist)
     d_pos, d_nrm = torch.from_numpy(pos).cuda(), torch.from_numpy(cloud["normals"]).cuda()
+    # the largest case also runs on the cost-balanced partition (fi_slab_balanced_cuts); its gather below uses the cuts
+    cuts = fid.balanced_cuts(sizes, world, d_pos, 0.0, 4) if sizes[2] >= 256 and "--uniform" not in sys.argv else None
+    runner = fid.SlabRunner(sizes, weights, rank, world, dist, cuts=cuts)
+    own = (lambda r: (cuts[r], cuts[r + 1])) if cuts else (lambda r: fid.slab_range(sizes[2], world, r))
     for prec, name, tol in ((fi.FI_F32, "f32", 2e-4), (fi.FI_F64, "f64", 1e-10)):
         for its in (1, 2, 25):
             opt = fi.solve_options(prec, its, 1e-30, check_every=8)
             out = torch.zeros(runner.local_cells, device="cuda")
             st = runner.step(d_pos, d_nrm, opt, out)
-            parts = [torch.zeros(fid.slab_range(sizes[2], world, r)[1] * sizes[0] * sizes[1] - fid.slab_range(sizes[2], world, r)[0] * sizes[0] * sizes[1],
-                                 device="cuda") for r in range(world)]
+            parts = [torch.zeros((own(r)[1] - own(r)[0]) * sizes[0] * sizes[1], device="cuda") for r in range(world)]
             dist.all_gather(parts, out)
             full = torch.cat(parts).cpu().numpy()
             if rank == 0:
@@ -47,7 +49,7 @@ for sizes, npts, orders in PCG_CASES:
                 err = float(np.linalg.norm(full - ref) / max(np.linalg.norm(ref), 1e-300))
                 good = err <= tol and st["iterations"] == st1["iterations"] == its and abs(st["relative_residual"] - st1["relative_residual"]) <= 1e-3 * st1["relative_residual"] + 1e-12
                 ok = ok and good
-                print(json.dumps({"sizes": sizes, "prec": name, "its": its, "rel_diff_vs_single": err, "relres_slab": st["relative_residual"],
+                print(json.dumps({"sizes": sizes, "cuts": cuts, "prec": name, "its": its, "rel_diff_vs_single": err, "relres_slab": st["relative_residual"],
                                   "relres_single": st1["relative_residual"], "true_slab": st["true_residual"], "true_single": st1["true_residual"], "ok": bool(good)}), flush=True)
                 f.close()
     runner.close()

@@ -56,8 +56,10 @@ def main():
     weights = fi.Weights(**case.get("weights", {}))
     runner = fid.SlabRunner.__new__(fid.SlabRunner)
     runner.sizes, runner.weights, runner.rank, runner.world, runner.comm = sizes, weights, rank, world, comm
-    runner.z0, runner.z1 = fid.slab_range(sizes[2], world, rank)
-    runner.local_cells = (runner.z1 - runner.z0) * sizes[0] * sizes[1]
+    cuts = case.get("cuts")  # None: uniform; "balanced": fi_slab_balanced_cuts of the cloud; else world + 1 plane numbers
+    if cuts == "balanced":
+        cuts = fid.balanced_cuts(sizes, world, pos, case.get("point_weight", 0.0), case.get("min_planes", 4))
+    runner.set_cuts(cuts)
     results = {}
     for name, o in case["solves"].items():
         opt = fi.solve_options(fi.FI_F64 if o["precision"] == "f64" else fi.FI_F32, o["max_iterations"], o["tolerance"],
@@ -66,6 +68,7 @@ def main():
         st = runner.step(pos, cloud["normals"], opt, out)
         np.save(os.path.join(work, f"{name}_rank{rank}.npy"), out)
         results[name] = st
+    results["cuts"] = runner.cuts
     with open(os.path.join(work, f"stats_rank{rank}.json"), "w") as f:
         json.dump(results, f)
     runner.close()

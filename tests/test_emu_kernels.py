@@ -96,6 +96,8 @@ def _run_ranks(world, case, gather=None, p2p=False):
                     p.kill()
         assert [p.returncode for p in procs] == [0] * world, "\n".join(e[-800:] for e in errs)
         stats = json.load(open(os.path.join(work, "stats_rank0.json")))
+        for r in range(1, world):  # every rank computed the same partition
+            assert json.load(open(os.path.join(work, f"stats_rank{r}.json")))["cuts"] == stats["cuts"]
         fields = {k: np.concatenate([np.load(os.path.join(work, f"{k}_rank{r}.npy")) for r in range(world)]) for k in case["solves"]}
     return fields, stats
 
@@ -174,3 +176,25 @@ def test_cpp_drop_in_callers_pass_on_the_emulator(tmp_path):
                        env=env, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
     assert " passed" in r.stdout and " failed" not in r.stdout
+
+
+def test_slab_custom_and_balanced_cuts_match_one_rank():
+    """fi_comm_set_slab_cuts / fi_slab_balanced_cuts: a deliberately lopsided partition and the cost-balanced one (point
+    weight exaggerated so that it differs visibly from the uniform cuts) give the same iterates and fields as one rank,
+    over NCCL, over peer memory, and through the sharded multigrid."""
+    solves = dict(SLAB_SOLVES)
+    case = {"sizes": [32, 16, 40], "points": 3000, "seed": 5, "weights": {}, "solves": solves}
+    base, st1 = _run_ranks(1, case)
+    for cuts, p2p in (([0, 6, 29, 40], False), ([0, 6, 29, 40], True), ("balanced", True)):
+        c = dict(case, cuts=cuts, point_weight=60.0, min_planes=4)
+        out, st = _run_ranks(3, c, p2p=p2p)
+        if cuts == "balanced":
+            got = st["cuts"]
+            assert got[0] == 0 and got[-1] == 40 and all(b - a >= 4 for a, b in zip(got, got[1:])) and got != [0, 13, 26, 40]
+            assert got[2] - got[1] < 13  # the middle slab holds most of the cloud: it gets fewer planes
+        else:
+            assert st["cuts"] == cuts
+        assert np.linalg.norm(out["pcg64"] - base["pcg64"]) <= 1e-7 * np.linalg.norm(base["pcg64"])
+        assert np.linalg.norm(out["pcg32"] - base["pcg32"]) <= 2e-4 * np.linalg.norm(base["pcg32"])
+        assert st["mg64"]["converged"] and abs(st["mg64"]["iterations"] - st1["mg64"]["iterations"]) <= 1
+        assert np.linalg.norm(out["mg64"] - base["mg64"]) <= 1e-6 * np.linalg.norm(base["mg64"])
