@@ -13,3 +13,12 @@ timeout 200 python bench.py --impl reference > gpurun_out/bench11_reference.json
 timeout 240 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches11.csv \
     python bench.py --steps 1 --warmup 3 --iters 20 --no-cpu-baseline --no-time-to-tol > gpurun_out/bench11_under_ncu.log 2>&1
 python scripts/ncu_summary.py launches gpurun_out/launches11.csv > gpurun_out/launches11.md 2>&1; head -30 gpurun_out/launches11.md
+# full captures (one launch of each distinct kernel): the multigrid V-cycle (TMA epilogue smoother, transfers) — the
+# iteration runs at ~54 % of the HBM roofline by byte count, and nothing in profiles/ says why yet —
+# and the assembly kernels (sort, scatter), which have launch-list times but no counters
+timeout 300 ncu --set full --clock-control none --import-source on --profile-from-start off -o gpurun_out/mg11 \
+    python scripts/profile_mg.py 512 1 > gpurun_out/mg11_ncu.log 2>&1
+python scripts/ncu_summary.py full gpurun_out/mg11.ncu-rep > gpurun_out/mg11_full.md 2>&1; grep -c "^###" gpurun_out/mg11_full.md
+timeout 300 ncu --set full --clock-control none --import-source on -k "regex:scatter|radix|scan|cell_keys|canonicalise|mark_heads|slots" -c 40 -o gpurun_out/asm11 \
+    python scripts/profile_step.py 512 2 > gpurun_out/asm11_ncu.log 2>&1
+python scripts/ncu_summary.py full gpurun_out/asm11.ncu-rep > gpurun_out/asm11_full.md 2>&1; grep -c "^###" gpurun_out/asm11_full.md
