@@ -25,7 +25,8 @@
 extern "C" {
 #endif
 
-#define FI_B200_ABI_VERSION 1
+/* 2: + fi_marching_squares, fi_calc_area, fi_bicubic_upsample, fi_slab_balanced_cuts, fi_comm_set_slab_cuts (additions only) */
+#define FI_B200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define FI_API __attribute__((visibility("default")))
