@@ -61,11 +61,18 @@ def main():
         cuts = fid.balanced_cuts(sizes, world, pos, case.get("point_weight", 0.0), case.get("min_planes", 4))
     runner.set_cuts(cuts)
     results = {}
+    normals = cloud["normals"] if case.get("normals", True) else None
+    pw = np.random.default_rng(7).uniform(0.0, 2.0, len(pos)).astype(np.float32) if case.get("point_weights") else None
+    nxy = sizes[0] * sizes[1]
     for name, o in case["solves"].items():
         opt = fi.solve_options(fi.FI_F64 if o["precision"] == "f64" else fi.FI_F32, o["max_iterations"], o["tolerance"],
                                preconditioner=fi.FI_PRECOND_MULTIGRID if o.get("multigrid") else fi.FI_PRECOND_JACOBI)
         out = np.zeros(runner.local_cells, np.float32)
-        st = runner.step(pos, cloud["normals"], opt, out)
+        guess = None
+        if o.get("guess"):  # this rank's planes of a smooth global guess
+            zz, yy, xx = np.meshgrid(np.arange(runner.z0, runner.z1), np.arange(sizes[1]), np.arange(sizes[0]), indexing="ij")
+            guess = (0.1 * np.sin(0.3 * xx) + 0.05 * yy - 0.02 * zz).astype(np.float32).ravel()
+        st = runner.step(pos, normals, opt, out, guess=guess, point_weights=pw)
         np.save(os.path.join(work, f"{name}_rank{rank}.npy"), out)
         results[name] = st
     results["cuts"] = runner.cuts

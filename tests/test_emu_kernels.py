@@ -134,14 +134,17 @@ def test_slab_peer_memory_path_matches_one_rank():
     same iteration count to a tolerance (the device-side stop and the leftover replays of a finished solve included)."""
     solves = {"pcg64": {"precision": "f64", "max_iterations": 12, "tolerance": 1e-30},
               "pcg32": {"precision": "f32", "max_iterations": 12, "tolerance": 1e-30},
-              "conv64": {"precision": "f64", "max_iterations": 2000, "tolerance": 1e-3}}
-    case = {"sizes": [32, 16, 24], "points": 2500, "seed": 5, "weights": {}, "solves": solves}
+              "conv64": {"precision": "f64", "max_iterations": 2000, "tolerance": 1e-3},
+              "guess64": {"precision": "f64", "max_iterations": 12, "tolerance": 1e-30, "guess": True}}  # each rank passes its planes of a guess
+    case = {"sizes": [32, 16, 24], "points": 2500, "seed": 5, "weights": {}, "point_weights": True, "solves": solves}
     base, st1 = _run_ranks(1, case)
     assert st1["conv64"]["converged"]
     for world in (2, 3):
         out, st = _run_ranks(world, case, p2p=True)
         assert st["pcg64"]["iterations"] == st["pcg32"]["iterations"] == 12
         assert np.linalg.norm(out["pcg64"] - base["pcg64"]) <= 1e-7 * np.linalg.norm(base["pcg64"])
+        assert np.linalg.norm(out["guess64"] - base["guess64"]) <= 1e-7 * np.linalg.norm(base["guess64"])
+        assert np.linalg.norm(out["guess64"] - base["pcg64"]) > 1e-3 * np.linalg.norm(base["pcg64"])  # the guess did enter
         assert np.linalg.norm(out["pcg32"] - base["pcg32"]) <= 2e-4 * np.linalg.norm(base["pcg32"])
         assert st["conv64"]["converged"] and abs(st["conv64"]["iterations"] - st1["conv64"]["iterations"]) <= 2
         assert np.linalg.norm(out["conv64"] - base["conv64"]) <= 1e-4 * np.linalg.norm(base["conv64"])
