@@ -352,8 +352,35 @@ static void unlink_all_mappings()
 	}
 }
 
+// CUDA_EMU_GUARD=1: every allocation ends (to 16 bytes) at an inaccessible page and starts after one, so a kernel that
+// indexes outside its buffer faults at the offending access — the emulator's stand-in for compute-sanitizer memcheck.
+static bool guard_enabled()
+{
+	static const bool on = std::getenv("CUDA_EMU_GUARD") != nullptr;
+	return on;
+}
+struct Guarded
+{
+	void*  map;
+	size_t map_bytes;
+};
+static std::map<void*, Guarded> g_guarded;
+
 cudaError_t cudaMalloc(void** p, size_t n)
 {
+	if (guard_enabled() && !ipc_enabled()) {
+		const size_t page = 4096, body = ((std::max<size_t>(n, 1) + 15) & ~size_t{15});
+		const size_t inner = (body + page - 1) & ~(page - 1), total = inner + 2 * page;
+		char* m = static_cast<char*>(mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0));
+		if (m == MAP_FAILED) { return cudaErrorMemoryAllocation; }
+		mprotect(m, page, PROT_NONE);
+		mprotect(m + page + inner, page, PROT_NONE);
+		char* user = m + page + inner - body;  // the buffer's end touches the trailing guard page
+		std::memset(m + page, 0xCB, inner - body);  // slack before the buffer: poison (reads of it yield garbage, not zeros)
+		g_guarded[user] = Guarded{m, total};
+		*p = user;
+		return cudaSuccess;
+	}
 	if (!ipc_enabled()) {
 		*p = std::malloc(n ? n : 1);
 		return *p ? cudaSuccess : cudaErrorMemoryAllocation;
@@ -378,6 +405,12 @@ cudaError_t cudaMalloc(void** p, size_t n)
 }
 cudaError_t cudaFree(void* p)
 {
+	auto gi = g_guarded.find(p);
+	if (gi != g_guarded.end()) {
+		munmap(gi->second.map, gi->second.map_bytes);
+		g_guarded.erase(gi);
+		return cudaSuccess;
+	}
 	auto it = g_mappings.find(p);
 	if (it == g_mappings.end()) {
 		std::free(p);
