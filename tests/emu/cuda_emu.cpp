@@ -377,6 +377,7 @@ cudaError_t cudaMalloc(void** p, size_t n)
 		mprotect(m + page + inner, page, PROT_NONE);
 		char* user = m + page + inner - body;  // the buffer's end touches the trailing guard page
 		std::memset(m + page, 0xCB, inner - body);  // slack before the buffer: poison (reads of it yield garbage, not zeros)
+		std::memset(user, 0xFF, body);              // fresh device memory is not zero: NaN for floats, -1 for integers
 		g_guarded[user] = Guarded{m, total};
 		*p = user;
 		return cudaSuccess;
@@ -399,6 +400,7 @@ cudaError_t cudaMalloc(void** p, size_t n)
 	void* q = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
 	close(fd);
 	if (q == MAP_FAILED) { return cudaErrorMemoryAllocation; }
+	if (guard_enabled()) { std::memset(q, 0xFF, bytes); }  // fresh device memory is not zero
 	g_mappings[q] = Mapping{name, bytes};
 	*p            = q;
 	return cudaSuccess;
