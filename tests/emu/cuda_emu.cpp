@@ -139,9 +139,23 @@ void run_block(dim3 block)
 		for (int r = 0; r < 6; ++r) { *--sp = nullptr; }
 		f.sp = sp;
 	}
+	// CUDA_EMU_SCHED=reverse|shuffle: the order in which runnable threads of a block are resumed.  Results that change with
+	// it point at a race or a missing barrier (the hardware promises no order between warps).
+	static const char* sched_env = std::getenv("CUDA_EMU_SCHED");
+	static const int   sched     = !sched_env ? 0 : (std::strcmp(sched_env, "reverse") == 0 ? 1 : 2);
+	static unsigned    lcg       = 12345u;
+	std::vector<int>   order(n);
+	for (int i = 0; i < n; ++i) { order[i] = sched == 1 ? n - 1 - i : i; }
 	while (g_alive > 0) {
 		bool ran = false;
-		for (int i = 0; i < n; ++i) {
+		if (sched == 2) {
+			for (int i = n - 1; i > 0; --i) {
+				lcg = lcg * 1664525u + 1013904223u;
+				std::swap(order[i], order[(lcg >> 8) % (i + 1)]);
+			}
+		}
+		for (int oi = 0; oi < n; ++oi) {
+			const int i = order[oi];
 			Fiber& f = g_fibers[i];
 			if (f.state != kRunnable) { continue; }
 			ran         = true;
