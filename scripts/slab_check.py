@@ -23,8 +23,11 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ok = True
+QUICK = "--quick" in sys.argv  # the small cases only (tests/test_gpu_zz_multi_gpu.py)
 PCG_CASES = () if "--mg-only" in sys.argv else (([64, 48, 40], 4000, {}), ([128, 64, 37], 20000, dict(model_1=0.3)), ([96, 40, 64], 8000, dict(model_2=0.0, model_4=0.2)),
                             ([256, 256, 256], 1000000, {}))
+if QUICK:
+    PCG_CASES = PCG_CASES[:3]
 for sizes, npts, orders in PCG_CASES:
     cloud = W.sphere_torus_3d(npts, seed=1)
     pos = W.to_lattice(cloud["unit_pos"], sizes)
@@ -62,8 +65,9 @@ def gather_own(out, sizes):
     return torch.cat(parts).cpu().numpy()
 
 
-for sizes, npts, orders, gather in (([64, 48, 40], 5000, {}, 1000), ([128, 64, 72], 20000, dict(model_1=0.2), 0), ([128, 128, 128], 200000, {}, 100000),
-                                    ([256, 256, 256], 1000000, {}, 0), ([256, 256, 256], 1000000, {}, 300000)):
+MG_CASES = (([64, 48, 40], 5000, {}, 1000), ([128, 64, 72], 20000, dict(model_1=0.2), 0), ([128, 128, 128], 200000, {}, 100000),
+            ([256, 256, 256], 1000000, {}, 0), ([256, 256, 256], 1000000, {}, 300000))
+for sizes, npts, orders, gather in (MG_CASES[:2] if QUICK else MG_CASES):
     if gather:
         os.environ["FI_B200_MG_GATHER_CELLS"] = str(gather)
     else:
