@@ -34,7 +34,7 @@ for sizes, npts, orders in PCG_CASES:
     weights = fi.Weights(**orders)
     d_pos, d_nrm = torch.from_numpy(pos).cuda(), torch.from_numpy(cloud["normals"]).cuda()
     # the largest case also runs on the cost-balanced partition (fi_slab_balanced_cuts); its gather below uses the cuts
-    cuts = fid.balanced_cuts(sizes, world, d_pos, 0.0, 4) if sizes[2] >= 256 and "--uniform" not in sys.argv else None
+    cuts = fid.balanced_cuts(sizes, world, d_pos, 60.0 if QUICK else 0.0, 4) if (sizes[2] >= 256 or (QUICK and sizes[2] == 40)) and "--uniform" not in sys.argv else None
     runner = fid.SlabRunner(sizes, weights, rank, world, dist, cuts=cuts)
     own = (lambda r: (cuts[r], cuts[r + 1])) if cuts else (lambda r: fid.slab_range(sizes[2], world, r))
     for prec, name, tol in ((fi.FI_F32, "f32", 2e-4), (fi.FI_F64, "f64", 1e-10)):
