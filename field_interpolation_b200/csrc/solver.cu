@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace fi {
 
@@ -328,13 +329,20 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads) pcg_update_peer_kernel(int64_t n, T* __restrict__ x, T* __restrict__ r,
                                                                    const T* __restrict__ p, const T* __restrict__ q,
                                                                    const T* __restrict__ minv, PcgState* st, int par, double* partial,
-                                                                   unsigned* ticket, PeerLink L, HaloPush<T> push, unsigned long long base)
+                                                                   unsigned* ticket, PeerLink L, HaloPush<T> push, unsigned long long base, int fold)
 {
 	__shared__ double red[32];
 	__shared__ double s_pq, s_tot[2];
 	__shared__ int    s_ok, s_pub;
 	const bool was_done = st->done != 0;
 	const unsigned long long seq_pq = seq_of(base, st, 0), seq_rr = seq_of(base, st, 1);
+	// fold (FI_B200_PEER_FOLD=1): this kernel also does the work of peer_publish_kernel (block 0, before anybody waits) and
+	// of pcg_update_finish_peer_kernel (the last block, after it has published) — two kernel boundaries fewer per iteration
+	if (fold && blockIdx.x == 0 && threadIdx.x < 32) {
+		double mine[1] = {was_done ? 0.0 : st->pq};  // a finished solve still publishes: the peers' kernels are waiting
+		if (threadIdx.x == 0 && !was_done) { L.local->stamp[0][st->iters & 511] = global_ns(); }
+		peer_publish_warp(L, 0, par, seq_pq, mine, 1);
+	}
 	if (threadIdx.x < 32) {
 		double     pq = 0.0;
 		const bool ok = peer_collect_warp(L, 0, par, seq_pq, &pq, 1);
@@ -406,6 +414,22 @@ __global__ void __launch_bounds__(kThreads) pcg_update_peer_kernel(int64_t n, T*
 	if (s_pub && threadIdx.x < 32) {
 		const double tot[2] = {s_tot[0], s_tot[1]};
 		peer_publish_warp(L, 1, par, seq_rr, tot, 2);
+		if (fold) {  // every other block of this kernel has finished: end the iteration here (pcg_update_finish_peer_kernel)
+			double     all[2];
+			const bool ok = peer_collect_warp(L, 1, par, seq_rr, all, 2);
+			if (threadIdx.x == 0 && !st->done) {
+				if (!ok) {
+					st->breakdown = 2;
+					st->done      = 1;
+				} else {
+					L.local->stamp[2][st->iters & 511] = global_ns();
+					st->rho[par ^ 1] = all[0];
+					st->rr           = all[1];
+					st->iters += 1;
+					if (all[1] <= st->tol2bb || st->iters >= st->max_iters || !(all[0] > 0.0)) { st->done = 1; }
+				}
+			}
+		}
 	}
 }
 
@@ -639,6 +663,9 @@ PcgResult pcg_solve(Operator<T>& op, const T* b, T* x, double tol, long long max
 		T*   pp[2] = {w.p.data(), w.p2.data()};
 		// every solve gets its own block of mailbox sequence numbers (all ranks count solves alike)
 		const unsigned long long seq_base = link ? (dist->next_seq() << 40) : 0ull;
+		// opt-in until measured on the GPUs: publish / finish folded into the update kernel (same on every rank: environment)
+		const char* fold_env  = std::getenv("FI_B200_PEER_FOLD");
+		const bool  peer_fold = link && fold_env && *fold_env == '1';
 		auto enqueue_round = [&] {
 			for (int it = 0; it < check_every; ++it) {
 				const int par = it & 1;
@@ -648,11 +675,11 @@ PcgResult pcg_solve(Operator<T>& op, const T* b, T* x, double tol, long long max
 				if (fused && link) {
 					// peer-memory path: no NCCL inside the iteration
 					apply_data_term<T>(op.g, op.data, pp[par ^ 1], w.q.data(), d_pq, d_done, s);
-					FI_LAUNCH(peer_publish_kernel, 1, 32, 0, s, *link, 0, par, seq_base, w.state.data(), d_pq, 1, d_done);
+					if (!peer_fold) { FI_LAUNCH(peer_publish_kernel, 1, 32, 0, s, *link, 0, par, seq_base, w.state.data(), d_pq, 1, d_done); }
 					auto ku = pcg_update_peer_kernel<T>;
 					FI_LAUNCH(ku, grid, kThreads, 0, s, n, x + off, r_vec + off, pp[par ^ 1] + off, w.q.data() + off, op.minv.data() + off,
-					          w.state.data(), par, w.partial.data(), w.ticket.data(), *link, push, seq_base);
-					FI_LAUNCH(pcg_update_finish_peer_kernel, 1, 32, 0, s, w.state.data(), par, *link, seq_base);
+					          w.state.data(), par, w.partial.data(), w.ticket.data(), *link, push, seq_base, peer_fold ? 1 : 0);
+					if (!peer_fold) { FI_LAUNCH(pcg_update_finish_peer_kernel, 1, 32, 0, s, w.state.data(), par, *link, seq_base); }
 				} else if (fused) {
 					apply_data_term<T>(op.g, op.data, pp[par ^ 1], w.q.data(), d_pq, d_done, s);
 					if (dist) { dist->allreduce(d_pq, 1, s); }

@@ -11,3 +11,9 @@ timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --mas
 grep -v "^\[fi" gpurun_out/slab_check12_n$N.jsonl | tail -30
 FI_B200_TRACE=1 timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N \
     > gpurun_out/bench12_n$N.json 2> gpurun_out/bench12_n$N.err; tail -c 2500 gpurun_out/bench12_n$N.json; grep "per-iteration us" gpurun_out/bench12_n$N.err | tail -8
+# the same bench with publish / finish folded into the update kernel (opt-in; emulator-validated): two kernels fewer per iteration
+FI_B200_PEER_FOLD=1 FI_B200_TRACE=1 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $N --no-time-to-tol \
+    > gpurun_out/bench12_fold_n$N.json 2> gpurun_out/bench12_fold_n$N.err; tail -c 1200 gpurun_out/bench12_fold_n$N.json; grep "per-iteration us" gpurun_out/bench12_fold_n$N.err | tail -8
+# and on the uniform partition, to separate the two effects
+FI_B200_BENCH_UNIFORM=1 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus $N --no-time-to-tol \
+    > gpurun_out/bench12_uniform_n$N.json 2> gpurun_out/bench12_uniform_n$N.err; tail -c 1200 gpurun_out/bench12_uniform_n$N.json

@@ -281,7 +281,7 @@ namespace {
 
 void launch(const char* name, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, std::function<void()> body)
 {
-	static const bool trace = std::getenv("CUDA_EMU_TRACE") != nullptr;
+	static const bool trace = std::getenv("CUDA_EMU_TRACE") != nullptr && *std::getenv("CUDA_EMU_TRACE") != '\0';
 	auto run = [name, grid, block, smem, body]() {
 		if (trace) { std::fprintf(stderr, "cuda_emu: %s <<<(%u,%u,%u),(%u,%u,%u),%zu>>>\n", name, grid.x, grid.y, grid.z, block.x, block.y, block.z, smem); }
 		if (g_dyn_smem.size() < smem + 256) { g_dyn_smem.resize(smem + 256); }
@@ -356,7 +356,7 @@ struct Mapping
 static std::map<void*, Mapping> g_mappings;
 static bool ipc_enabled()
 {
-	static const bool on = std::getenv("CUDA_EMU_IPC") != nullptr;
+	static const bool on = std::getenv("CUDA_EMU_IPC") != nullptr && *std::getenv("CUDA_EMU_IPC") != '\0';
 	return on;
 }
 static void unlink_all_mappings()
@@ -370,7 +370,7 @@ static void unlink_all_mappings()
 // indexes outside its buffer faults at the offending access — the emulator's stand-in for compute-sanitizer memcheck.
 static bool guard_enabled()
 {
-	static const bool on = std::getenv("CUDA_EMU_GUARD") != nullptr;
+	static const bool on = std::getenv("CUDA_EMU_GUARD") != nullptr && *std::getenv("CUDA_EMU_GUARD") != '\0';
 	return on;
 }
 struct Guarded

@@ -71,7 +71,7 @@ def test_assembly_and_solves_small_3d(emu, port):
 
 
 # ---- world_size > 1: the z-slab sharded solves over the fake NCCL (processes + shared memory) ---------------------------
-def _run_ranks(world, case, gather=None, p2p=False):
+def _run_ranks(world, case, gather=None, p2p=False, extra_env=None):
     sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
     import build_emu
     build_emu.build()
@@ -84,16 +84,24 @@ def _run_ranks(world, case, gather=None, p2p=False):
             env.pop("FI_B200_P2P", None)
         else:    # ncclSend / ncclRecv + ncclAllReduce inside the iteration
             env["FI_B200_P2P"] = "0"
+        env.pop("FI_B200_PEER_FOLD", None)
+        env.update(extra_env or {})
         if gather:
             env["FI_B200_MG_GATHER_CELLS"] = str(gather)
+        # stderr goes to files: a rank blocked on a full pipe would stall its peers in the next collective
+        logs = [open(os.path.join(work, f"stderr_rank{r}.log"), "w") for r in range(world)]
         procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "emu", "slab_rank.py"), str(r), str(world), work, json.dumps(case)],
-                                  env=env, stderr=subprocess.PIPE, text=True) for r in range(world)]
+                                  env=env, stderr=logs[r]) for r in range(world)]
         try:
-            errs = [p.communicate(timeout=600)[1] for p in procs]
+            for p in procs:
+                p.wait(timeout=600)
         finally:
             for p in procs:
                 if p.poll() is None:
                     p.kill()
+            for f in logs:
+                f.close()
+        errs = [open(os.path.join(work, f"stderr_rank{r}.log")).read() for r in range(world)]
         assert [p.returncode for p in procs] == [0] * world, "\n".join(e[-800:] for e in errs)
         stats = json.load(open(os.path.join(work, "stats_rank0.json")))
         for r in range(1, world):  # every rank computed the same partition
@@ -201,3 +209,17 @@ def test_slab_custom_and_balanced_cuts_match_one_rank():
         assert np.linalg.norm(out["pcg32"] - base["pcg32"]) <= 2e-4 * np.linalg.norm(base["pcg32"])
         assert st["mg64"]["converged"] and abs(st["mg64"]["iterations"] - st1["mg64"]["iterations"]) <= 1
         assert np.linalg.norm(out["mg64"] - base["mg64"]) <= 1e-6 * np.linalg.norm(base["mg64"])
+
+
+def test_slab_peer_fold_mode_matches_one_rank():
+    """FI_B200_PEER_FOLD=1 (opt-in until measured on GPUs): p.Ap is published by block 0 of the update kernel and the
+    iteration is finished by its last block — two kernels fewer per iteration.  Same iterates, same stop."""
+    solves = {"pcg64": {"precision": "f64", "max_iterations": 12, "tolerance": 1e-30},
+              "conv64": {"precision": "f64", "max_iterations": 2000, "tolerance": 1e-3}}
+    case = {"sizes": [32, 16, 24], "points": 2500, "seed": 5, "weights": {}, "solves": solves}
+    base, st1 = _run_ranks(1, case)
+    for world in (2, 3):
+        out, st = _run_ranks(world, case, p2p=True, extra_env={"FI_B200_PEER_FOLD": "1"})
+        assert st["pcg64"]["iterations"] == 12 and np.linalg.norm(out["pcg64"] - base["pcg64"]) <= 1e-7 * np.linalg.norm(base["pcg64"])
+        assert st["conv64"]["converged"] and abs(st["conv64"]["iterations"] - st1["conv64"]["iterations"]) <= 2
+        assert np.linalg.norm(out["conv64"] - base["conv64"]) <= 1e-4 * np.linalg.norm(base["conv64"])
