@@ -322,6 +322,12 @@ def main():
         # update kernel with peer stores, plus two 8/16-byte mailbox all-reduces), from rank 0's last step
         R = 2  # default Weights: model_2 -> radius-2 star
         it_ms = last_stats.get("solve_ms", 0.0) / max(1, last_stats.get("iterations", 1))
+        if it_ms > 0:
+            # no single kernel is timed alone on the slabs: the whole iteration in SURVEY §8(d)'s 52 B/cell convention, per GPU
+            per_gpu = BYTES_PER_CELL_ITER[args.precision] * N / world / (it_ms * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": "whole Jacobi-PCG iteration on one slab (stencil + data term + update, exchanges included)",
+                    "achieved": per_gpu, "peak": peak, "unit": "GB/s", "frac": per_gpu / peak, "traffic": None,
+                    "algorithmic_bytes_per_cell": BYTES_PER_CELL_ITER[args.precision], "peak_source": peak_src, "per": "GPU"}
         halo_bytes = 2 * R * n * n * (4 if args.precision == "f32" else 8)  # an interior rank: both neighbours
         extra = {"slab": {"planes_per_rank": [b - a for a, b in zip(runner.cuts, runner.cuts[1:])] if runner.cuts else n // world,
                           "partition": "cost-balanced (fi_slab_balanced_cuts)" if runner.cuts else "uniform", "setup_ms": last_stats.get("setup_ms"), "solve_ms": last_stats.get("solve_ms"),
