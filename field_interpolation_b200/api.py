@@ -105,7 +105,7 @@ def _common_loc(bufs):
 
 
 def solve_options(precision=FI_F32, max_iterations=0, tolerance=1e-3, check_every=32, use_fast_stencil=True,
-                  refine_max_outer=20, refine_inner_tolerance=1e-3, preconditioner=FI_PRECOND_JACOBI, mg_smoothing_steps=3,
+                  refine_max_outer=20, refine_inner_tolerance=1e-3, preconditioner=FI_PRECOND_JACOBI, mg_smoothing_steps=0,
                   mg_cheb_ratio=12.0) -> L.fi_solve_options:
     return L.fi_solve_options(int(precision), int(max_iterations), float(tolerance), int(check_every),
                               int(use_fast_stencil), int(refine_max_outer), float(refine_inner_tolerance), int(preconditioner),

@@ -207,6 +207,7 @@ struct fi_field
 	fi::Multigrid& get_mg(const fi_solve_options& o)
 	{
 		fi::MgOptions want;
+		want.nu = fi::default_smoothing_steps(model);
 		if (o.mg_smoothing_steps > 0) { want.nu = o.mg_smoothing_steps; }
 		if (o.mg_cheb_ratio > 1.0) { want.cheb_ratio = o.mg_cheb_ratio; }
 		if (const char* e = getenv("FI_B200_MG_COARSEST")) {  // tuning knob: cells of the dense coarsest level
@@ -587,7 +588,7 @@ void fi_solve_options_default(fi_solve_options* o)
 	o->refine_max_outer       = 20;
 	o->refine_inner_tolerance = 1e-3;
 	o->preconditioner         = FI_PRECOND_JACOBI;
-	o->mg_smoothing_steps     = 3;
+	o->mg_smoothing_steps     = 0;  // by the smoothness model: fi::default_smoothing_steps
 	o->mg_cheb_ratio          = 12.0;
 }
 

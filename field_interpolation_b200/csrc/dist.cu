@@ -366,6 +366,7 @@ void slab_mg_solve_typed(fi_comm* c, const Geom& g, const SlabMgPlan& plan, cons
 	op32->dist     = &hooks;
 	op32->use_fast = kStencilAuto;
 	MgOptions mo;
+	mo.nu = default_smoothing_steps(model);
 	if (o.mg_smoothing_steps > 0) { mo.nu = o.mg_smoothing_steps; }
 	if (o.mg_cheb_ratio > 1.0) { mo.cheb_ratio = o.mg_cheb_ratio; }
 	if (const char* e = getenv("FI_B200_MG_COARSEST")) {

@@ -189,6 +189,11 @@ struct MgOptions
 	int    power_iterations = 12;    // for lambda_max, per level, at setup
 };
 
+// Chebyshev steps when the caller leaves mg_smoothing_steps at 0: 3 for operators up to model_2 (tuned on the GPU, r1c),
+// 5 when model_3 / model_4 rows are present — their 6th / 8th-order stencils leave more high-frequency error per step
+// (model_3 alone, 32x16x24: 80 MG-PCG iterations reach 3e-7 with 5 steps, 2e-3 with 3).
+inline int default_smoothing_steps(const ModelAccum& m) { return (m.on[3] || m.on[4]) ? 5 : 3; }
+
 struct Multigrid
 {
 	struct Level;

@@ -86,9 +86,8 @@ typedef struct fi_solve_options {
 	int32_t refine_max_outer; /* FI_MIXED: max fp64 refinement sweeps; <= 0: 20 */
 	double  refine_inner_tolerance; /* FI_MIXED: relative tolerance of each inner fp32 solve; <= 0: 1e-3 */
 	int32_t preconditioner;   /* fi_preconditioner.  FI_PRECOND_JACOBI is what the reference's Eigen solvers use */
-	int32_t mg_smoothing_steps; /* FI_PRECOND_MULTIGRID: Chebyshev steps before and after each coarse correction; <= 0: 3.
-	                             * Tuned for model_1 / model_2 smoothness; operators dominated by model_3 / model_4 (6th / 8th
-	                             * order) want 5 (model_3 alone, 32x16x24: 80 iterations reach 3e-7 with 5, 2e-3 with 3) */
+	int32_t mg_smoothing_steps; /* FI_PRECOND_MULTIGRID: Chebyshev steps before and after each coarse correction; <= 0: by the
+	                             * smoothness model — 3, or 5 when model_3 / model_4 rows (6th / 8th-order stencils) are present */
 	double  mg_cheb_ratio;    /* ... smoothed part of the spectrum is [lambda_max / ratio, lambda_max]; <= 0: 12 */
 } fi_solve_options;
 
