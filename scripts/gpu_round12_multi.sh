@@ -17,3 +17,8 @@ FI_B200_PEER_FOLD=1 FI_B200_TRACE=1 timeout 300 python -m torch.distributed.run 
 # and on the uniform partition, to separate the two effects
 FI_B200_BENCH_UNIFORM=1 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus $N --no-time-to-tol \
     > gpurun_out/bench12_uniform_n$N.json 2> gpurun_out/bench12_uniform_n$N.err; tail -c 1200 gpurun_out/bench12_uniform_n$N.json
+# BASELINE configs[4] (1024^3 lattice, 20M points) when all 8 GPUs are there
+if [ "$N" = "8" ]; then
+    timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29515 bench.py --gpus 8 --workload sdf3d_1024_20M --steps 2 --warmup 3 \
+        > gpurun_out/bench12_c5_n8.json 2> gpurun_out/bench12_c5_n8.err; tail -c 2500 gpurun_out/bench12_c5_n8.json; tail -3 gpurun_out/bench12_c5_n8.err
+fi
