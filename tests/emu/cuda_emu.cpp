@@ -276,9 +276,6 @@ size_t tma_load_3d(void* dst, const CUtensorMap* map, int x, int y, int z)
 	return static_cast<size_t>(m.box[0]) * m.box[1] * m.box[2] * m.elem;
 }
 
-namespace {
-}
-
 void launch(const char* name, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, std::function<void()> body)
 {
 	static const bool trace = std::getenv("CUDA_EMU_TRACE") != nullptr && *std::getenv("CUDA_EMU_TRACE") != '\0';
