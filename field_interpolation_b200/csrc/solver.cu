@@ -115,7 +115,8 @@ __global__ void __launch_bounds__(kThreads) pcg_init_kernel(int64_t n, const T* 
 // ---- peer-memory all-reduce (see solver.hpp) ----------------------------------------------------------------
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
 {
-#ifdef FI_B200_EMU  // tests/emu: no PTX on the CPU functional emulator
+#ifdef FI_B200_EMU  // tests/emu: no PTX on the CPU functional emulator; a polling thread lets its siblings run (the hardware
+	::cuda_emu::spin_yield();  // guarantees forward progress to the other lanes of a warp, sequential fibers do not)
 	return *reinterpret_cast<const volatile unsigned long long*>(p);
 #else
 	unsigned long long v;
