@@ -209,13 +209,12 @@ def main():
         # iteration: partition by cost (lattice planes + data points, fi_slab_balanced_cuts) instead of by plane count.
         # One histogram kernel over the resident points, computed once for the cloud (it fixes the size of every rank's
         # output buffer); FI_B200_BENCH_UNIFORM=1 keeps the uniform partition.
-        cuts = None
+        runner = fid.SlabRunner(sizes, weights, rank, world, dist)
         if os.environ.get("FI_B200_BENCH_UNIFORM") != "1":
             try:
-                cuts = fid.balanced_cuts(sizes, world, d_pos, 0.0, 8)
-            except fi.FiError:  # deterministic (same arguments on every rank): everybody falls back to the uniform partition
-                cuts = None
-        runner = fid.SlabRunner(sizes, weights, rank, world, dist, cuts=cuts)
+                runner.set_cuts(fid.balanced_cuts(sizes, world, d_pos, 0.0, 8))
+            except fi.FiError:  # deterministic (same arguments on every rank): everybody stays on the uniform partition
+                runner.set_cuts(None)
     else:
         runner = None
 
