@@ -223,3 +223,28 @@ def test_slab_peer_fold_mode_matches_one_rank():
         assert st["pcg64"]["iterations"] == 12 and np.linalg.norm(out["pcg64"] - base["pcg64"]) <= 1e-7 * np.linalg.norm(base["pcg64"])
         assert st["conv64"]["converged"] and abs(st["conv64"]["iterations"] - st1["conv64"]["iterations"]) <= 2
         assert np.linalg.norm(out["conv64"] - base["conv64"]) <= 1e-4 * np.linalg.norm(base["conv64"])
+
+
+def test_balanced_cuts_of_the_bench_cloud(emu):
+    """fi_slab_balanced_cuts on bench.py's workload (512^3 lattice, 1M sphere+torus points): the partition the 8-, 4- and
+    2-GPU bench lines run on, against the same cost model in numpy; slabs holding the cloud get fewer planes."""
+    from field_interpolation_b200 import dist as fid
+    n = 512
+    cloud = W.sphere_torus_3d(1_000_000, seed=0)
+    pos = W.to_lattice(cloud["unit_pos"], [n, n, n])
+    z = np.floor(pos[:, 2])
+    hist = np.bincount(z[(z >= 0) & (z < n)].astype(np.int64), minlength=n)
+    cum = np.concatenate([[0.0], np.cumsum(float(n) * n + 9.0 * hist)])
+    for world in (2, 4, 8):
+        want = [0]
+        for k in range(1, world):
+            t = cum[-1] * k / world
+            zc = int(np.searchsorted(cum, t, side="left"))
+            if zc > 0 and t - cum[zc - 1] < cum[zc] - t:
+                zc -= 1
+            want.append(zc)
+        want.append(n)
+        got = fid.balanced_cuts([n, n, n], world, pos, 0.0, 8)
+        assert got == want, (world, got, want)
+    planes = np.diff(got)
+    assert planes.tolist() == [68, 67, 64, 57, 57, 64, 67, 68]
