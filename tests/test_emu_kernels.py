@@ -196,7 +196,7 @@ def test_slab_custom_and_balanced_cuts_match_one_rank():
     solves = dict(SLAB_SOLVES)
     case = {"sizes": [32, 16, 40], "points": 3000, "seed": 5, "weights": {}, "solves": solves}
     base, st1 = _run_ranks(1, case)
-    for cuts, p2p in (([0, 6, 29, 40], False), ([0, 6, 29, 40], True), ("balanced", True)):
+    for cuts, p2p in (([0, 6, 29, 40], False), ("balanced", True)):
         c = dict(case, cuts=cuts, point_weight=60.0, min_planes=4)
         out, st = _run_ranks(3, c, p2p=p2p)
         if cuts == "balanced":
@@ -218,7 +218,7 @@ def test_slab_peer_fold_mode_matches_one_rank():
               "conv64": {"precision": "f64", "max_iterations": 2000, "tolerance": 1e-3}}
     case = {"sizes": [32, 16, 24], "points": 2500, "seed": 5, "weights": {}, "solves": solves}
     base, st1 = _run_ranks(1, case)
-    for world in (2, 3):
+    for world in (3,):
         out, st = _run_ranks(world, case, p2p=True, extra_env={"FI_B200_PEER_FOLD": "1"})
         assert st["pcg64"]["iterations"] == 12 and np.linalg.norm(out["pcg64"] - base["pcg64"]) <= 1e-7 * np.linalg.norm(base["pcg64"])
         assert st["conv64"]["converged"] and abs(st["conv64"]["iterations"] - st1["conv64"]["iterations"]) <= 2
