@@ -41,7 +41,7 @@ class fi_solve_stats(C.Structure):
     _fields_ = [("iterations", C.c_int64), ("relative_residual", C.c_double), ("true_residual", C.c_double),
                 ("initial_residual", C.c_double), ("setup_ms", C.c_double), ("solve_ms", C.c_double),
                 ("converged", C.c_int32), ("outer_sweeps", C.c_int32), ("occupied_cells", C.c_int64),
-                ("generic_rows", C.c_int64)]
+                ("generic_rows", C.c_int64), ("widened_after", C.c_int64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -78,6 +78,7 @@ SIGNATURES = {
     "fi_solve_options_default": (None, [_p(fi_solve_options)]),
     "fi_field_create": (C.c_int, [_i32, _pi32, _p(_vp)]),
     "fi_field_destroy": (C.c_int, [_vp]),
+    "fi_field_clone": (C.c_int, [_vp, _p(_vp)]),
     "fi_field_add_model": (C.c_int, [_vp, _p(fi_weights)]),
     "fi_field_add_points": (C.c_int, [_vp, _f, _i32, _f, _i32, _i64, _vp, _vp, _vp, _vp, _i32, _pi64]),
     "fi_field_add_rows": (C.c_int, [_vp, _i64, _i64, _pi32, _pi32, _pf, _pf]),

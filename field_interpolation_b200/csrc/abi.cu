@@ -71,7 +71,7 @@ struct Pool
 	std::mutex                        mu;
 	std::multimap<size_t, void*>      free_blocks;  // per device: keyed by (device, bytes) folded into one size_t below
 	size_t                            cached = 0;
-	bool                              dirty  = false;  // blocks were released since the last device synchronisation
+	bool                              dirty[16] = {};  // per device: blocks were released since its last synchronisation
 	size_t                            limit  = 0;
 };
 Pool& pool()
@@ -80,18 +80,23 @@ Pool& pool()
 	return p;
 }
 size_t round_block(size_t bytes) { return bytes >= (1u << 20) ? ((bytes + (2u << 20) - 1) >> 21) << 21 : ((bytes + 511) >> 9) << 9; }
-size_t pool_key(size_t rounded)
+int pool_device()
 {
 	int dev = 0;
 	cudaGetDevice(&dev);
-	return rounded * 16 + static_cast<size_t>(dev & 15);  // sizes are multiples of 512: the low bits are free for the device
+	return dev & 15;
+}
+size_t pool_key(size_t rounded, int dev)
+{
+	return rounded * 16 + static_cast<size_t>(dev);  // sizes are multiples of 512: the low bits are free for the device
 }
 }  // namespace
 
 void* pool_alloc(size_t bytes)
 {
 	Pool&        P = pool();
-	const size_t rb = round_block(bytes), key = pool_key(rb);
+	const int    dev = pool_device();
+	const size_t rb = round_block(bytes), key = pool_key(rb, dev);
 	{
 		std::lock_guard<std::mutex> lock(P.mu);
 		auto it = P.free_blocks.find(key);
@@ -99,9 +104,9 @@ void* pool_alloc(size_t bytes)
 			void* p = it->second;
 			P.free_blocks.erase(it);
 			P.cached -= rb;
-			if (P.dirty) {  // whoever released it may still have had work in flight on some stream
+			if (P.dirty[dev]) {  // whoever released it may still have had work in flight on some stream of this device
 				cudaDeviceSynchronize();
-				P.dirty = false;
+				P.dirty[dev] = false;
 			}
 			return p;
 		}
@@ -133,9 +138,10 @@ void pool_free(void* p, size_t bytes)
 		cudaFree(p);
 		return;
 	}
-	P.free_blocks.emplace(pool_key(rb), p);
+	const int dev = pool_device();
+	P.free_blocks.emplace(pool_key(rb, dev), p);
 	P.cached += rb;
-	P.dirty = true;
+	P.dirty[dev] = true;
 }
 
 void pool_trim()
@@ -145,7 +151,7 @@ void pool_trim()
 	for (auto& kv : P.free_blocks) { cudaFree(kv.second); }
 	P.free_blocks.clear();
 	P.cached = 0;
-	P.dirty  = false;
+	for (bool& d : P.dirty) { d = false; }
 }
 
 size_t pool_cached_bytes()
@@ -414,6 +420,7 @@ void fill_stats(fi_solve_stats* st, const PcgResult& r, double setup_ms, int64_t
 	st->outer_sweeps      = 0;
 	st->occupied_cells    = nocc;
 	st->generic_rows      = grows;
+	st->widened_after     = -1;
 }
 
 // Solves into d_out (device, N floats) from d_guess (device, nullable).
@@ -424,40 +431,55 @@ void solve_device(fi_field* f, const fi_solve_options& o, const float* d_guess, 
 	const int     fast = o.use_fast_stencil;
 	if (o.preconditioner == FI_PRECOND_MULTIGRID) {
 		const bool fresh = !f->mg;
-		double     setup = 0;
-		cudaEvent_t e0, e1;
-		FI_CUDA(cudaEventCreate(&e0));
-		FI_CUDA(cudaEventCreate(&e1));
-		FI_CUDA(cudaEventRecord(e0, s));
+		CudaEvent  e0, e1;
+		e0.record(s);
 		Multigrid& mg = f->get_mg(o);
+		PcgResult  r;
+		long long  widened_after = -1;
+		bool       start_wide = o.precision != FI_F32;
 		if (o.precision == FI_F32) {
 			Operator<float>& op = f->get32();
-			FI_CUDA(cudaEventRecord(e1, s));
+			op.use_fast         = fast;
+			e1.record(s);
 			if (d_guess) {
 				if (d_guess != d_out) { FI_CUDA(cudaMemcpyAsync(d_out, d_guess, N * sizeof(float), cudaMemcpyDeviceToDevice, s)); }
 			} else {
 				FI_CUDA(cudaMemsetAsync(d_out, 0, N * sizeof(float), s));
 			}
-			const PcgResult r = mgpcg_solve<float>(op, mg, nullptr, d_out, o.tolerance, o.max_iterations, s);
-			float ms = 0;
-			FI_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-			setup = ms;
-			fill_stats(st, r, fresh ? setup : 0.0, op.data.nocc, op.data.nrows);
-		} else {  // FI_F64 and FI_MIXED: fp64 outer CG around the fp32 V-cycle
+			// fp32 outer CG, watched: a fourth-order operator on a large lattice has cond ~ n^4, and fp32 vectors stop
+			// describing the solution long before a tight tolerance is met (C3, 2048^2: breakdown after a handful of
+			// iterations).  The solve then continues from the fp32 iterate with the fp64 outer CG (same fp32 V-cycle).
+			r = mgpcg_solve<float>(op, mg, nullptr, d_out, o.tolerance, o.max_iterations, s, 4);
+			const bool budget_left = o.max_iterations <= 0 || r.iterations < o.max_iterations;
+			if (!r.converged && !r.zero_rhs && r.stalled && budget_left) {
+				widened_after = r.iterations;
+				start_wide    = true;
+			}
+		}
+		if (start_wide) {  // FI_F64 and FI_MIXED (and a widened FI_F32): fp64 outer CG around the fp32 V-cycle
 			Operator<double>& op = f->get64();
 			op.use_fast          = fast;
-			FI_CUDA(cudaEventRecord(e1, s));
+			if (widened_after < 0) { e1.record(s); }
 			DevBuf<double> x(N);
-			if (d_guess) { convert(d_guess, x.data(), N, s); } else { x.zero(s); }
-			const PcgResult r = mgpcg_solve<double>(op, mg, nullptr, x.data(), o.tolerance, o.max_iterations, s);
+			const float*   from = widened_after >= 0 ? d_out : d_guess;
+			if (from) { convert(from, x.data(), N, s); } else { x.zero(s); }
+			const long long cap = o.max_iterations > 0 ? o.max_iterations - std::max<long long>(widened_after, 0) : 0;
+			const PcgResult w   = mgpcg_solve<double>(op, mg, nullptr, x.data(), o.tolerance, cap, s);
 			convert(x.data(), d_out, N, s);
-			float ms = 0;
-			FI_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-			setup = ms;
-			fill_stats(st, r, fresh ? setup : 0.0, op.data.nocc, op.data.nrows);
+			if (widened_after >= 0) {
+				PcgResult tot        = w;
+				tot.iterations       = r.iterations + w.iterations;
+				tot.solve_ms         = r.solve_ms + w.solve_ms;
+				tot.initial_residual = r.initial_residual;
+				r                    = tot;
+			} else {
+				r = w;
+			}
 		}
-		cudaEventDestroy(e0);
-		cudaEventDestroy(e1);
+		e1.sync();
+		const double setup = e1.ms_since(e0);
+		fill_stats(st, r, fresh ? setup : 0.0, f->op32 ? f->op32->data.nocc : 0, f->op32 ? f->op32->data.nrows : 0);
+		if (st) { st->widened_after = widened_after; }
 		FI_CUDA(cudaStreamSynchronize(s));
 		return;
 	}
@@ -609,6 +631,34 @@ int fi_field_destroy(fi_field* f)
 	});
 }
 
+int fi_field_clone(const fi_field* f, fi_field** out)
+{
+	return guarded([&] {
+		FI_REQUIRE(f != nullptr && out != nullptr, FI_ERR_INVALID, "null argument");
+		*out = nullptr;
+		std::unique_ptr<fi_field> c(create_impl(f->g.ndim, f->g.size));
+		c->segs  = f->segs;
+		c->rows  = f->rows;
+		c->model = f->model;
+		c->fast  = f->fast;
+		cudaStream_t s = c->stream;
+		FI_CUDA(cudaStreamSynchronize(f->stream));  // the source's point records are complete
+		auto copy = [&](auto& dst, const auto& src) {
+			dst.resize(src.size());
+			if (src.size()) { FI_CUDA(cudaMemcpyAsync(dst.data(), src.data(), src.size() * sizeof(*src.data()), cudaMemcpyDeviceToDevice, s)); }
+		};
+		copy(c->pts.pos, f->pts.pos);
+		copy(c->pts.grad, f->pts.grad);
+		copy(c->pts.value, f->pts.value);
+		copy(c->pts.vw, f->pts.vw);
+		copy(c->pts.gw, f->pts.gw);
+		copy(c->pts.kind, f->pts.kind);
+		c->pts.count = f->pts.count;
+		FI_CUDA(cudaStreamSynchronize(s));
+		*out = c.release();
+	});
+}
+
 int fi_field_add_model(fi_field* f, const fi_weights* w)
 {
 	return guarded([&] {
@@ -636,12 +686,21 @@ int fi_field_add_rows(fi_field* f, int64_t num_rows, int64_t num_triplets, const
 		FI_REQUIRE(num_rows >= 0 && num_triplets >= 0, FI_ERR_INVALID, "negative count");
 		if (num_rows == 0) { return; }
 		FI_REQUIRE(trip_row && trip_col && trip_val && rhs, FI_ERR_INVALID, "null row arrays");
+		// validate everything before the first push: a call that fails leaves the row store exactly as it was
+		for (int64_t k = 0; k < num_triplets; ++k) {
+			FI_REQUIRE(0 <= trip_col[k] && trip_col[k] < f->g.N, FI_ERR_INVALID, "column out of range");
+			FI_REQUIRE(0 <= trip_row[k] && trip_row[k] < num_rows && (k == 0 || trip_row[k - 1] <= trip_row[k]), FI_ERR_INVALID,
+			           "trip_row must be non-decreasing and < num_rows");
+		}
 		HostRows& R  = f->rows;
 		const int64_t r0 = R.rows();
-		int64_t       at = 0;
+		R.col.reserve(R.col.size() + static_cast<size_t>(num_triplets));
+		R.val.reserve(R.val.size() + static_cast<size_t>(num_triplets));
+		R.ptr.reserve(R.ptr.size() + static_cast<size_t>(num_rows));
+		R.rhs.reserve(R.rhs.size() + static_cast<size_t>(num_rows));
+		int64_t at = 0;
 		for (int64_t r = 0; r < num_rows; ++r) {
 			while (at < num_triplets && trip_row[at] == r) {
-				FI_REQUIRE(0 <= trip_col[at] && trip_col[at] < f->g.N, FI_ERR_INVALID, "column out of range");
 				R.col.push_back(trip_col[at]);
 				R.val.push_back(trip_val[at]);
 				++at;
@@ -649,7 +708,6 @@ int fi_field_add_rows(fi_field* f, int64_t num_rows, int64_t num_triplets, const
 			R.ptr.push_back(R.col.size());
 			R.rhs.push_back(rhs[r]);
 		}
-		FI_REQUIRE(at == num_triplets, FI_ERR_INVALID, "trip_row must be non-decreasing and < num_rows");
 		Segment sg;
 		sg.kind = Segment::kRows;
 		sg.r0   = r0;

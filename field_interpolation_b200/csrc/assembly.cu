@@ -807,6 +807,157 @@ __global__ void __launch_bounds__(kThreads, 3) apply_blocks_epilogue_kernel(Geom
 	}
 }
 
+// ---- node-major form of P (DataTerm::node_*) ----------------------------------------------------------------------
+__host__ __device__ constexpr int pow3(int d) { return d == 1 ? 3 : (d == 2 ? 9 : 27); }
+
+// One key per (occupied cell, corner): the local index of the corner's node when this process owns its row, else
+// `sentinel` (sorts behind every node).
+template <int D>
+__global__ void node_keys_kernel(Geom g, int64_t nocc, const int64_t* __restrict__ cell_base, const uint32_t* __restrict__ cell_mask,
+                                 uint64_t sentinel, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, unsigned long long* valid)
+{
+	constexpr int C = 1 << D;
+	const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	bool          own = false;
+	if (i < nocc * C) {
+		const int64_t cell = i / C;
+		const int     c    = static_cast<int>(i % C);
+		own                = (cell_mask[cell] >> (8 + c)) & 1u;
+		int64_t off = 0;
+#pragma unroll
+		for (int d = 0; d < D; ++d) { off += ((c >> d) & 1) ? g.stride[d] : 0; }
+		keys[i] = own ? static_cast<uint64_t>(cell_base[cell] + off) : sentinel;
+		vals[i] = 0;
+	}
+	const unsigned b = __ballot_sync(0xffffffffu, own);
+	if ((threadIdx.x & 31) == 0 && b) { atomicAdd(valid, static_cast<unsigned long long>(__popc(b))); }
+}
+
+// Row of P of every touched node, gathered from the blocks of the 2^D cells around it (found by binary search in the
+// sorted cell keys).  Fixed summation order: cells in ascending corner order.
+template <typename T, int D>
+__global__ void __launch_bounds__(kThreads) node_rows_kernel(Geom g, int64_t nnode, const uint64_t* __restrict__ node_key, int64_t nocc,
+                                                             const uint64_t* __restrict__ cell_key, const T* __restrict__ blocks,
+                                                             int64_t* __restrict__ node_index, T* __restrict__ coef)
+{
+	constexpr int C = 1 << D, K = pow3(D);
+	const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (i >= nnode) { return; }
+	const int64_t idx = static_cast<int64_t>(node_key[i]);
+	node_index[i]     = idx;
+	int     coord[D];
+	int64_t v = idx - g.shift;  // = sum coord_d * stride_d over the whole lattice
+#pragma unroll
+	for (int d = 0; d < D; ++d) {
+		if (d + 1 < D) {
+			coord[d] = static_cast<int>(v % g.size[d]);
+			v /= g.size[d];
+		} else {
+			coord[d] = static_cast<int>(v);
+		}
+	}
+	T acc[K];
+#pragma unroll
+	for (int k = 0; k < K; ++k) { acc[k] = T(0); }
+#pragma unroll
+	for (int ci = 0; ci < C; ++ci) {
+		uint64_t key = 0, kstr = 1;
+#pragma unroll
+		for (int d = 0; d < D; ++d) {
+			key += static_cast<uint64_t>(coord[d] - ((ci >> d) & 1) + 1) * kstr;  // cell base in [-1, size - 1]
+			kstr *= static_cast<uint64_t>(g.size[d] + 1);
+		}
+		int64_t lo = 0, hi = nocc;
+		while (lo < hi) {
+			const int64_t mid = (lo + hi) >> 1;
+			if (cell_key[mid] < key) { lo = mid + 1; } else { hi = mid; }
+		}
+		if (lo >= nocc || cell_key[lo] != key) { continue; }
+#pragma unroll
+		for (int cj = 0; cj < C; ++cj) {
+			bool inside = true;
+			int  slot = 0, p3 = 1;
+#pragma unroll
+			for (int d = 0; d < D; ++d) {
+				const int delta = ((cj >> d) & 1) - ((ci >> d) & 1);
+				const int n     = coord[d] + delta;
+				inside          = inside && (0 <= n) && (n < g.size[d]);
+				slot += (delta + 1) * p3;
+				p3 *= 3;
+			}
+			const int a = ci < cj ? ci : cj, b = ci < cj ? cj : ci;
+			const int tri = a * C - (a * (a - 1)) / 2 + (b - a);  // row-major upper triangle, as the scatter kernel stores it
+			if (inside) { acc[slot] += blocks[static_cast<size_t>(tri) * nocc + lo]; }
+		}
+	}
+#pragma unroll
+	for (int k = 0; k < K; ++k) { coef[static_cast<size_t>(k) * nnode + i] = acc[k]; }
+}
+
+// u = (P in)[node] for the touched node i of this thread (zero coefficients are never followed: their neighbour may
+// lie outside the lattice).
+template <typename T, int D>
+__device__ __forceinline__ T node_row_dot(const Geom& g, int64_t nnode, int64_t i, int64_t idx, const T* __restrict__ coef, const T* __restrict__ in)
+{
+	constexpr int K = pow3(D);
+	T c[K];
+#pragma unroll
+	for (int k = 0; k < K; ++k) { c[k] = __ldg(&coef[static_cast<size_t>(k) * nnode + i]); }
+	T acc = T(0);
+#pragma unroll
+	for (int k = 0; k < K; ++k) {
+		int64_t off = 0;
+		int     r = k;
+#pragma unroll
+		for (int d = 0; d < D; ++d) {
+			off += static_cast<int64_t>(r % 3 - 1) * g.stride[d];
+			r /= 3;
+		}
+		if (c[k] != T(0)) { acc += c[k] * in[idx + off]; }
+	}
+	return acc;
+}
+
+// q += P p over the touched nodes, p.(P p) added to *dot_accum: one thread per node, one writer per element of q.
+template <typename T, int D>
+__global__ void __launch_bounds__(kThreads) apply_nodes_kernel(Geom g, int64_t nnode, const int64_t* __restrict__ node_index,
+                                                               const T* __restrict__ coef, const T* __restrict__ p, T* __restrict__ q,
+                                                               double* partial, unsigned* ticket, double* dot_accum, const int* done)
+{
+	__shared__ double red[32];
+	if (done && *done) { return; }
+	const int64_t i       = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	double        mine[1] = {0.0};
+	if (i < nnode) {
+		const int64_t idx = node_index[i];
+		const T       u   = node_row_dot<T, D>(g, nnode, i, idx, coef, p);
+		q[idx] += u;
+		mine[0] = static_cast<double>(p[idx]) * static_cast<double>(u);
+	}
+	if (dot_accum) {
+		mine[0] = block_sum(mine[0], red);
+		grid_sum<1>(mine, partial, ticket, red, [&](const double(&tot)[1]) { *dot_accum += tot[0]; });
+	}
+}
+
+// Epilogue form for the multigrid smoother: u = P in, res -= u and (d_new given) d_new -= b minv u, e -= b minv u.
+template <typename T, int D>
+__global__ void __launch_bounds__(kThreads) apply_nodes_epilogue_kernel(Geom g, int64_t nnode, const int64_t* __restrict__ node_index,
+                                                                        const T* __restrict__ coef, const T* __restrict__ in, T* __restrict__ res,
+                                                                        const T* __restrict__ minv, T* __restrict__ e, T* __restrict__ d_new, T b)
+{
+	const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (i >= nnode) { return; }
+	const int64_t idx = node_index[i];
+	const T       u   = node_row_dot<T, D>(g, nnode, i, idx, coef, in);
+	res[idx] -= u;
+	if (d_new) {
+		const T dd = -b * minv[idx] * u;
+		d_new[idx] += dd;
+		e[idx] += dd;
+	}
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads) apply_rows_kernel(int64_t nrows, const uint64_t* __restrict__ row_ptr,
                                                               const int32_t* __restrict__ col, const float* __restrict__ val,
@@ -935,6 +1086,53 @@ void upscale_device(const Geom& small, const Geom& large, const float* d_small, 
 	FI_LAUNCH(upscale_kernel, div_up(large.N, kThreads), kThreads, 0, s, small, large, d_small, d_large, post_scale);
 }
 
+// Node-major form of the cell blocks (DataTerm::node_index / node_coef), built once per operator.
+template <typename T>
+static void build_node_rows(const Geom& g, DataTerm<T>& out, cudaStream_t s)
+{
+	out.nnode = 0;
+	if (out.nocc == 0) { return; }
+	const int     C = 1 << g.ndim;
+	const int64_t n = out.nocc * C;
+	FI_REQUIRE(n < (1ll << 32), FI_ERR_RANGE, "too many occupied cells for the node-major data term");
+	DevBuf<uint64_t>           keys(n), flags(n), scan(n), total(1), uniq;
+	DevBuf<uint32_t>           vals(n), slot(n);
+	DevBuf<unsigned long long> valid(1);
+	valid.zero(s);
+	const uint64_t sentinel = static_cast<uint64_t>(g.N);
+	by_dim(g.ndim, [&](auto dim) {
+		auto kern = node_keys_kernel<decltype(dim)::value>;
+		FI_LAUNCH(kern, div_up(n, kThreads), kThreads, 0, s, g, out.nocc, out.cell_base.data(), out.cell_mask.data(), sentinel, keys.data(), vals.data(),
+		          valid.data());
+	});
+	int bits = 1;
+	while (bits < 63 && (1ull << bits) <= sentinel) { ++bits; }
+	radix_sort_pairs(keys, vals, n, bits, s);
+	unsigned long long h_valid = 0;
+	FI_CUDA(cudaMemcpyAsync(&h_valid, valid.data(), sizeof(h_valid), cudaMemcpyDeviceToHost, s));
+	FI_CUDA(cudaStreamSynchronize(s));
+	const int64_t V = static_cast<int64_t>(h_valid);
+	if (V == 0) { return; }
+	FI_LAUNCH(mark_heads_kernel, div_up(V, kThreads), kThreads, 0, s, keys.data(), V, flags.data());
+	exclusive_scan_u64(flags.data(), scan.data(), V, total.data(), s);
+	uint64_t h_nnode = 0;
+	FI_CUDA(cudaMemcpyAsync(&h_nnode, total.data(), sizeof(h_nnode), cudaMemcpyDeviceToHost, s));
+	FI_CUDA(cudaStreamSynchronize(s));
+	out.nnode = static_cast<int64_t>(h_nnode);
+	uniq.resize(out.nnode);
+	FI_LAUNCH(slots_kernel, div_up(V, kThreads), kThreads, 0, s, keys.data(), flags.data(), scan.data(), V, slot.data(), uniq.data());
+	int K = 1;
+	for (int d = 0; d < g.ndim; ++d) { K *= 3; }
+	out.node_index.resize(out.nnode);
+	out.node_coef.resize(static_cast<size_t>(K) * out.nnode);
+	by_dim(g.ndim, [&](auto dim) {
+		auto kern = node_rows_kernel<T, decltype(dim)::value>;
+		FI_LAUNCH(kern, div_up(out.nnode, kThreads), kThreads, 0, s, g, out.nnode, uniq.data(), out.nocc, out.cell_key.data(), out.blocks.data(),
+		          out.node_index.data(), out.node_coef.data());
+	});
+	FI_CUDA(cudaStreamSynchronize(s));  // the scratch buffers go out of scope
+}
+
 template <typename T>
 void build_data_term(const Geom& g, const PointStore& pts, const HostRows& user, DataTerm<T>& out, T* d_atb, T* d_diag,
                      cudaStream_t s)
@@ -991,6 +1189,8 @@ void build_data_term(const Geom& g, const PointStore& pts, const HostRows& user,
 				auto kern = scatter_points_kernel<T, decltype(dim)::value>;
 				FI_LAUNCH(kern, grid, kThreads, 0, s, g, pv, order.data(), slot.data(), V, out.nocc, out.blocks.data(), d_atb, d_diag);
 			});
+			// 4'. the node-major form the solver applies (tile mode keeps using the blocks)
+			build_node_rows<T>(g, out, s);
 			FI_CUDA(cudaStreamSynchronize(s));
 		}
 	}
@@ -1031,18 +1231,20 @@ void build_data_term(const Geom& g, const PointStore& pts, const HostRows& user,
 			FI_CUDA(cudaStreamSynchronize(s));
 		}
 	}
-	out.partial.resize(static_cast<size_t>(div_up(std::max<int64_t>(out.nocc, 1), kThreads)) + div_up(std::max<int64_t>(out.nrows, 1), kThreads) + 4);
+	out.partial.resize(static_cast<size_t>(div_up(std::max<int64_t>(std::max(out.nocc, out.nnode), 1), kThreads)) + div_up(std::max<int64_t>(out.nrows, 1), kThreads) + 4);
 	out.ticket.resize(2);
 	out.ticket.zero(s);
 	FI_CUDA(cudaStreamSynchronize(s));
 }
 
-// FI_B200_DATA_TERM=cell selects the one-thread-per-cell kernel (kept for comparison); default: per (cell, row).
-static bool split_data_term()
+// Which kernel applies the cell blocks: the node-major gather (default; no atomics), or — kept for comparison,
+// FI_B200_DATA_TERM=cell / split — one thread per cell / per (cell, row) with atomics into q.
+enum DataTermKernel { kDataNode, kDataCell, kDataSplit };
+static DataTermKernel data_term_kernel()
 {
-	static const bool v = [] {
+	static const DataTermKernel v = [] {
 		const char* e = getenv("FI_B200_DATA_TERM");
-		return !(e && e[0] == 'c');
+		return !e ? kDataNode : (e[0] == 'c' ? kDataCell : (e[0] == 's' ? kDataSplit : kDataNode));
 	}();
 	return v;
 }
@@ -1053,6 +1255,7 @@ void apply_data_term(const Geom& g, const DataTerm<T>& dt, const T* p, T* q, dou
 {
 	const int gb = dt.nocc > 0 ? div_up(dt.nocc, kThreads) : 0;
 	const int gr = dt.nrows > 0 ? div_up(dt.nrows, kThreads) : 0;
+	const int gp = dt.nocc > 0 ? div_up(std::max(dt.nocc, dt.nnode), kThreads) : 0;  // partial sums of the rows kernel start behind the widest block / node grid
 	double*   partial = const_cast<double*>(dt.partial.data());
 	unsigned* ticket  = const_cast<unsigned*>(dt.ticket.data());
 	if (gb > 0) {
@@ -1061,7 +1264,13 @@ void apply_data_term(const Geom& g, const DataTerm<T>& dt, const T* p, T* q, dou
 				auto kern = apply_blocks_kernel<T, decltype(dim)::value, true>;
 				FI_LAUNCH(kern, gb, kThreads, 0, s, g, dt.nocc, dt.cell_base.data(), dt.cell_mask.data(), dt.blocks.data(), p, q, partial, ticket,
 				          d_dot_accum, d_done, dt.cell_key.data());
-			} else if (split_data_term()) {
+			} else if (data_term_kernel() == kDataNode) {
+				if (dt.nnode > 0) {
+					auto kern = apply_nodes_kernel<T, decltype(dim)::value>;
+					FI_LAUNCH(kern, div_up(dt.nnode, kThreads), kThreads, 0, s, g, dt.nnode, dt.node_index.data(), dt.node_coef.data(), p, q, partial, ticket,
+					          d_dot_accum, d_done);
+				}
+			} else if (data_term_kernel() == kDataSplit) {
 				auto kern = apply_blocks_split_kernel<T, decltype(dim)::value>;
 				FI_LAUNCH(kern, gb, kThreads, 0, s, g, dt.nocc, dt.cell_base.data(), dt.cell_mask.data(), dt.blocks.data(), p, q, partial, ticket,
 				          d_dot_accum, d_done);
@@ -1075,11 +1284,11 @@ void apply_data_term(const Geom& g, const DataTerm<T>& dt, const T* p, T* q, dou
 	if (gr > 0 && g.tile) {
 		auto kern = apply_rows_tiled_kernel<T>;
 		FI_LAUNCH(kern, gr, kThreads, 0, s, g, dt.nrows, dt.row_ptr.data(), dt.col.data(), dt.val.data(), p, q,
-		          partial + gb + 1, ticket + 1, d_dot_accum, d_done);
+		          partial + gp + 1, ticket + 1, d_dot_accum, d_done);
 	} else if (gr > 0) {
 		auto kern = apply_rows_kernel<T>;
 		FI_LAUNCH(kern, gr, kThreads, 0, s, dt.nrows, dt.row_ptr.data(), dt.col.data(), dt.val.data(), p, q,
-		          partial + gb + 1, ticket + 1, d_dot_accum, d_done);
+		          partial + gp + 1, ticket + 1, d_dot_accum, d_done);
 	}
 }
 
@@ -1091,9 +1300,17 @@ bool apply_data_term_epilogue(const Geom& g, const DataTerm<T>& dt, const T* in,
 	if (dt.nrows > 0 || g.tile) { return false; }
 	if (dt.nocc > 0) {
 		by_dim(g.ndim, [&](auto dim) {
-			auto kern = apply_blocks_epilogue_kernel<T, decltype(dim)::value>;
-			FI_LAUNCH(kern, div_up(dt.nocc, kThreads), kThreads, 0, s, g, dt.nocc, dt.cell_base.data(), dt.cell_mask.data(), dt.blocks.data(), in,
-			          res_out, minv, e, d_new, b);
+			if (data_term_kernel() == kDataNode) {
+				if (dt.nnode > 0) {
+					auto kern = apply_nodes_epilogue_kernel<T, decltype(dim)::value>;
+					FI_LAUNCH(kern, div_up(dt.nnode, kThreads), kThreads, 0, s, g, dt.nnode, dt.node_index.data(), dt.node_coef.data(), in, res_out, minv, e,
+					          d_new, b);
+				}
+			} else {
+				auto kern = apply_blocks_epilogue_kernel<T, decltype(dim)::value>;
+				FI_LAUNCH(kern, div_up(dt.nocc, kThreads), kThreads, 0, s, g, dt.nocc, dt.cell_base.data(), dt.cell_mask.data(), dt.blocks.data(), in,
+				          res_out, minv, e, d_new, b);
+			}
 		});
 	}
 	return true;

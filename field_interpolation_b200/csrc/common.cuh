@@ -139,6 +139,32 @@ private:
 	size_t cap_ = 0;
 };
 
+// cudaEvent_t that is destroyed when it goes out of scope (also when an exception unwinds past it)
+class CudaEvent
+{
+public:
+	CudaEvent() { FI_CUDA(cudaEventCreate(&e_)); }
+	CudaEvent(const CudaEvent&)            = delete;
+	CudaEvent& operator=(const CudaEvent&) = delete;
+	~CudaEvent()
+	{
+		if (e_) { cudaEventDestroy(e_); }
+	}
+	operator cudaEvent_t() const { return e_; }
+	void record(cudaStream_t s) { FI_CUDA(cudaEventRecord(e_, s)); }
+	void sync() { FI_CUDA(cudaEventSynchronize(e_)); }
+	// milliseconds from `from` to this event (both recorded and this one complete)
+	double ms_since(const CudaEvent& from)
+	{
+		float ms = 0;
+		FI_CUDA(cudaEventElapsedTime(&ms, from.e_, e_));
+		return ms;
+	}
+
+private:
+	cudaEvent_t e_ = nullptr;
+};
+
 template <typename T>
 class PinnedBuf
 {

@@ -347,19 +347,19 @@ void slab_solve_typed(fi_comm* c, const Geom& g, int halo, const ModelAccum& mod
 		st->converged         = r.converged ? 1 : 0;
 		st->occupied_cells    = op->data.nocc;
 		st->generic_rows      = op->data.nrows;
+		st->widened_after     = -1;
 	}
 }
 
 
-// Multigrid-preconditioned CG on the slab (mg.cu: SlabMultigrid): the V-cycle always runs in fp32, the outer CG in T.
-template <typename T>
-void slab_mg_solve_typed(fi_comm* c, const Geom& g, const SlabMgPlan& plan, const ModelAccum& model, const PointStore& pts, const fi_solve_options& o,
-                         const float* d_guess_own, float* d_out_own, fi_solve_stats* st, cudaStream_t s)
+// Multigrid-preconditioned CG on the slab (mg.cu: SlabMultigrid): the V-cycle always runs in fp32; the outer CG in fp32
+// (`wide` false) — continued in fp64 from the fp32 iterate when that stalls at its rounding floor, as on one GPU
+// (abi.cu: solve_device) — or in fp64 from the start.
+void slab_mg_solve(fi_comm* c, const Geom& g, const SlabMgPlan& plan, const ModelAccum& model, const PointStore& pts, const fi_solve_options& o,
+                   bool wide, const float* d_guess_own, float* d_out_own, fi_solve_stats* st, cudaStream_t s)
 {
-	cudaEvent_t e0, e1;
-	FI_CUDA(cudaEventCreate(&e0));
-	FI_CUDA(cudaEventCreate(&e1));
-	FI_CUDA(cudaEventRecord(e0, s));
+	CudaEvent e0, e1;
+	e0.record(s);
 	HostRows  none;
 	SlabHooks hooks(c, g, plan.halo);
 	auto      op32 = build_operator<float>(g, model, pts, none, s);
@@ -373,38 +373,54 @@ void slab_mg_solve_typed(fi_comm* c, const Geom& g, const SlabMgPlan& plan, cons
 		if (atoi(e) > 0) { mo.coarsest_cells = atoi(e); }
 	}
 	auto mg = build_slab_multigrid(*op32, model, pts, mo, plan, s);
-	std::unique_ptr<Operator<T>> op_wide;  // the outer CG's operator when it is not the V-cycle's
-	Operator<T>*                 op = nullptr;
-	if constexpr (std::is_same<T, float>::value) {
-		op = op32.get();
-	} else {
-		op_wide           = build_operator<T>(g, model, pts, none, s);
-		op_wide->dist     = &hooks;
-		op_wide->use_fast = kStencilAuto;
-		op                = op_wide.get();
-	}
-	FI_CUDA(cudaEventRecord(e1, s));
+	std::unique_ptr<Operator<double>> op64;  // the outer CG's operator when it is not the V-cycle's
+	auto wide_operator = [&]() -> Operator<double>& {
+		if (!op64) {
+			op64           = build_operator<double>(g, model, pts, none, s);
+			op64->dist     = &hooks;
+			op64->use_fast = kStencilAuto;
+		}
+		return *op64;
+	};
+	if (wide) { wide_operator(); }
+	e1.record(s);
 	const int64_t off = g.own_offset(), n = g.own_cells();
-	DevBuf<T>     x(g.N);
-	x.zero(s);
-	if (d_guess_own) {
-		if (std::is_same<T, float>::value) {
-			FI_CUDA(cudaMemcpyAsync(x.data() + off, d_guess_own, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
-		} else {
-			convert(d_guess_own, reinterpret_cast<double*>(x.data()) + off, n, s);
+	PcgResult     r;
+	long long     widened_after = -1;
+	if (!wide) {
+		DevBuf<float> x(g.N);
+		x.zero(s);
+		if (d_guess_own) { FI_CUDA(cudaMemcpyAsync(x.data() + off, d_guess_own, n * sizeof(float), cudaMemcpyDeviceToDevice, s)); }
+		r = slab_mgpcg_solve<float>(*op32, *mg, nullptr, x.data(), o.tolerance, o.max_iterations, s, 4);
+		FI_CUDA(cudaMemcpyAsync(d_out_own, x.data() + off, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+		// every rank sees the same all-reduced sums, so every rank takes the same decision
+		const bool budget_left = o.max_iterations <= 0 || r.iterations < o.max_iterations;
+		if (!r.converged && !r.zero_rhs && r.stalled && budget_left) {
+			widened_after = r.iterations;
+			wide          = true;
 		}
 	}
-	const PcgResult r = slab_mgpcg_solve<T>(*op, *mg, nullptr, x.data(), o.tolerance, o.max_iterations, s);
-	if (std::is_same<T, float>::value) {
-		FI_CUDA(cudaMemcpyAsync(d_out_own, x.data() + off, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
-	} else {
-		convert(reinterpret_cast<const double*>(x.data()) + off, d_out_own, n, s);
+	if (wide) {
+		Operator<double>& op = wide_operator();
+		DevBuf<double>    x(g.N);
+		x.zero(s);
+		const float* from = widened_after >= 0 ? d_out_own : d_guess_own;
+		if (from) { convert(from, x.data() + off, n, s); }
+		const long long cap = o.max_iterations > 0 ? o.max_iterations - std::max<long long>(widened_after, 0) : 0;
+		const PcgResult w   = slab_mgpcg_solve<double>(op, *mg, nullptr, x.data(), o.tolerance, cap, s);
+		convert(x.data() + off, d_out_own, n, s);
+		if (widened_after >= 0) {
+			PcgResult tot        = w;
+			tot.iterations       = r.iterations + w.iterations;
+			tot.solve_ms         = r.solve_ms + w.solve_ms;
+			tot.initial_residual = r.initial_residual;
+			r                    = tot;
+		} else {
+			r = w;
+		}
 	}
 	FI_CUDA(cudaStreamSynchronize(s));
-	float setup = 0;
-	FI_CUDA(cudaEventElapsedTime(&setup, e0, e1));
-	cudaEventDestroy(e0);
-	cudaEventDestroy(e1);
+	const double setup = e1.ms_since(e0);
 	if (st) {
 		std::memset(st, 0, sizeof(*st));
 		st->iterations        = r.iterations;
@@ -414,8 +430,9 @@ void slab_mg_solve_typed(fi_comm* c, const Geom& g, const SlabMgPlan& plan, cons
 		st->setup_ms          = setup;
 		st->solve_ms          = r.solve_ms;
 		st->converged         = r.converged ? 1 : 0;
-		st->occupied_cells    = op->data.nocc;
-		st->generic_rows      = op->data.nrows;
+		st->occupied_cells    = op32->data.nocc;
+		st->generic_rows      = op32->data.nrows;
+		st->widened_after     = widened_after;
 	}
 }
 
@@ -497,10 +514,8 @@ void slab_sdf_solve(fi_comm* c, const int32_t* sizes, const fi_weights& w, int64
 				gptr = d_guess.data();
 			}
 		}
-		if (multigrid && o.precision == FI_F32) {
-			slab_mg_solve_typed<float>(c, g, plan, model, pts, o, gptr, optr, st, s);
-		} else if (multigrid) {
-			slab_mg_solve_typed<double>(c, g, plan, model, pts, o, gptr, optr, st, s);
+		if (multigrid) {
+			slab_mg_solve(c, g, plan, model, pts, o, o.precision != FI_F32, gptr, optr, st, s);
 		} else if (o.precision == FI_F32) {
 			slab_solve_typed<float>(c, g, halo, model, pts, o, gptr, optr, st, s);
 		} else {

@@ -129,6 +129,12 @@ struct DataTerm
 	DevBuf<int64_t>    cell_base; // local index of the cell's corner 0 (may lie outside the lattice: see cell_mask)
 	DevBuf<uint32_t>   cell_mask; // bits 0..7: corner is a lattice node; bits 8..15: ... whose row this process owns
 	DevBuf<T>          blocks;    // [tri(2^D)][nocc]
+	// The same matrix P = sum of the cell blocks, node-major (what the solver applies): for every lattice node that is a
+	// corner of an occupied cell (and whose row this process owns) the 3^D coefficients of its row, so that q += P p is a
+	// gather with one writer per node — no atomics, bit-reproducible.
+	int64_t            nnode = 0;
+	DevBuf<int64_t>    node_index; // [nnode] local index of the node, ascending
+	DevBuf<T>          node_coef;  // [3^D][nnode]; slot = sum_d (delta_d + 1) 3^d for the neighbour at offset delta in {-1,0,1}^D
 	int64_t            nrows = 0; // generic rows (derived + caller-appended)
 	DevBuf<uint64_t>   row_ptr;   // nrows + 1
 	DevBuf<int32_t>    col;

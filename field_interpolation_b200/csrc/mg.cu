@@ -978,7 +978,7 @@ void SlabMultigrid::vcycle(const float* r, float* z, cudaStream_t s) { slab_vcyc
 namespace {
 
 template <typename T, typename Precond>
-PcgResult mgpcg_impl(Operator<T>& op, Precond& mg, const T* b, T* x, double tol, long long max_iter, cudaStream_t s)
+PcgResult mgpcg_impl(Operator<T>& op, Precond& mg, const T* b, T* x, double tol, long long max_iter, cudaStream_t s, int guard_every)
 {
 	TraceScope    trace("mgpcg_solve");
 	DistHooks*    dist = op.dist;
@@ -1036,7 +1036,10 @@ PcgResult mgpcg_impl(Operator<T>& op, Precond& mg, const T* b, T* x, double tol,
 			}
 			read(h, 1);
 			const double rz_new = h[0];
-			if (!(rz_new > 0.0) || !std::isfinite(rz_new)) { break; }  // breakdown: keep the last iterate
+			if (!(rz_new > 0.0) || !std::isfinite(rz_new)) {  // breakdown: keep the last iterate
+				res.stalled = true;
+				break;
+			}
 			const double beta = it == 0 ? 0.0 : rz_new / rz;
 			rz                = rz_new;
 			{
@@ -1047,7 +1050,10 @@ PcgResult mgpcg_impl(Operator<T>& op, Precond& mg, const T* b, T* x, double tol,
 			op.apply(p.data(), q.data(), out.data(), nullptr, s);
 			read(h, 1);
 			const double pq = h[0];
-			if (!(pq > 0.0) || !std::isfinite(pq)) { break; }
+			if (!(pq > 0.0) || !std::isfinite(pq)) {
+				res.stalled = true;
+				break;
+			}
 			const double alpha = rz / pq;
 			{
 				auto k = mg_update_kernel<T>;
@@ -1058,6 +1064,19 @@ PcgResult mgpcg_impl(Operator<T>& op, Precond& mg, const T* b, T* x, double tol,
 			rr = h[0];
 			++it;
 			if (rr <= target) { break; }
+			if (!std::isfinite(rr)) {
+				res.stalled = true;
+				break;
+			}
+			if (guard_every > 0 && it % guard_every == 0) {
+				// does the recurrence still describe x?  (q is free between iterations; the operator's own work vectors carry A x)
+				double trr = 0, tbb = 0;
+				residual<T>(op, rhs, x, nullptr, &trr, &tbb, s);
+				if (!(trr <= 4.0 * rr)) {  // |b - A x| > 2 |r|: the floor of this arithmetic
+					res.stalled = true;
+					break;
+				}
+			}
 		}
 	}
 	FI_CUDA(cudaEventRecord(e1, s));
@@ -1076,6 +1095,10 @@ PcgResult mgpcg_impl(Operator<T>& op, Precond& mg, const T* b, T* x, double tol,
 		double trr = 0, tbb = 0;
 		residual<T>(op, rhs, x, nullptr, &trr, &tbb, s);
 		res.true_residual = tbb > 0 ? std::sqrt(trr / tbb) : 0.0;
+		// the stopping rule must hold for the residual of x itself, not merely for the recurrence
+		const bool recurrence_met = res.converged;
+		res.converged             = res.true_residual <= kConvergedSlack * tol;
+		if (recurrence_met && !res.converged) { res.stalled = true; }
 	}
 	return res;
 }
@@ -1083,22 +1106,22 @@ PcgResult mgpcg_impl(Operator<T>& op, Precond& mg, const T* b, T* x, double tol,
 }  // namespace
 
 template <typename T>
-PcgResult mgpcg_solve(Operator<T>& op, Multigrid& mg, const T* b, T* x, double tol, long long max_iter, cudaStream_t s)
+PcgResult mgpcg_solve(Operator<T>& op, Multigrid& mg, const T* b, T* x, double tol, long long max_iter, cudaStream_t s, int guard_every)
 {
 	FI_REQUIRE(op.dist == nullptr && !op.g.sharded(), FI_ERR_UNSUPPORTED, "mgpcg_solve takes an unsharded lattice (slabs: slab_mgpcg_solve)");
-	return mgpcg_impl<T, Multigrid>(op, mg, b, x, tol, max_iter, s);
+	return mgpcg_impl<T, Multigrid>(op, mg, b, x, tol, max_iter, s, guard_every);
 }
 
 template <typename T>
-PcgResult slab_mgpcg_solve(Operator<T>& op, SlabMultigrid& mg, const T* b, T* x, double tol, long long max_iter, cudaStream_t s)
+PcgResult slab_mgpcg_solve(Operator<T>& op, SlabMultigrid& mg, const T* b, T* x, double tol, long long max_iter, cudaStream_t s, int guard_every)
 {
 	FI_REQUIRE(op.dist != nullptr, FI_ERR_INVALID, "slab_mgpcg_solve needs the slab's communicator hooks");
-	return mgpcg_impl<T, SlabMultigrid>(op, mg, b, x, tol, max_iter, s);
+	return mgpcg_impl<T, SlabMultigrid>(op, mg, b, x, tol, max_iter, s, guard_every);
 }
 
-template PcgResult mgpcg_solve<float>(Operator<float>&, Multigrid&, const float*, float*, double, long long, cudaStream_t);
-template PcgResult mgpcg_solve<double>(Operator<double>&, Multigrid&, const double*, double*, double, long long, cudaStream_t);
-template PcgResult slab_mgpcg_solve<float>(Operator<float>&, SlabMultigrid&, const float*, float*, double, long long, cudaStream_t);
-template PcgResult slab_mgpcg_solve<double>(Operator<double>&, SlabMultigrid&, const double*, double*, double, long long, cudaStream_t);
+template PcgResult mgpcg_solve<float>(Operator<float>&, Multigrid&, const float*, float*, double, long long, cudaStream_t, int);
+template PcgResult mgpcg_solve<double>(Operator<double>&, Multigrid&, const double*, double*, double, long long, cudaStream_t, int);
+template PcgResult slab_mgpcg_solve<float>(Operator<float>&, SlabMultigrid&, const float*, float*, double, long long, cudaStream_t, int);
+template PcgResult slab_mgpcg_solve<double>(Operator<double>&, SlabMultigrid&, const double*, double*, double, long long, cudaStream_t, int);
 
 }  // namespace fi

@@ -788,6 +788,11 @@ PcgResult pcg_solve(Operator<T>& op, const T* b, T* x, double tol, long long max
 		double rr = 0, bb = 0;
 		residual<T>(op, rhs, x, nullptr, &rr, &bb, s);
 		res.true_residual = bb > 0 ? std::sqrt(rr / bb) : 0.0;
+		// the stopping rule must hold for the residual of x itself, not merely for the recurrence (fp32 on a large
+		// lattice: the recurrence keeps falling after b - A x has reached its rounding floor)
+		const bool recurrence_met = res.converged;
+		res.converged             = res.true_residual <= kConvergedSlack * tol;
+		res.stalled               = (recurrence_met && !res.converged) || h.breakdown != 0;
 	}
 	return res;
 }

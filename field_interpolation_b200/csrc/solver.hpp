@@ -142,7 +142,15 @@ struct PcgResult
 	double    rel_residual = 0, initial_residual = 0, true_residual = 0, solve_ms = 0;
 	double    loop_ms = 0;  // graph launches only (no init, capture or instantiation)
 	bool      converged = false, zero_rhs = false;
+	// The iteration cannot get further in this arithmetic: CG broke down, or the residual recomputed from x stopped
+	// following the recurrence (an fp32 solve at the rounding floor of an ill-conditioned system).  The caller may continue
+	// from x in wider arithmetic.
+	bool      stalled = false;
 };
+
+// `converged` means the TRUE residual met the stopping rule, with this much slack on |r| for the difference between the
+// recurrence (which decided when to stop) and the residual recomputed from x.
+constexpr double kConvergedSlack = 1.25;
 
 // Solves A x = b from the guess in x (device, N elements of T).  b == nullptr: the operator's own A^T b.
 // With op.dist set, x / b are local slab vectors (halo planes included) and every rank calls this together.
@@ -266,12 +274,14 @@ struct SlabMultigrid
 std::unique_ptr<SlabMultigrid> build_slab_multigrid(Operator<float>& fine, const ModelAccum& model, const PointStore& pts, const MgOptions& opt,
                                                     const SlabMgPlan& plan, cudaStream_t s);
 
-// CG preconditioned by one V-cycle per iteration; same contract as pcg_solve.
+// CG preconditioned by one V-cycle per iteration; same contract as pcg_solve.  guard_every > 0: every that many
+// iterations the residual is recomputed from x, and the solve stops with `stalled` set once it is more than twice the
+// recurrence residual (the floor of the arithmetic T has been reached; see PcgResult::stalled).
 template <typename T>
-PcgResult mgpcg_solve(Operator<T>& op, Multigrid& mg, const T* b, T* x, double tol, long long max_iter, cudaStream_t s);
+PcgResult mgpcg_solve(Operator<T>& op, Multigrid& mg, const T* b, T* x, double tol, long long max_iter, cudaStream_t s, int guard_every = 0);
 // The same on a slab (op.dist set; x / b are slab-local vectors, every rank calls this together).
 template <typename T>
-PcgResult slab_mgpcg_solve(Operator<T>& op, SlabMultigrid& mg, const T* b, T* x, double tol, long long max_iter, cudaStream_t s);
+PcgResult slab_mgpcg_solve(Operator<T>& op, SlabMultigrid& mg, const T* b, T* x, double tol, long long max_iter, cudaStream_t s, int guard_every = 0);
 
 // Tile phase of solve_tiled_with_guess (reference sparse_linear.cpp:246-390): x holds the guess on entry and the
 // tile-by-tile solution on exit.  The returned statistics are those of the block-diagonal solve.

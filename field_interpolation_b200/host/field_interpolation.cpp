@@ -27,10 +27,11 @@ static fi_weights to_c(const Weights& w)
 	return c;
 }
 
-bool forward_tail_rows(const LinearEquation& eq, Structured* st)
+Forwarded forward_tail_rows(const LinearEquation& eq, Structured* st)
 {
-	if (eq.rhs.size() <= st->eq_rows && eq.triplets.size() <= st->eq_triplets) { return true; }
-	if (eq.rhs.size() < st->eq_rows || eq.triplets.size() < st->eq_triplets) { return false; }  // eq was truncated: not ours any more
+	if (eq.rhs.size() == st->eq_rows && eq.triplets.size() == st->eq_triplets) { return Forwarded::kOk; }
+	// the list shrank (clear(), resize, assignment from a shorter system): what the handle holds is not a prefix of it any more
+	if (eq.rhs.size() < st->eq_rows || eq.triplets.size() < st->eq_triplets) { return Forwarded::kInconsistent; }
 	const size_t nrows = eq.rhs.size() - st->eq_rows, ntrip = eq.triplets.size() - st->eq_triplets;
 	std::vector<int32_t> r(ntrip), c(ntrip);
 	std::vector<float>   v(ntrip);
@@ -38,7 +39,7 @@ bool forward_tail_rows(const LinearEquation& eq, Structured* st)
 	for (size_t k = 0; k < ntrip; ++k) {
 		const Triplet& t = eq.triplets[st->eq_triplets + k];
 		const long long rel = static_cast<long long>(t.row) - static_cast<long long>(st->eq_rows);
-		if (rel < 0 || rel >= static_cast<long long>(nrows)) { return false; }
+		if (rel < 0 || rel >= static_cast<long long>(nrows)) { return Forwarded::kInconsistent; }
 		r[k] = static_cast<int32_t>(rel);
 		c[k] = t.col;
 		v[k] = t.value;
@@ -60,13 +61,36 @@ bool forward_tail_rows(const LinearEquation& eq, Structured* st)
 		c.swap(c2);
 		v.swap(v2);
 	}
+	// fi_field_add_rows validates before it stores anything: a refused call leaves the handle as it was
 	if (fi_field_add_rows(st->handle, static_cast<int64_t>(nrows), static_cast<int64_t>(ntrip), r.data(), c.data(), v.data(),
 	                      eq.rhs.data() + st->eq_rows) != FI_OK) {
-		return false;
+		return Forwarded::kError;
 	}
 	st->eq_rows     = eq.rhs.size();
 	st->eq_triplets = eq.triplets.size();
-	return true;
+	return Forwarded::kOk;
+}
+
+std::shared_ptr<Structured> clone_description(const Structured& src)
+{
+	auto st = std::make_shared<Structured>();
+	if (fi_field_clone(src.handle, &st->handle) != FI_OK) { return nullptr; }
+	st->sizes       = src.sizes;
+	st->deferred    = src.deferred;
+	st->eq_rows     = src.eq_rows;
+	st->eq_triplets = src.eq_triplets;
+	return st;
+}
+
+std::shared_ptr<Structured> description_from_triplets(const LinearEquation& eq, const std::vector<int>& sizes)
+{
+	if (sizes.empty() || static_cast<int>(sizes.size()) > MAX_DIM) { return nullptr; }
+	auto st   = std::make_shared<Structured>();
+	st->sizes = sizes;
+	std::vector<int32_t> sz(sizes.begin(), sizes.end());
+	if (fi_field_create(static_cast<int32_t>(sz.size()), sz.data(), &st->handle) != FI_OK) { return nullptr; }
+	if (forward_tail_rows(eq, st.get()) != Forwarded::kOk) { return nullptr; }
+	return st;
 }
 
 Structured* structured_for_append(LatticeField* field)
@@ -80,9 +104,22 @@ Structured* structured_for_append(LatticeField* field)
 		if (fi_field_create(static_cast<int32_t>(sz.size()), sz.data(), &st->handle) != FI_OK) { return nullptr; }
 		eq.structured = st;
 	}
-	Structured* st = eq.structured.get();
-	if (!forward_tail_rows(eq, st)) { return nullptr; }
-	return st;
+	// a copied LatticeField / LinearEquation shares the description with its source until one of them is written to
+	if (eq.structured.use_count() > 1) {
+		auto own = clone_description(*eq.structured);
+		if (!own) { return nullptr; }
+		eq.structured = own;
+	}
+	Structured*     st  = eq.structured.get();
+	const Forwarded fwd = forward_tail_rows(eq, st);
+	if (fwd == Forwarded::kInconsistent && !st->deferred) {
+		// the caller rewrote eq (cleared it, assigned another system): the triplet list is the truth, start again from it
+		auto fresh = description_from_triplets(eq, field->sizes);
+		if (!fresh) { return nullptr; }
+		eq.structured = fresh;
+		return fresh.get();
+	}
+	return fwd == Forwarded::kOk ? st : nullptr;
 }
 
 bool mirror_new_rows(LinearEquation* eq, Structured* st, long long rows_before, long long trips_before)

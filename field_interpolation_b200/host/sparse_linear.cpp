@@ -74,20 +74,26 @@ static Structured* description_of(const LinearEquation& eq, long long num_column
 		long long n = 1;
 		for (int s : st->sizes) { n *= s; }
 		const bool shape_ok = !lattice || st->sizes == *lattice;
-		if (shape_ok && (num_columns <= 0 || n == num_columns) && forward_tail_rows(eq, st)) { return st; }
+		if (shape_ok && (num_columns <= 0 || n == num_columns)) {
+			const bool pending = eq.rhs.size() != st->eq_rows || eq.triplets.size() != st->eq_triplets;
+			if (pending && eq.structured.use_count() > 1) {
+				// hand-written rows wait to be forwarded and the description is shared with a copy of this equation:
+				// forward them into a private clone, the other owner must not see them
+				*temp = clone_description(*st);
+				st    = temp->get();
+				if (!st) { return nullptr; }
+			}
+			const Forwarded fwd = forward_tail_rows(eq, st);
+			if (fwd == Forwarded::kOk) { return st; }
+			if (fwd == Forwarded::kError || st->deferred) { return nullptr; }
+			// kInconsistent: eq was rewritten since the handle was built; fall through to the triplet list itself
+		}
 	}
 	if (num_columns <= 0) { return nullptr; }
-	auto g   = std::make_shared<Structured>();
-	g->sizes = {static_cast<int>(num_columns)};
-	if (lattice) {
-		if (lattice->empty() || lattice->size() > 3) { return nullptr; }
-		g->sizes = *lattice;
-	}
-	std::vector<int32_t> sz(g->sizes.begin(), g->sizes.end());
-	if (fi_field_create(static_cast<int32_t>(sz.size()), sz.data(), &g->handle) != FI_OK) { return nullptr; }
-	if (!forward_tail_rows(eq, g.get())) { return nullptr; }
-	*temp = g;
-	return g.get();
+	std::vector<int> sizes = {static_cast<int>(num_columns)};
+	if (lattice) { sizes = *lattice; }
+	*temp = description_from_triplets(eq, sizes);
+	return temp->get();
 }
 
 std::vector<float> solve(const LinearEquation& eq, int num_columns, Precision precision, const std::vector<float>* guess, int max_iterations,

@@ -4,6 +4,7 @@
 #pragma once
 
 #include <cstdint>
+#include <memory>
 #include <vector>
 
 #include "../../include/fi_b200.h"
@@ -35,8 +36,17 @@ struct Structured
 // Returns nullptr when the library reports an error (b200::last_error() has the text).
 Structured* structured_for_append(LatticeField* field);
 
-// Forwards rows of `eq` beyond what `st` already accounts for.  False on error.
-bool forward_tail_rows(const LinearEquation& eq, Structured* st);
+// Forwards rows of `eq` beyond what `st` already accounts for (as generic rows).  kInconsistent: eq is no longer an
+// extension of what the handle holds (it was cleared, truncated or re-assigned) — nothing was forwarded and the
+// handle must not be used for this eq; kError: the library refused the rows (handle unchanged).
+enum class Forwarded { kOk, kInconsistent, kError };
+Forwarded forward_tail_rows(const LinearEquation& eq, Structured* st);
+
+// An independent deep copy of a description (fi_field_clone); nullptr on error.
+std::shared_ptr<Structured> clone_description(const Structured& src);
+
+// A fresh description of the lattice `sizes` holding all of eq as generic rows; nullptr on error.
+std::shared_ptr<Structured> description_from_triplets(const LinearEquation& eq, const std::vector<int>& sizes);
 
 // After a builder call on st->handle: mirrors the rows added since `rows_before` into eq (unless deferred).
 bool mirror_new_rows(LinearEquation* eq, Structured* st, long long rows_before, long long trips_before);

@@ -26,7 +26,7 @@ extern "C" {
 #endif
 
 /* 2: + fi_marching_squares, fi_calc_area, fi_bicubic_upsample, fi_slab_balanced_cuts, fi_comm_set_slab_cuts (additions only) */
-#define FI_B200_ABI_VERSION 2
+#define FI_B200_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define FI_API __attribute__((visibility("default")))
@@ -98,10 +98,14 @@ typedef struct fi_solve_stats {
 	double  initial_residual;  /* |Atb - AtA guess|/|Atb| */
 	double  setup_ms;          /* operator build: sort, scatter, diagonal (device time) */
 	double  solve_ms;          /* iteration loop (device time) */
-	int32_t converged;         /* 1 if the stopping rule was met */
+	int32_t converged;         /* 1 if the stopping rule was met by the TRUE residual (recomputed from x), not merely by the
+	                            * recurrence: an fp32 solve that stalls at its rounding floor reports 0 */
 	int32_t outer_sweeps;      /* FI_MIXED only */
 	int64_t occupied_cells;    /* cells holding at least one data row */
 	int64_t generic_rows;      /* rows applied through the COO fallback */
+	int64_t widened_after;     /* -1: the solve ran in the requested arithmetic throughout.  k >= 0: an FI_F32 multigrid solve
+	                            * reached the fp32 rounding floor of this system (or broke down) after k iterations and was
+	                            * continued from that iterate with the fp64 outer CG (FI_MIXED); `iterations` counts both */
 } fi_solve_stats;
 
 typedef struct fi_field fi_field; /* opaque: one LatticeField (field_interpolation.hpp:97-114) on one GPU */
@@ -118,6 +122,11 @@ FI_API void        fi_solve_options_default(fi_solve_options* o);
 /* LatticeField{sizes}, field_interpolation.hpp:104-111.  1 <= ndim <= 3 (MAX_DIM, :44). */
 FI_API int fi_field_create(int32_t ndim, const int32_t* sizes, fi_field** out);
 FI_API int fi_field_destroy(fi_field* f);
+/* Deep copy of everything a field holds (model calls, point records, caller rows).  The reference's LatticeField is a
+ * plain value type (field_interpolation.hpp:97-114: `b = a` copies the triplet list); the C++ host layer clones the
+ * device description the first time a copied LatticeField / LinearEquation is appended to, so the copies stay
+ * independent. */
+FI_API int fi_field_clone(const fi_field* f, fi_field** out);
 
 /* ---- builders (each call appends rows after all earlier ones, like the reference) ---------- */
 /* add_field_constraints, field_interpolation.cpp:326-341 (+ add_model_constraint :243-316). */

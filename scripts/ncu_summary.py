@@ -27,21 +27,32 @@ def short(name):
 
 
 def launches(path):
+    """Launch list of a `--metrics gpu__time_duration.sum[,dram__bytes_read.sum,dram__bytes_write.sum]` pass: time per
+    kernel and, when the DRAM byte counters were collected too, the DRAM GB/s each kernel sustained."""
     lines = [l for l in open(path) if not l.startswith("==")]
     agg = collections.OrderedDict()
+    scale_t = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6, "nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3, "second": 1e6}
+    scale_b = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    have_bytes = False
     for row in csv.DictReader(lines):
-        if row.get("Metric Name") != "gpu__time_duration.sum":
+        m = row.get("Metric Name")
+        if m not in ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum"):
             continue
         v = float(row["Metric Value"].replace(",", ""))
-        v = {"ns": v / 1e3, "us": v, "ms": v * 1e3, "s": v * 1e6}.get(row["Metric Unit"], v)
         key = (short(row["Kernel Name"]), row["Grid Size"], row["Block Size"])
-        a = agg.setdefault(key, [0, 0.0])
-        a[0] += 1
-        a[1] += v
+        a = agg.setdefault(key, [0, 0.0, 0.0])
+        if m == "gpu__time_duration.sum":
+            a[0] += 1
+            a[1] += v * scale_t.get(row["Metric Unit"], 1.0)
+        else:
+            have_bytes = True
+            a[2] += v * scale_b.get(row["Metric Unit"], 1.0)
     tot = sum(v[1] for v in agg.values())
-    print(f"| kernel | grid | block | launches | total us | share | avg us |\n|---|---|---|---:|---:|---:|---:|")
+    extra_h = " DRAM MB / launch | DRAM GB/s |" if have_bytes else ""
+    print(f"| kernel | grid | block | launches | total us | share | avg us |{extra_h}\n|---|---|---|---:|---:|---:|---:|" + ("---:|---:|" if have_bytes else ""))
     for (k, g, b), v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-        print(f"| `{k}` | {g} | {b} | {v[0]} | {v[1]:.1f} | {100 * v[1] / tot:.1f}% | {v[1] / v[0]:.1f} |")
+        extra = f" {v[2] / v[0] / 1e6:.2f} | {v[2] / (v[1] * 1e-6) / 1e9:.0f} |" if have_bytes else ""
+        print(f"| `{k}` | {g} | {b} | {v[0]} | {v[1]:.1f} | {100 * v[1] / tot:.1f}% | {v[1] / v[0]:.1f} |{extra}")
     print(f"\ntotal {tot:.1f} us over {sum(v[0] for v in agg.values())} launches (ncu per-launch times: cold-cache, serialised)")
 
 

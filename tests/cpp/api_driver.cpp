@@ -249,6 +249,46 @@ static int scenario_deferred_3d()
 	return 0;
 }
 
+// LatticeField / LinearEquation are plain value types in the reference (field_interpolation.hpp:97-114,
+// sparse_linear.hpp:18-22): a copy is an independent system, and callers may clear or rewrite eq between calls.
+static int scenario_value_semantics()
+{
+	const int n = 14;
+	fi::Weights w;
+	fi::LatticeField a{{n, n}};
+	add_field_constraints(&a, w);
+	const float p0[2] = {3.25f, 4.5f}, p1[2] = {9.75f, 8.125f}, p2[2] = {6.5f, 2.25f};
+	add_value_constraint(&a, p0, 1.0f, 1.0f);
+	add_value_constraint(&a, p1, -2.0f, 1.0f);
+	fi::LatticeField b = a;  // shares nothing observable with a from here on
+	add_value_constraint(&b, p2, 5.0f, 2.0f);
+	add_equation(&b.eq, fi::Weight{1.5f}, fi::Rhs{0.25f}, {{0, 1.0f}, {n * n - 1, -1.0f}});
+	put_i("a_counts", {static_cast<int>(a.eq.rhs.size()), static_cast<int>(a.eq.triplets.size())});
+	put_f("a_exact", solve_sparse_linear_exact(a.eq, n * n));
+	put_f("b_exact", solve_sparse_linear_exact(b.eq, n * n));
+	put_f("a_again", solve_sparse_linear_exact(a.eq, n * n));  // b's solve (which forwarded b's hand-written row) left a alone
+	// a copy with pending hand-written rows on the ORIGINAL: the copy must not see them
+	fi::LatticeField c = a;
+	add_equation(&a.eq, fi::Weight{3.0f}, fi::Rhs{1.0f}, {{5, 1.0f}});
+	put_f("a_plus_row", solve_sparse_linear_exact(a.eq, n * n));
+	put_f("c_exact", solve_sparse_linear_exact(c.eq, n * n));
+	// the caller empties the equation and builds another system in the same field object
+	fi::LatticeField d = b;
+	d.eq.triplets.clear();
+	d.eq.rhs.clear();
+	add_field_constraints(&d, w);
+	add_value_constraint(&d, p2, 7.0f, 1.0f);
+	put_i("d_counts", {static_cast<int>(d.eq.rhs.size()), static_cast<int>(d.eq.triplets.size())});
+	put_f("d_exact", solve_sparse_linear_exact(d.eq, n * n));
+	// ... or truncates it (drops the last constraint) and solves without another builder call
+	fi::LatticeField e = b;  // b's description already holds its hand-written row (2 triplets): e.eq is no extension of it any more
+	e.eq.rhs.pop_back();
+	e.eq.triplets.pop_back();
+	e.eq.triplets.pop_back();
+	put_f("e_exact", solve_sparse_linear_exact(e.eq, n * n));
+	return 0;
+}
+
 // reference src/sdf_field.cpp:660-670 — what the demo does with a solved 2D field: optional bicubic upsampling, the zero
 // contour by marching squares, its area relative to the lattice; plus one off-zero iso line (:701).
 static int scenario_iso_2d(const char* in_path)
@@ -298,6 +338,7 @@ int main(int argc, char** argv)
 	else if (sc == "iso_2d" && argc > 3) { rc = scenario_iso_2d(argv[3]); }
 	else if (sc == "hand_rows") { rc = scenario_hand_rows(); }
 	else if (sc == "deferred_3d") { rc = scenario_deferred_3d(); }
+	else if (sc == "value_semantics") { rc = scenario_value_semantics(); }
 	std::fclose(g_out);
 	if (rc != 0) { std::fprintf(stderr, "scenario %s failed (%d): %s\n", sc.c_str(), rc, fi::b200::last_error()); }
 	return rc;

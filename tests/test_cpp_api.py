@@ -190,6 +190,45 @@ def test_hand_written_rows_without_a_lattice(tmp_path, port):
 
 
 @pytest.mark.gpu
+def test_copies_are_independent_and_rewritten_equations_are_noticed(tmp_path, port):
+    """LatticeField is a value type in the reference (field_interpolation.hpp:97-114): `b = a` copies the system.  Here
+    the device description is shared until somebody writes (clone on write), hand-written rows pending on one owner never
+    reach the other, and an equation the caller cleared or truncated is rebuilt from its triplet list."""
+    got = _run("value_semantics", tmp_path)
+    n = 14
+    w = O.make_weights()
+    p0, p1, p2 = [3.25, 4.5], [9.75, 8.125], [6.5, 2.25]
+
+    def base():
+        f = port.field([n, n])
+        f.add_field_constraints(w)
+        f.add_value_constraint(p0, 1.0, 1.0)
+        f.add_value_constraint(p1, -2.0, 1.0)
+        return f
+    a = base().system()
+    assert list(got["a_counts"]) == [a.num_rows, a.num_triplets]
+    xa = O.exact_solve(a, n * n)
+    assert rel(got["a_exact"], xa) <= 1e-5 and rel(got["a_again"], xa) <= 1e-5 and rel(got["c_exact"], xa) <= 1e-5
+    fb = base()
+    fb.add_value_constraint(p2, 5.0, 2.0)
+    fb.add_equation(1.5, 0.25, [0, n * n - 1], [1.0, -1.0])
+    xb = O.exact_solve(fb.system(), n * n)
+    assert rel(got["b_exact"], xb) <= 1e-5 and rel(xa, xb) > 1e-2  # the two systems really differ
+    fa2 = base()
+    fa2.add_equation(3.0, 1.0, [5], [1.0])
+    assert rel(got["a_plus_row"], O.exact_solve(fa2.system(), n * n)) <= 1e-5
+    fd = port.field([n, n])
+    fd.add_field_constraints(w)
+    fd.add_value_constraint(p2, 7.0, 1.0)
+    d = fd.system()
+    assert list(got["d_counts"]) == [d.num_rows, d.num_triplets]
+    assert rel(got["d_exact"], O.exact_solve(d, n * n)) <= 1e-5
+    fe = base()
+    fe.add_value_constraint(p2, 5.0, 2.0)
+    assert rel(got["e_exact"], O.exact_solve(fe.system(), n * n)) <= 1e-5  # b without its hand-written row
+
+
+@pytest.mark.gpu
 def test_deferred_triplets_3d(tmp_path, port):
     got = _run("deferred_3d", tmp_path)
     n = 20

@@ -234,6 +234,9 @@ def test_cascade_matches_manual_recipe(fi, port):
 
 
 # ---- multigrid-preconditioned CG (FI_PRECOND_MULTIGRID): same system, same stopping rule, different preconditioner ----
+_EXACT_CACHE = {}
+
+
 @pytest.mark.parametrize("sizes,npts", [([97], 20), ([40, 37], 400), ([65, 64], 900), ([24, 20, 22], 1500), ([48, 33, 40], 4000)])
 @pytest.mark.parametrize("prec", ["f32", "f64"])
 def test_multigrid_pcg_vs_exact(fi, port, sizes, npts, prec):
@@ -247,9 +250,11 @@ def test_multigrid_pcg_vs_exact(fi, port, sizes, npts, prec):
         cloud = W.circles_2d(npts, seed=2) if D == 2 else W.sphere_torus_3d(npts, seed=2)
     pos = W.to_lattice(cloud["unit_pos"], sizes)
     f = fi.sdf_from_points(sizes, fi.Weights(), pos, cloud["normals"])
-    sys_ = port.sdf_from_points(sizes, O.make_weights(), pos, cloud["normals"]).system()
     n = int(np.prod(sizes))
-    exact = O.exact_solve(sys_, n)
+    if tuple(sizes) not in _EXACT_CACHE:  # the sparse direct solve of the largest case takes over a minute of host time
+        sys_ = port.sdf_from_points(sizes, O.make_weights(), pos, cloud["normals"]).system()
+        _EXACT_CACHE[tuple(sizes)] = O.exact_solve(sys_, n)
+    exact = _EXACT_CACHE[tuple(sizes)]
     if prec == "f64":
         x, st = f.solve(fi.solve_options(fi.FI_F64, 0, 1e-11, preconditioner=fi.FI_PRECOND_MULTIGRID))
         assert st["converged"] and rel(x, exact) <= TOL_F64, st

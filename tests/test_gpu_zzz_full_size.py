@@ -137,9 +137,26 @@ def test_full_size_solve_to_1e6_independent_residual(fi, full):
     # ... and so does the residual recomputed here from the returned float32 field, up to what that narrowing costs:
     # |A dx| <= |A|_inf |dx|, |A|_inf <= 16 w2^2 D + data term < 20 with default Weights, |dx| <= 2^-24 |x|
     assert np.linalg.norm(r) <= 1.0e-6 * np.linalg.norm(rhs) + 20.0 * 2.0 ** -24 * np.linalg.norm(x64)
+    # FI_F32: the outer CG starts in fp32; on these lattices (cond ~ n^4) it reaches its rounding floor before 1e-6 — C3
+    # breaks down after a handful of iterations — and the library continues from that iterate with the fp64 outer CG.
+    # Whatever happened inside, `converged` speaks about the residual recomputed from x.
     x32, st32 = f.solve(fi.solve_options(fi.FI_F32, 500, 1e-6, preconditioner=fi.FI_PRECOND_MULTIGRID))
-    assert st32["iterations"] > 0
-    assert rel(x32, x64) <= TOL_F32
+    assert st32["iterations"] > 0 and st32["converged"] and st32["true_residual"] <= 1.25e-6, st32
+    r32 = rhs - f.apply(x32.astype(np.float64), fi.FI_F64)
+    assert np.linalg.norm(r32) <= 1.25e-6 * np.linalg.norm(rhs) + 20.0 * 2.0 ** -24 * np.linalg.norm(x32)
+    # solutions: at |r| = 1e-6 |b| the error is still ~6e-4 (C3; error / residual ~ 600), so two 1e-6 solves may differ by
+    # more than the north_star tolerance without either being wrong: compare at 1e-8, against a 1e-10 reference
+    x_ref, st_ref = f.solve(fi.solve_options(fi.FI_F64, 500, 1e-10, preconditioner=fi.FI_PRECOND_MULTIGRID))
+    assert st_ref["converged"]
+    x64b, st64b = f.solve(fi.solve_options(fi.FI_F64, 500, 1e-8, preconditioner=fi.FI_PRECOND_MULTIGRID))
+    assert st64b["converged"] and rel(x64b, x_ref) <= TOL_F64
+    x32b, st32b = f.solve(fi.solve_options(fi.FI_F32, 500, 1e-8, preconditioner=fi.FI_PRECOND_MULTIGRID))
+    assert st32b["converged"] and st32b["widened_after"] >= 0, st32b  # fp32 alone cannot reach 1e-8 here
+    assert rel(x32b, x_ref) <= TOL_F32
+    assert rel(x32, x_ref) <= 2e-3  # and the 1e-6 field is where error / residual ~ 600 puts it
+    # an fp32 Jacobi-PCG solve (the reference's float path, sparse_linear.cpp:186-212) that cannot meet its tolerance says so
+    x_j32, st_j32 = f.solve(fi.solve_options(fi.FI_F32, 64, 1e-9), guess=x64)
+    assert not st_j32["converged"] and rel(x_j32, x64) <= TOL_F32
     # Jacobi-PCG (the reference's preconditioner) from the multigrid solution stays there: same system, same fixed point
     x_j, st_j = f.solve(fi.solve_options(fi.FI_F64, 50, 1e-6), guess=x64)
     assert rel(x_j, x64) <= TOL_F64
