@@ -17,7 +17,7 @@ COMMON = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-l
           "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-I", os.path.join(HERE, "..", "include")]
 # assembly.cu and isosurface.cu restate the reference's scalar fp32 arithmetic bit for bit: no FMA contraction there.
 PER_FILE = {"assembly.cu": ["-fmad=false"], "isosurface.cu": ["-fmad=false"]}
-SOURCES = ["abi.cu", "assembly.cu", "sort_scan.cu", "stencil.cu", "stencil_fast.cu", "stencil_tma.cu", "solver.cu", "mg.cu", "errormap.cu", "isosurface.cu", "dist.cu"]
+SOURCES = ["abi.cu", "assembly.cu", "sort_scan.cu", "stencil.cu", "stencil_fast.cu", "stencil_tma.cu", "stencil_2d.cu", "solver.cu", "mg.cu", "errormap.cu", "isosurface.cu", "dist.cu"]
 
 
 def _stale(src, obj):

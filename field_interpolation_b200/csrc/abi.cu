@@ -212,14 +212,12 @@ struct fi_field
 	}
 	fi::Multigrid& get_mg(const fi_solve_options& o)
 	{
-		fi::MgOptions want;
-		want.nu = fi::default_smoothing_steps(model);
-		if (o.mg_smoothing_steps > 0) { want.nu = o.mg_smoothing_steps; }
-		if (o.mg_cheb_ratio > 1.0) { want.cheb_ratio = o.mg_cheb_ratio; }
-		if (const char* e = getenv("FI_B200_MG_COARSEST")) {  // tuning knob: cells of the dense coarsest level
-			if (atoi(e) > 0) { want.coarsest_cells = atoi(e); }
+		fi::MgOptions want = fi::default_mg_options(model, g, false, o.mg_smoothing_steps, o.mg_cheb_ratio);
+		fi::mg_options_from_env(want);
+		if (mg && (mg_opt.nu != want.nu || mg_opt.cheb_ratio != want.cheb_ratio || mg_opt.nu_coarse != want.nu_coarse || mg_opt.gamma != want.gamma ||
+		           mg_opt.coarsest_cells != want.coarsest_cells || mg_opt.w_levels != want.w_levels)) {
+			mg.reset();
 		}
-		if (mg && (mg_opt.nu != want.nu || mg_opt.cheb_ratio != want.cheb_ratio)) { mg.reset(); }
 		if (!mg) {
 			fi::Operator<float>& fine = get32();
 			fine.use_fast             = fi::kStencilAuto;
@@ -479,7 +477,10 @@ void solve_device(fi_field* f, const fi_solve_options& o, const float* d_guess, 
 		e1.sync();
 		const double setup = e1.ms_since(e0);
 		fill_stats(st, r, fresh ? setup : 0.0, f->op32 ? f->op32->data.nocc : 0, f->op32 ? f->op32->data.nrows : 0);
-		if (st) { st->widened_after = widened_after; }
+		if (st) {
+			st->widened_after = widened_after;
+			st->outer_sweeps  = mg.opt.gamma;  // the cycle the solve ended with: 1 V, 2 W (a W-cycle CG breaks down on is demoted)
+		}
 		FI_CUDA(cudaStreamSynchronize(s));
 		return;
 	}
@@ -610,7 +611,7 @@ void fi_solve_options_default(fi_solve_options* o)
 	o->refine_max_outer       = 20;
 	o->refine_inner_tolerance = 1e-3;
 	o->preconditioner         = FI_PRECOND_JACOBI;
-	o->mg_smoothing_steps     = 0;  // by the smoothness model: fi::default_smoothing_steps
+	o->mg_smoothing_steps     = 0;  // by the smoothness model and the lattice: fi::default_mg_options
 	o->mg_cheb_ratio          = 12.0;
 }
 

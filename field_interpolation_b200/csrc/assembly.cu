@@ -13,6 +13,7 @@
 #include <type_traits>
 
 #include "internal.hpp"
+#include "peer.cuh"
 
 namespace fi {
 
@@ -630,11 +631,21 @@ __global__ void __launch_bounds__(kThreads, 3) apply_blocks_kernel(Geom g, int64
                                                                 const uint32_t* __restrict__ cell_mask, const T* __restrict__ blocks,
                                                                 const T* __restrict__ p, T* __restrict__ q, double* partial,
                                                                 unsigned* ticket, double* dot_accum, const int* done,
-                                                                const uint64_t* __restrict__ cell_key)
+                                                                const uint64_t* __restrict__ cell_key, PeerPublish pub, int do_pub)
 {
 	constexpr int C = 1 << D;
 	__shared__ double red[32];
-	if (done && *done) { return; }
+	__shared__ double s_tot;
+	__shared__ int    s_pub;
+	if (done && *done) {
+		// a finished solve still publishes (zeros): the peers' kernels of this round are already waiting
+		if (do_pub && blockIdx.x == 0 && threadIdx.x < 32) {
+			const double zero[1] = {0.0};
+			peer_publish_warp(pub.link, pub.which, pub.par, seq_of(pub.base, pub.st, pub.which), zero, 1);
+		}
+		return;
+	}
+	if (threadIdx.x == 0) { s_pub = 0; }
 	const int64_t cell = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
 	double        mine[1] = {0.0};
 	if (cell < nocc) {
@@ -692,7 +703,20 @@ __global__ void __launch_bounds__(kThreads, 3) apply_blocks_kernel(Geom g, int64
 	}
 	if (dot_accum) {
 		mine[0] = block_sum(mine[0], red);
-		grid_sum<1>(mine, partial, ticket, red, [&](const double(&tot)[1]) { *dot_accum += tot[0]; });
+		grid_sum<1>(mine, partial, ticket, red, [&](const double(&tot)[1]) {
+			const double all = *dot_accum + tot[0];
+			*dot_accum       = all;
+			s_tot            = all;
+			s_pub            = 1;
+		});
+	}
+	if (do_pub) {  // the block that completed p.Ap of this rank sends it to every rank (solver.cu: peer-memory path)
+		__syncthreads();
+		if (s_pub && threadIdx.x < 32) {
+			const double v[1] = {s_tot};
+			if (threadIdx.x == 0) { pub.link.local->stamp[0][pub.st->iters & 511] = global_ns(); }
+			peer_publish_warp(pub.link, pub.which, pub.par, seq_of(pub.base, pub.st, pub.which), v, 1);
+		}
 	}
 }
 
@@ -1086,6 +1110,15 @@ void upscale_device(const Geom& small, const Geom& large, const float* d_small, 
 	FI_LAUNCH(upscale_kernel, div_up(large.N, kThreads), kThreads, 0, s, small, large, d_small, d_large, post_scale);
 }
 
+static bool node_major_data_term()
+{
+	static const bool v = [] {
+		const char* e = getenv("FI_B200_DATA_TERM");
+		return e && e[0] == 'n';
+	}();
+	return v;
+}
+
 // Node-major form of the cell blocks (DataTerm::node_index / node_coef), built once per operator.
 template <typename T>
 static void build_node_rows(const Geom& g, DataTerm<T>& out, cudaStream_t s)
@@ -1189,8 +1222,8 @@ void build_data_term(const Geom& g, const PointStore& pts, const HostRows& user,
 				auto kern = scatter_points_kernel<T, decltype(dim)::value>;
 				FI_LAUNCH(kern, grid, kThreads, 0, s, g, pv, order.data(), slot.data(), V, out.nocc, out.blocks.data(), d_atb, d_diag);
 			});
-			// 4'. the node-major form the solver applies (tile mode keeps using the blocks)
-			build_node_rows<T>(g, out, s);
+			// 4'. the node-major form, when it was asked for (tile mode keeps using the blocks)
+			if (node_major_data_term()) { build_node_rows<T>(g, out, s); }
 			FI_CUDA(cudaStreamSynchronize(s));
 		}
 	}
@@ -1237,22 +1270,26 @@ void build_data_term(const Geom& g, const PointStore& pts, const HostRows& user,
 	FI_CUDA(cudaStreamSynchronize(s));
 }
 
-// Which kernel applies the cell blocks: the node-major gather (default; no atomics), or — kept for comparison,
-// FI_B200_DATA_TERM=cell / split — one thread per cell / per (cell, row) with atomics into q.
-enum DataTermKernel { kDataNode, kDataCell, kDataSplit };
+// Which kernel applies the cell blocks.  Default: one thread per occupied cell, atomics into q.  Measured on the B200
+// (512^3, 1M points = 898k occupied cells, fp32; profiles/r2b_data_term_kernels.md): per cell 0.078 ms, per (cell, row)
+// 0.172 ms, node-major gather 0.192 ms.  The node-major form (FI_B200_DATA_TERM=node: no atomics, bit-reproducible) loses
+// on scattered clouds because nearly every cell holds one point and touches 8 nodes of its own: 27 coefficients for each
+// of ~6 nodes per cell against 36 per cell; it is kept for clouds dense enough to share nodes.
+enum DataTermKernel { kDataCell, kDataNode, kDataSplit };
 static DataTermKernel data_term_kernel()
 {
 	static const DataTermKernel v = [] {
 		const char* e = getenv("FI_B200_DATA_TERM");
-		return !e ? kDataNode : (e[0] == 'c' ? kDataCell : (e[0] == 's' ? kDataSplit : kDataNode));
+		return !e ? kDataCell : (e[0] == 'n' ? kDataNode : (e[0] == 's' ? kDataSplit : kDataCell));
 	}();
 	return v;
 }
 
 template <typename T>
-void apply_data_term(const Geom& g, const DataTerm<T>& dt, const T* p, T* q, double* d_dot_accum, const int* d_done,
-                     cudaStream_t s)
+bool apply_data_term(const Geom& g, const DataTerm<T>& dt, const T* p, T* q, double* d_dot_accum, const int* d_done,
+                     cudaStream_t s, const PeerPublish* pub)
 {
+	bool published = false;
 	const int gb = dt.nocc > 0 ? div_up(dt.nocc, kThreads) : 0;
 	const int gr = dt.nrows > 0 ? div_up(dt.nrows, kThreads) : 0;
 	const int gp = dt.nocc > 0 ? div_up(std::max(dt.nocc, dt.nnode), kThreads) : 0;  // partial sums of the rows kernel start behind the widest block / node grid
@@ -1263,7 +1300,7 @@ void apply_data_term(const Geom& g, const DataTerm<T>& dt, const T* p, T* q, dou
 			if (g.tile) {
 				auto kern = apply_blocks_kernel<T, decltype(dim)::value, true>;
 				FI_LAUNCH(kern, gb, kThreads, 0, s, g, dt.nocc, dt.cell_base.data(), dt.cell_mask.data(), dt.blocks.data(), p, q, partial, ticket,
-				          d_dot_accum, d_done, dt.cell_key.data());
+				          d_dot_accum, d_done, dt.cell_key.data(), PeerPublish(), 0);
 			} else if (data_term_kernel() == kDataNode) {
 				if (dt.nnode > 0) {
 					auto kern = apply_nodes_kernel<T, decltype(dim)::value>;
@@ -1275,9 +1312,12 @@ void apply_data_term(const Geom& g, const DataTerm<T>& dt, const T* p, T* q, dou
 				FI_LAUNCH(kern, gb, kThreads, 0, s, g, dt.nocc, dt.cell_base.data(), dt.cell_mask.data(), dt.blocks.data(), p, q, partial, ticket,
 				          d_dot_accum, d_done);
 			} else {
+				// the last block to finish may publish the rank's p.Ap itself (only when nothing else adds to it afterwards)
+				const bool do_pub = pub != nullptr && d_dot_accum != nullptr && gr == 0;
 				auto kern = apply_blocks_kernel<T, decltype(dim)::value, false>;
 				FI_LAUNCH(kern, gb, kThreads, 0, s, g, dt.nocc, dt.cell_base.data(), dt.cell_mask.data(), dt.blocks.data(), p, q, partial, ticket,
-				          d_dot_accum, d_done, static_cast<const uint64_t*>(nullptr));
+				          d_dot_accum, d_done, static_cast<const uint64_t*>(nullptr), do_pub ? *pub : PeerPublish(), do_pub ? 1 : 0);
+				published = do_pub;
 			}
 		});
 	}
@@ -1290,6 +1330,7 @@ void apply_data_term(const Geom& g, const DataTerm<T>& dt, const T* p, T* q, dou
 		FI_LAUNCH(kern, gr, kThreads, 0, s, dt.nrows, dt.row_ptr.data(), dt.col.data(), dt.val.data(), p, q,
 		          partial + gp + 1, ticket + 1, d_dot_accum, d_done);
 	}
+	return published;
 }
 
 template <typename T>
@@ -1320,7 +1361,7 @@ template bool apply_data_term_epilogue<float>(const Geom&, const DataTerm<float>
                                               cudaStream_t);
 template void build_data_term<float>(const Geom&, const PointStore&, const HostRows&, DataTerm<float>&, float*, float*, cudaStream_t);
 template void build_data_term<double>(const Geom&, const PointStore&, const HostRows&, DataTerm<double>&, double*, double*, cudaStream_t);
-template void apply_data_term<float>(const Geom&, const DataTerm<float>&, const float*, float*, double*, const int*, cudaStream_t);
-template void apply_data_term<double>(const Geom&, const DataTerm<double>&, const double*, double*, double*, const int*, cudaStream_t);
+template bool apply_data_term<float>(const Geom&, const DataTerm<float>&, const float*, float*, double*, const int*, cudaStream_t, const PeerPublish*);
+template bool apply_data_term<double>(const Geom&, const DataTerm<double>&, const double*, double*, double*, const int*, cudaStream_t, const PeerPublish*);
 
 }  // namespace fi

@@ -365,13 +365,9 @@ void slab_mg_solve(fi_comm* c, const Geom& g, const SlabMgPlan& plan, const Mode
 	auto      op32 = build_operator<float>(g, model, pts, none, s);
 	op32->dist     = &hooks;
 	op32->use_fast = kStencilAuto;
-	MgOptions mo;
-	mo.nu = default_smoothing_steps(model);
-	if (o.mg_smoothing_steps > 0) { mo.nu = o.mg_smoothing_steps; }
-	if (o.mg_cheb_ratio > 1.0) { mo.cheb_ratio = o.mg_cheb_ratio; }
-	if (const char* e = getenv("FI_B200_MG_COARSEST")) {
-		if (atoi(e) > 0) { mo.coarsest_cells = atoi(e); }
-	}
+	MgOptions mo = default_mg_options(model, g, true, o.mg_smoothing_steps, o.mg_cheb_ratio);
+	mg_options_from_env(mo);
+	mo.gamma = 1;  // the sharded levels run V-cycles only
 	auto mg = build_slab_multigrid(*op32, model, pts, mo, plan, s);
 	std::unique_ptr<Operator<double>> op64;  // the outer CG's operator when it is not the V-cycle's
 	auto wide_operator = [&]() -> Operator<double>& {

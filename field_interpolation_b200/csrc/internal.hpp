@@ -129,9 +129,9 @@ struct DataTerm
 	DevBuf<int64_t>    cell_base; // local index of the cell's corner 0 (may lie outside the lattice: see cell_mask)
 	DevBuf<uint32_t>   cell_mask; // bits 0..7: corner is a lattice node; bits 8..15: ... whose row this process owns
 	DevBuf<T>          blocks;    // [tri(2^D)][nocc]
-	// The same matrix P = sum of the cell blocks, node-major (what the solver applies): for every lattice node that is a
-	// corner of an occupied cell (and whose row this process owns) the 3^D coefficients of its row, so that q += P p is a
-	// gather with one writer per node — no atomics, bit-reproducible.
+	// The same matrix P = sum of the cell blocks, node-major (built only with FI_B200_DATA_TERM=node, assembly.cu): for
+	// every lattice node that is a corner of an occupied cell (and whose row this process owns) the 3^D coefficients of its
+	// row, so that q += P p is a gather with one writer per node — no atomics, bit-reproducible.
 	int64_t            nnode = 0;
 	DevBuf<int64_t>    node_index; // [nnode] local index of the node, ascending
 	DevBuf<T>          node_coef;  // [3^D][nnode]; slot = sum_d (delta_d + 1) 3^d for the neighbour at offset delta in {-1,0,1}^D
@@ -158,9 +158,12 @@ void build_data_term(const Geom& g, const PointStore& pts, const HostRows& user_
                      T* d_diag, cudaStream_t s);
 
 // q += P p over the compact data term; p.(P p) is *added* to d_dot_accum[0] (nullable).
+// pub (multi-GPU peer path, nullable): the block that completes the sum also publishes d_dot_accum[0] to every rank's
+// mailbox (peer.cuh) — returns true when it did, false when the caller has to (no occupied cells here, generic rows).
+struct PeerPublish;
 template <typename T>
-void apply_data_term(const Geom& g, const DataTerm<T>& dt, const T* p, T* q, double* d_dot_accum, const int* d_done,
-                     cudaStream_t s);
+bool apply_data_term(const Geom& g, const DataTerm<T>& dt, const T* p, T* q, double* d_dot_accum, const int* d_done,
+                     cudaStream_t s, const PeerPublish* pub = nullptr);
 
 // The data term's share of the epilogue-mode stencil step (stencil_tma_3d_epilogue): with u = P in,
 // res_out -= u and, when d_new is given, d_new -= b minv u, e -= b minv u — by atomics over the occupied cells.
@@ -200,8 +203,9 @@ struct ModelAccum
 
 StencilTables make_tables(const Geom& g, const ModelAccum& m);
 
+// d_diag += diag(S); with d_minv also the Jacobi preconditioner of the finished diagonal: 1 / diag (1 where diag == 0)
 template <typename T>
-void stencil_diagonal(const Geom& g, const StencilTables& t, T* d_diag /* += */, cudaStream_t s);
+void stencil_diagonal(const Geom& g, const StencilTables& t, T* d_diag /* += */, T* d_minv /* nullable */, cudaStream_t s);
 
 // q = S p (overwrites q).  When d_dot_out is non-null, p.q is reduced deterministically (per-block partials in
 // d_partial, summed in block order by the last block to arrive) and *stored* to d_dot_out[0].  d_done

@@ -65,6 +65,13 @@ __global__ void __launch_bounds__(kThreads) residual_sub_kernel(int64_t n, const
 	for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) { res[i] = r[i] - q[i]; }
 }
 
+// e += e2
+__global__ void __launch_bounds__(kThreads) add_kernel(int64_t n, const float* __restrict__ e2, float* __restrict__ e)
+{
+	const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+	for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) { e[i] += e2[i]; }
+}
+
 // ---- transfers -----------------------------------------------------------------------------------------------------
 // Prolongation is upscale_field's multilinear, align-corners interpolation (field_interpolation.cpp:431-485): fine node
 // i of an axis sits at coarse position t = i * (nc - 1) / (nf - 1), between coarse nodes floor(t) and floor(t) + 1.
@@ -82,60 +89,85 @@ struct Xfer  // fine <-> coarse geometry of one level pair; unused axes have nf 
 	const float* weight[kMaxDim]; // [nc][kMaxFan]
 };
 
-// e_f += P e_c : every fine node gathers its 2^D coarse neighbours.  Block = 128 threads along x; y and z come from
-// the block index (no integer division per node).
+// e_f += P e_c : every fine node gathers its 2^D coarse neighbours.  Block = 128 threads along x covering kXferRows
+// consecutive y rows of one z plane (a block per row was 1 M blocks of 128 threads at 512^3: scheduling-bound, 1.6 TB/s);
+// y and z come from the block index (no integer division per node).
+constexpr int kXferRows = 4;
+
 __global__ void __launch_bounds__(128) prolong_add_kernel(Xfer x, const float* __restrict__ ec, float* __restrict__ ef)
 {
-	const int ix = blockIdx.x * 128 + threadIdx.x, iy = blockIdx.y, iz = blockIdx.z;
+	const int ix = blockIdx.x * 128 + threadIdx.x, iy0 = blockIdx.y * kXferRows, iz = blockIdx.z;
 	if (ix >= x.nf[0]) { return; }
-	const int   bx = __ldg(x.base[0] + ix), by = __ldg(x.base[1] + iy), bz = __ldg(x.base[2] + iz);
-	const float fx = __ldg(x.frac[0] + ix), fy = __ldg(x.frac[1] + iy), fz = __ldg(x.frac[2] + iz);
+	const int   bx = __ldg(x.base[0] + ix), bz = __ldg(x.base[2] + iz);
+	const float fx = __ldg(x.frac[0] + ix), fz = __ldg(x.frac[2] + iz);
 	// the upper neighbour of the last node does not exist; its weight is zero, the clamped read is harmless
-	const int   bx1 = min(bx + 1, x.nc[0] - 1), by1 = min(by + 1, x.nc[1] - 1), bz1 = min(bz + 1, x.nc[2] - 1);
+	const int     bx1 = min(bx + 1, x.nc[0] - 1), bz1 = min(bz + 1, x.nc[2] - 1);
 	const int64_t sy = x.nc[0], sz = static_cast<int64_t>(x.nc[0]) * x.nc[1];
-	const float*  p00 = ec + bz * sz + by * sy;
-	const float*  p01 = ec + bz * sz + by1 * sy;
-	const float*  p10 = ec + bz1 * sz + by * sy;
-	const float*  p11 = ec + bz1 * sz + by1 * sy;
-	const float   gx = 1.0f - fx, gy = 1.0f - fy, gz = 1.0f - fz;
-	const float   v00 = gx * __ldg(p00 + bx) + fx * __ldg(p00 + bx1);
-	const float   v01 = gx * __ldg(p01 + bx) + fx * __ldg(p01 + bx1);
-	const float   v10 = gx * __ldg(p10 + bx) + fx * __ldg(p10 + bx1);
-	const float   v11 = gx * __ldg(p11 + bx) + fx * __ldg(p11 + bx1);
-	const float   acc = gz * (gy * v00 + fy * v01) + fz * (gy * v10 + fy * v11);
-	const int64_t i   = (static_cast<int64_t>(iz) * x.nf[1] + iy) * x.nf[0] + ix;
-	ef[i] += acc;
+	const float   gx = 1.0f - fx, gz = 1.0f - fz;
+	float         acc[kXferRows], old[kXferRows];
+#pragma unroll
+	for (int r = 0; r < kXferRows; ++r) {
+		const int iy = iy0 + r;
+		acc[r]       = 0.0f;
+		old[r]       = 0.0f;
+		if (iy >= x.nf[1]) { continue; }
+		const int    by  = __ldg(x.base[1] + iy);
+		const float  fy  = __ldg(x.frac[1] + iy), gy = 1.0f - fy;
+		const int    by1 = min(by + 1, x.nc[1] - 1);
+		const float* p00 = ec + bz * sz + by * sy;
+		const float* p01 = ec + bz * sz + by1 * sy;
+		const float* p10 = ec + bz1 * sz + by * sy;
+		const float* p11 = ec + bz1 * sz + by1 * sy;
+		const float  v00 = gx * __ldg(p00 + bx) + fx * __ldg(p00 + bx1);
+		const float  v01 = gx * __ldg(p01 + bx) + fx * __ldg(p01 + bx1);
+		const float  v10 = gx * __ldg(p10 + bx) + fx * __ldg(p10 + bx1);
+		const float  v11 = gx * __ldg(p11 + bx) + fx * __ldg(p11 + bx1);
+		acc[r]           = gz * (gy * v00 + fy * v01) + fz * (gy * v10 + fy * v11);
+		old[r]           = ef[(static_cast<int64_t>(iz) * x.nf[1] + iy) * x.nf[0] + ix];
+	}
+#pragma unroll
+	for (int r = 0; r < kXferRows; ++r) {
+		const int iy = iy0 + r;
+		if (iy < x.nf[1]) { ef[(static_cast<int64_t>(iz) * x.nf[1] + iy) * x.nf[0] + ix] = old[r] + acc[r]; }
+	}
 }
 
-// r_c = P^T res_f : every coarse node gathers the fine nodes whose interpolation touches it.
+// r_c = P^T res_f : every coarse node gathers the fine nodes whose interpolation touches it; a block covers kXferRows
+// coarse rows.
 __global__ void __launch_bounds__(128) restrict_kernel(Xfer x, const float* __restrict__ rf, float* __restrict__ rc)
 {
-	const int cx = blockIdx.x * 128 + threadIdx.x, cy = blockIdx.y, cz = blockIdx.z;
+	const int cx = blockIdx.x * 128 + threadIdx.x, cy0 = blockIdx.y * kXferRows, cz = blockIdx.z;
 	if (cx >= x.nc[0]) { return; }
-	const int    x0 = __ldg(x.first[0] + cx), y0 = __ldg(x.first[1] + cy), z0 = __ldg(x.first[2] + cz);
-	const int    nx = __ldg(x.count[0] + cx), ny = __ldg(x.count[1] + cy), nz = __ldg(x.count[2] + cz);
+	const int    x0 = __ldg(x.first[0] + cx), z0 = __ldg(x.first[2] + cz);
+	const int    nx = __ldg(x.count[0] + cx), nz = __ldg(x.count[2] + cz);
 	const float* wx = x.weight[0] + static_cast<size_t>(cx) * kMaxFan;
-	const float* wy = x.weight[1] + static_cast<size_t>(cy) * kMaxFan;
 	const float* wz = x.weight[2] + static_cast<size_t>(cz) * kMaxFan;
 	float wxr[kMaxFan];
 #pragma unroll
 	for (int i = 0; i < kMaxFan; ++i) { wxr[i] = i < nx ? __ldg(wx + i) : 0.0f; }
 	const int64_t sy = x.nf[0], sz = static_cast<int64_t>(x.nf[0]) * x.nf[1];
-	float acc = 0.0f;
-	for (int k = 0; k < nz; ++k) {
-		const float wk = __ldg(wz + k);
-		for (int j = 0; j < ny; ++j) {
-			const float  wkj = wk * __ldg(wy + j);
-			const float* row = rf + (z0 + k) * sz + (y0 + j) * sy + x0;
-			float        s   = 0.0f;
 #pragma unroll
-			for (int i = 0; i < kMaxFan; ++i) {
-				if (i < nx) { s += wxr[i] * __ldg(row + i); }
+	for (int r = 0; r < kXferRows; ++r) {
+		const int cy = cy0 + r;
+		if (cy >= x.nc[1]) { break; }
+		const int    y0 = __ldg(x.first[1] + cy), ny = __ldg(x.count[1] + cy);
+		const float* wy = x.weight[1] + static_cast<size_t>(cy) * kMaxFan;
+		float        acc = 0.0f;
+		for (int k = 0; k < nz; ++k) {
+			const float wk = __ldg(wz + k);
+			for (int j = 0; j < ny; ++j) {
+				const float  wkj = wk * __ldg(wy + j);
+				const float* row = rf + (z0 + k) * sz + (y0 + j) * sy + x0;
+				float        s   = 0.0f;
+#pragma unroll
+				for (int i = 0; i < kMaxFan; ++i) {
+					if (i < nx) { s += wxr[i] * __ldg(row + i); }
+				}
+				acc += wkj * s;
 			}
-			acc += wkj * s;
 		}
+		rc[(static_cast<int64_t>(cz) * x.nc[1] + cy) * x.nc[0] + cx] = acc;
 	}
-	rc[(static_cast<int64_t>(cz) * x.nc[1] + cy) * x.nc[0] + cx] = acc;
 }
 
 // ---- coarsest level: e = Ainv r (dense, one block per row) --------------------------------------------------------
@@ -309,6 +341,7 @@ struct Multigrid::Level
 	std::unique_ptr<Operator<float>> owned;
 	PointStore                       pts;
 	DevBuf<float>                    r, e, res, d, d2, q;  // r / e of level 0 are the caller's vectors; d / d2 ping-pong
+	DevBuf<float>                    r2, e2;               // W-cycle: residual after the first coarse correction and its correction
 	double                           lmax = 0;
 	Xfer                             to_coarser;     // this level (fine) -> next level (coarse)
 	DevBuf<int>                      xfer_int;       // backing store of to_coarser's tables
@@ -428,6 +461,19 @@ void level_inputs(int D, const int* root_size, const ModelAccum& model, const Po
 
 }  // namespace
 
+void mg_options_from_env(MgOptions& o)
+{
+	auto geti = [](const char* name, int& v) {
+		if (const char* e = getenv(name)) {
+			if (atoi(e) > 0 || (e[0] == '0' && e[1] == 0 && std::string(name) == "FI_B200_MG_NU_COARSE")) { v = atoi(e); }
+		}
+	};
+	geti("FI_B200_MG_COARSEST", o.coarsest_cells);
+	geti("FI_B200_MG_NU_COARSE", o.nu_coarse);
+	geti("FI_B200_MG_GAMMA", o.gamma);
+	geti("FI_B200_MG_WLEVELS", o.w_levels);
+}
+
 Multigrid::Multigrid()  = default;
 Multigrid::~Multigrid()
 {
@@ -442,6 +488,7 @@ std::unique_ptr<Multigrid> build_multigrid(Operator<float>& fine, const ModelAcc
 	if (!root_size) { root_size = fine.g.size; }
 	auto mg     = std::make_unique<Multigrid>();
 	mg->opt     = opt;
+	mg->base_level = fine_level;
 	const int D = fine.g.ndim;
 	// levels
 	{
@@ -488,6 +535,10 @@ std::unique_ptr<Multigrid> build_multigrid(Operator<float>& fine, const ModelAcc
 		if (l > 0) {
 			lv.r.resize(n);
 			lv.e.resize(n);
+			if (opt.gamma > 1 && l < L - 1) {
+				lv.r2.resize(n);
+				lv.e2.resize(n);
+			}
 		}
 		if (l < L - 1) {
 			lv.res.resize(n);
@@ -563,7 +614,10 @@ bool fused_step(Multigrid::Level& lv, const float* in, const float* res_in, floa
 {
 	Operator<float>& op = *lv.op;
 	if (op.data.nrows > 0 || op.use_fast != kStencilAuto) { return false; }
-	if (!stencil_tma_3d_epilogue<float>(op.g, op.tabs, in, res_in, res_out, op.minv.data(), e, d_new, a, b, s)) { return false; }
+	if (!(op.g.ndim == 2 ? stencil_tma_2d_epilogue<float>(op.g, op.tabs, in, res_in, res_out, op.minv.data(), e, d_new, a, b, s)
+	                     : stencil_tma_3d_epilogue<float>(op.g, op.tabs, in, res_in, res_out, op.minv.data(), e, d_new, a, b, s))) {
+		return false;
+	}
 	const bool ok = apply_data_term_epilogue<float>(op.g, op.data, in, res_out, op.minv.data(), e, d_new, b, s);
 	FI_REQUIRE(ok, FI_ERR_UNSUPPORTED, "multigrid: data-term epilogue refused after the stencil epilogue ran");
 	return true;
@@ -576,7 +630,7 @@ struct Smoothed
 };
 
 // nu Chebyshev steps on A e = r at one level.  e_zero: e starts at zero (pre-smoothing).
-Smoothed smooth(Multigrid::Level& lv, const MgOptions& opt, const float* r, float* e, bool e_zero, cudaStream_t s)
+Smoothed smooth(Multigrid::Level& lv, const MgOptions& opt, int nu, const float* r, float* e, bool e_zero, cudaStream_t s)
 {
 	const int64_t n     = lv.g.N;
 	const double  lmax  = lv.lmax, lmin = lmax / opt.cheb_ratio;
@@ -595,7 +649,7 @@ Smoothed smooth(Multigrid::Level& lv, const MgOptions& opt, const float* r, floa
 		res_src = res;
 	}
 	double rho = 1.0 / sigma;
-	for (int k = 1; k < opt.nu; ++k) {
+	for (int k = 1; k < nu; ++k) {
 		const double rho_new = 1.0 / (2.0 * sigma - rho);
 		const float  a = static_cast<float>(rho_new * rho), b = static_cast<float>(2.0 * rho_new / delta);
 		if (fused_step(lv, d, res_src, res, e, d_other, a, b, s)) {
@@ -619,7 +673,8 @@ void vcycle_level(Multigrid& mg, int l, const float* r, float* e, cudaStream_t s
 		return;
 	}
 	Multigrid::Level& lc = *mg.levels[l + 1];
-	const Smoothed    sm = smooth(lv, mg.opt, r, e, true, s);
+	const int         nu = (l + mg.base_level > 0 && mg.opt.nu_coarse > 0) ? mg.opt.nu_coarse : mg.opt.nu;
+	const Smoothed    sm = smooth(lv, mg.opt, nu, r, e, true, s);
 	// residual after the last correction, restricted
 	if (!fused_step(lv, sm.d, sm.res, lv.res.data(), nullptr, nullptr, 0.0f, 0.0f, s)) {
 		lv.op->apply(sm.d, lv.q.data(), nullptr, nullptr, s);
@@ -627,14 +682,20 @@ void vcycle_level(Multigrid& mg, int l, const float* r, float* e, cudaStream_t s
 	}
 	{
 		const Xfer& x = lv.to_coarser;
-		FI_LAUNCH(restrict_kernel, dim3(div_up(x.nc[0], 128), x.nc[1], x.nc[2]), 128, 0, s, x, lv.res.data(), lc.r.data());
+		FI_LAUNCH(restrict_kernel, dim3(div_up(x.nc[0], 128), div_up(x.nc[1], kXferRows), x.nc[2]), 128, 0, s, x, lv.res.data(), lc.r.data());
 	}
 	vcycle_level(mg, l + 1, lc.r.data(), lc.e.data(), s);
+	if (mg.opt.gamma > 1 && l + 1 < L - 1 && l + 1 + mg.base_level <= mg.opt.w_levels) {  // W-cycle: a second coarse correction, on what the first one left
+		lc.op->apply(lc.e.data(), lc.q.data(), nullptr, nullptr, s);
+		FI_LAUNCH(residual_sub_kernel, vgrid(lc.g.N), kThreads, 0, s, lc.g.N, static_cast<const float*>(lc.r.data()), static_cast<const float*>(lc.q.data()), lc.r2.data());
+		vcycle_level(mg, l + 1, lc.r2.data(), lc.e2.data(), s);
+		FI_LAUNCH(add_kernel, vgrid(lc.g.N), kThreads, 0, s, lc.g.N, static_cast<const float*>(lc.e2.data()), lc.e.data());
+	}
 	{
 		const Xfer& x = lv.to_coarser;
-		FI_LAUNCH(prolong_add_kernel, dim3(div_up(x.nf[0], 128), x.nf[1], x.nf[2]), 128, 0, s, x, lc.e.data(), e);
+		FI_LAUNCH(prolong_add_kernel, dim3(div_up(x.nf[0], 128), div_up(x.nf[1], kXferRows), x.nf[2]), 128, 0, s, x, lc.e.data(), e);
 	}
-	smooth(lv, mg.opt, r, e, false, s);
+	smooth(lv, mg.opt, nu, r, e, false, s);
 }
 
 }  // namespace
@@ -669,6 +730,17 @@ void Multigrid::vcycle(const float* r, float* z, cudaStream_t s)
 	graph_z = z;
 	FI_CUDA(cudaGraphLaunch(exec, s));
 	count_launch(static_cast<int>(graph_launches));
+}
+
+bool Multigrid::demote_to_v_cycle()
+{
+	if (opt.gamma <= 1) { return false; }
+	opt.gamma = 1;
+	if (exec) {
+		cudaGraphExecDestroy(exec);
+		exec = nullptr;
+	}
+	return true;
 }
 
 // ---- the V-cycle with z-slab sharded fine levels ------------------------------------------------------------------------
@@ -772,6 +844,7 @@ std::unique_ptr<SlabMultigrid> build_slab_multigrid(Operator<float>& fine, const
 	DistHooks& hooks0 = *fine.dist;
 	const int  rank = hooks0.rank(), world = hooks0.world();
 	FI_REQUIRE(world == plan.world && plan.nd >= 1, FI_ERR_INVALID, "slab multigrid: the plan is for another communicator");
+	FI_REQUIRE(opt.gamma <= 1, FI_ERR_UNSUPPORTED, "slab multigrid: the sharded levels run V-cycles only");
 	FI_REQUIRE(fine.g.zown0 == plan.halo && fine.g.zoff == plan.own[0][rank].first - plan.halo && fine.g.zown1 - fine.g.zown0 == plan.own[0][rank].second - plan.own[0][rank].first,
 	           FI_ERR_INVALID, "slab multigrid: the fine operator's slab is not the plan's");
 	auto mg  = std::make_unique<SlabMultigrid>();
@@ -896,7 +969,7 @@ void slab_step(SlabMultigrid::DLevel& lv, float* in, const float* res_in, float*
 
 // nu Chebyshev steps on A e = r over the slab's owned planes (smooth() on a slab).  Returns the residual before the last
 // correction and the last correction, like smooth().
-Smoothed slab_smooth(SlabMultigrid::DLevel& lv, const MgOptions& opt, const float* r, float* e, bool e_zero, cudaStream_t s)
+Smoothed slab_smooth(SlabMultigrid::DLevel& lv, const MgOptions& opt, int nu, const float* r, float* e, bool e_zero, cudaStream_t s)
 {
 	const int64_t off = lv.g.own_offset(), n = lv.g.own_cells();
 	const double  lmax  = lv.lmax, lmin = lmax / opt.cheb_ratio;
@@ -913,7 +986,7 @@ Smoothed slab_smooth(SlabMultigrid::DLevel& lv, const MgOptions& opt, const floa
 		res_src = res;
 	}
 	double rho = 1.0 / sigma;
-	for (int k = 1; k < opt.nu; ++k) {
+	for (int k = 1; k < nu; ++k) {
 		const double rho_new = 1.0 / (2.0 * sigma - rho);
 		const float  a = static_cast<float>(rho_new * rho), b = static_cast<float>(2.0 * rho_new / delta);
 		slab_step(lv, d, res_src, res, e, d_other, a, b, s);
@@ -930,7 +1003,8 @@ void slab_vcycle_level(SlabMultigrid& mg, int l, const float* r, float* e, cudaS
 	const int64_t          off = lv.g.own_offset(), n = lv.g.own_cells();
 	const int              z0 = mg.plan.own[l][mg.rank].first, z1 = mg.plan.own[l][mg.rank].second;
 	const bool             last = l + 1 == mg.plan.nd;
-	const Smoothed         sm = slab_smooth(lv, mg.opt, r, e, true, s);
+	const int              nu = (l > 0 && mg.opt.nu_coarse > 0) ? mg.opt.nu_coarse : mg.opt.nu;
+	const Smoothed         sm = slab_smooth(lv, mg.opt, nu, r, e, true, s);
 	// residual after the last correction
 	slab_step(lv, sm.d, sm.res, lv.res.data(), nullptr, nullptr, 0.0f, 0.0f, s);
 	lv.hooks->exchange_halo(lv.res.data(), sizeof(float), s);
@@ -945,7 +1019,7 @@ void slab_vcycle_level(SlabMultigrid& mg, int l, const float* r, float* e, cudaS
 		x.weight[2] += static_cast<size_t>(lv.c0) * kMaxFan;
 		const float* rf = lv.res.data() - static_cast<int64_t>(lv.g.zoff) * plane_f;
 		float*       rc = last ? mg.tail_r.data() + static_cast<int64_t>(lv.c0) * plane_c : mg.dl[l + 1]->r.data() + mg.dl[l + 1]->g.own_offset();
-		FI_LAUNCH(restrict_kernel, dim3(div_up(x.nc[0], 128), x.nc[1], lv.c1 - lv.c0), 128, 0, s, x, rf, rc);
+		FI_LAUNCH(restrict_kernel, dim3(div_up(x.nc[0], 128), div_up(x.nc[1], kXferRows), lv.c1 - lv.c0), 128, 0, s, x, rf, rc);
 	}
 	const float* ec = nullptr;  // the coarse correction, indexable by the lattice z of the next level
 	if (last) {
@@ -962,9 +1036,9 @@ void slab_vcycle_level(SlabMultigrid& mg, int l, const float* r, float* e, cudaS
 		Xfer x = lv.to_coarser;
 		x.base[2] += z0;
 		x.frac[2] += z0;
-		FI_LAUNCH(prolong_add_kernel, dim3(div_up(x.nf[0], 128), x.nf[1], z1 - z0), 128, 0, s, x, ec, e + off);
+		FI_LAUNCH(prolong_add_kernel, dim3(div_up(x.nf[0], 128), div_up(x.nf[1], kXferRows), z1 - z0), 128, 0, s, x, ec, e + off);
 	}
-	slab_smooth(lv, mg.opt, r, e, false, s);
+	slab_smooth(lv, mg.opt, nu, r, e, false, s);
 }
 
 }  // namespace
@@ -1028,6 +1102,14 @@ PcgResult mgpcg_impl(Operator<T>& op, Precond& mg, const T* b, T* x, double tol,
 	} else if (rr > target) {
 		double rz = 0;
 		p.zero(s);
+		bool fresh = true;  // no search direction yet (first iteration, or restarted after the preconditioner changed)
+		// CG broke down on a W-cycle preconditioner: continue from x with V-cycles (r is the recurrence residual of x)
+		auto demoted = [&] {
+			if (!mg.demote_to_v_cycle()) { return false; }
+			fresh = true;
+			p.zero(s);  // beta = 0 next, but 0 * (a non-finite leftover) would not be
+			return true;
+		};
 		while (it < max_iter) {
 			mg.vcycle(r32.data(), z.data(), s);
 			{
@@ -1037,10 +1119,12 @@ PcgResult mgpcg_impl(Operator<T>& op, Precond& mg, const T* b, T* x, double tol,
 			read(h, 1);
 			const double rz_new = h[0];
 			if (!(rz_new > 0.0) || !std::isfinite(rz_new)) {  // breakdown: keep the last iterate
+				if (demoted()) { continue; }
 				res.stalled = true;
 				break;
 			}
-			const double beta = it == 0 ? 0.0 : rz_new / rz;
+			const double beta = fresh ? 0.0 : rz_new / rz;
+			fresh             = false;
 			rz                = rz_new;
 			{
 				auto k = mg_direction_kernel<T>;
@@ -1051,6 +1135,7 @@ PcgResult mgpcg_impl(Operator<T>& op, Precond& mg, const T* b, T* x, double tol,
 			read(h, 1);
 			const double pq = h[0];
 			if (!(pq > 0.0) || !std::isfinite(pq)) {
+				if (demoted()) { continue; }
 				res.stalled = true;
 				break;
 			}

@@ -60,16 +60,6 @@ __device__ __forceinline__ void for_each_pack(int64_t n, F&& f)
 	}
 }
 
-template <typename T>
-__global__ void inv_diag_kernel(int64_t n, const T* __restrict__ diag, T* __restrict__ minv)
-{
-	const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-	for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-		const T d = diag[i];
-		minv[i]   = d != T(0) ? T(1) / d : T(1);
-	}
-}
-
 // r = b - q, p = M r; rho = r.p, rr = r.r, bb = b.b
 template <typename T>
 __global__ void __launch_bounds__(kThreads) pcg_init_kernel(int64_t n, const T* __restrict__ b, const T* __restrict__ q,
@@ -110,94 +100,6 @@ __global__ void __launch_bounds__(kThreads) pcg_init_kernel(int64_t n, const T* 
 		st->breakdown = 0;
 		st->done      = (tot[2] == 0.0 || tot[1] <= tol * tol * tot[2] || max_iters <= 0) ? 1 : 0;
 	});
-}
-
-// ---- peer-memory all-reduce (see solver.hpp) ----------------------------------------------------------------
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
-{
-#ifdef FI_B200_EMU  // tests/emu: no PTX on the CPU functional emulator; a polling thread lets its siblings run (the hardware
-	::cuda_emu::spin_yield();  // guarantees forward progress to the other lanes of a warp, sequential fibers do not)
-	return *reinterpret_cast<const volatile unsigned long long*>(p);
-#else
-	unsigned long long v;
-	asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-	return v;
-#endif
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
-{
-#ifdef FI_B200_EMU
-	*reinterpret_cast<volatile unsigned long long*>(p) = v;
-#else
-	asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-#endif
-}
-
-// The first warp of a block, all 32 lanes: lane j stores this rank's `count` (<= 2) partial sums and then the sequence
-// number into rank j's mailbox — every peer in parallel, one NVLink round trip in all (a single thread doing the
-// `world` release stores one after the other costs `world` round trips: 20+ us at 8 ranks, measured).
-__device__ __forceinline__ void peer_publish_warp(const PeerLink& L, int which, int par, unsigned long long seq, const double* v, int count)
-{
-	const int j = threadIdx.x & 31;
-	if (j < L.world) {
-		PeerSlot* sl = &L.peer[j]->slot[which][par][L.rank];
-		for (int k = 0; k < count; ++k) { reinterpret_cast<volatile double*>(sl->v)[k] = v[k]; }
-		// cumulative: also orders the halo stores of the other blocks, observed through the ticket, before the flag
-		__threadfence_system();
-		st_release_sys(&sl->seq, seq);
-	}
-}
-
-// The first warp of a block, all 32 lanes: lane j waits until rank j's slot carries `seq`; lane 0 then adds the values in
-// rank order (every rank forms bit-identical sums).  Gives up after ~10 s (a peer died): flags the mailbox and returns
-// false.  The result is valid in lane 0 (and returned to every lane).
-__device__ __forceinline__ bool peer_collect_warp(const PeerLink& L, int which, int par, unsigned long long seq, double* out, int count)
-{
-	const int j  = threadIdx.x & 31;
-	double    v0 = 0.0, v1 = 0.0;
-	bool      ok = true;
-	if (j < L.world) {
-		const PeerSlot* sl = &L.local->slot[which][par][j];
-		const long long t0 = clock64();
-		while (ld_acquire_sys(&sl->seq) != seq) {
-			if (clock64() - t0 > 20000000000ll) {
-				L.local->error = 1;
-				ok             = false;
-				break;
-			}
-		}
-		v0 = reinterpret_cast<const volatile double*>(sl->v)[0];
-		if (count > 1) { v1 = reinterpret_cast<const volatile double*>(sl->v)[1]; }
-	}
-	ok = __all_sync(0xffffffffu, ok);
-	double t0s = 0.0, t1s = 0.0;
-	for (int r = 0; r < L.world; ++r) {
-		t0s += __shfl_sync(0xffffffffu, v0, r);
-		t1s += __shfl_sync(0xffffffffu, v1, r);
-	}
-	out[0] = t0s;
-	if (count > 1) { out[1] = t1s; }
-	return ok;
-}
-
-// Sequence numbers of iteration `iters` of the solve with epoch number `base`: 2 * iters + 1 for p.Ap, + 2 for
-// (r.Mr, r.r).  Derived from the device-side iteration counter so that the kernels can sit in a CUDA graph.  Once
-// the solve is done the counter stops and the leftover iterations of a round re-publish the same numbers, which
-// every waiting peer accepts at once (their values are ignored: all ranks are done together).
-__device__ __forceinline__ unsigned long long seq_of(unsigned long long base, const PcgState* st, int which)
-{
-	return base + 2ull * static_cast<unsigned long long>(st->iters) + 1ull + static_cast<unsigned long long>(which);
-}
-
-__device__ __forceinline__ unsigned long long global_ns()
-{
-#ifdef FI_B200_EMU
-	return 0;
-#else
-	unsigned long long t;
-	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-	return t;
-#endif
 }
 
 __global__ void peer_publish_kernel(PeerLink L, int which, int par, unsigned long long base, const PcgState* st, const double* src, int count,
@@ -337,9 +239,9 @@ __global__ void __launch_bounds__(kThreads) pcg_update_peer_kernel(int64_t n, T*
 	__shared__ int    s_ok, s_pub;
 	const bool was_done = st->done != 0;
 	const unsigned long long seq_pq = seq_of(base, st, 0), seq_rr = seq_of(base, st, 1);
-	// fold (FI_B200_PEER_FOLD=1): this kernel also does the work of peer_publish_kernel (block 0, before anybody waits) and
-	// of pcg_update_finish_peer_kernel (the last block, after it has published) — two kernel boundaries fewer per iteration
-	if (fold && blockIdx.x == 0 && threadIdx.x < 32) {
+	// fold bit 0: this kernel also does the work of peer_publish_kernel (block 0, before anybody waits); bit 1: and of
+	// pcg_update_finish_peer_kernel (the last block, after it has published) — a kernel boundary fewer per iteration each
+	if ((fold & 1) && blockIdx.x == 0 && threadIdx.x < 32) {
 		double mine[1] = {was_done ? 0.0 : st->pq};  // a finished solve still publishes: the peers' kernels are waiting
 		if (threadIdx.x == 0 && !was_done) { L.local->stamp[0][st->iters & 511] = global_ns(); }
 		peer_publish_warp(L, 0, par, seq_pq, mine, 1);
@@ -415,7 +317,7 @@ __global__ void __launch_bounds__(kThreads) pcg_update_peer_kernel(int64_t n, T*
 	if (s_pub && threadIdx.x < 32) {
 		const double tot[2] = {s_tot[0], s_tot[1]};
 		peer_publish_warp(L, 1, par, seq_rr, tot, 2);
-		if (fold) {  // every other block of this kernel has finished: end the iteration here (pcg_update_finish_peer_kernel)
+		if (fold & 2) {  // every other block of this kernel has finished: end the iteration here (pcg_update_finish_peer_kernel)
 			double     all[2];
 			const bool ok = peer_collect_warp(L, 1, par, seq_rr, all, 2);
 			if (threadIdx.x == 0 && !st->done) {
@@ -563,9 +465,7 @@ std::unique_ptr<Operator<T>> build_operator(const Geom& g, const ModelAccum& m, 
 	op->atb.zero(s);
 	op->diag.zero(s);
 	build_data_term<T>(g, pts, rows, op->data, op->atb.data(), op->diag.data(), s);
-	stencil_diagonal<T>(g, op->tabs, op->diag.data(), s);
-	auto kern = inv_diag_kernel<T>;
-	FI_LAUNCH(kern, vec_grid(g.N), kThreads, 0, s, g.N, op->diag.data(), op->minv.data());
+	stencil_diagonal<T>(g, op->tabs, op->diag.data(), op->minv.data(), s);  // + M^-1 = 1 / diag in the same pass
 	op->partial.resize(static_cast<size_t>(stencil_partial_slots(g)));
 	op->ticket.resize(1);
 	op->ticket.zero(s);
@@ -664,9 +564,15 @@ PcgResult pcg_solve(Operator<T>& op, const T* b, T* x, double tol, long long max
 		T*   pp[2] = {w.p.data(), w.p2.data()};
 		// every solve gets its own block of mailbox sequence numbers (all ranks count solves alike)
 		const unsigned long long seq_base = link ? (dist->next_seq() << 40) : 0ull;
-		// opt-in until measured on the GPUs: publish / finish folded into the update kernel (same on every rank: environment)
+		// Who publishes p.Ap and who ends the iteration on the peer-memory path (FI_B200_PEER_FOLD, the same on every rank):
+		//   0  separate one-warp kernels for both (5 graph nodes per iteration)
+		//   1  the update kernel publishes p.Ap (block 0) and ends the iteration (last block): 3 nodes
+		//   2  the data-term kernel's last block publishes p.Ap, the update kernel ends the iteration: 3 nodes, and the
+		//      publish travels while the update kernel is being launched (default)
+		//   3  the data-term kernel publishes, a separate kernel ends the iteration: 4 nodes
 		const char* fold_env  = std::getenv("FI_B200_PEER_FOLD");
-		const bool  peer_fold = link && fold_env && *fold_env == '1';
+		const int   fold_mode = !link ? 0 : (fold_env && *fold_env >= '0' && *fold_env <= '3' ? *fold_env - '0' : 2);
+		const bool  data_publishes = fold_mode >= 2, update_finishes = fold_mode == 1 || fold_mode == 2;
 		auto enqueue_round = [&] {
 			for (int it = 0; it < check_every; ++it) {
 				const int par = it & 1;
@@ -675,12 +581,19 @@ PcgResult pcg_solve(Operator<T>& op, const T* b, T* x, double tol, long long max
 				                                         w.state.data(), par, d_pq, op.partial.data(), op.ticket.data(), d_done, s);
 				if (fused && link) {
 					// peer-memory path: no NCCL inside the iteration
-					apply_data_term<T>(op.g, op.data, pp[par ^ 1], w.q.data(), d_pq, d_done, s);
-					if (!peer_fold) { FI_LAUNCH(peer_publish_kernel, 1, 32, 0, s, *link, 0, par, seq_base, w.state.data(), d_pq, 1, d_done); }
+					PeerPublish pub;
+					pub.link  = *link;
+					pub.which = 0;
+					pub.par   = par;
+					pub.base  = seq_base;
+					pub.st    = w.state.data();
+					const bool published = apply_data_term<T>(op.g, op.data, pp[par ^ 1], w.q.data(), d_pq, d_done, s, data_publishes ? &pub : nullptr);
+					const bool in_update = fold_mode == 1;
+					if (!published && !in_update) { FI_LAUNCH(peer_publish_kernel, 1, 32, 0, s, *link, 0, par, seq_base, w.state.data(), d_pq, 1, d_done); }
 					auto ku = pcg_update_peer_kernel<T>;
 					FI_LAUNCH(ku, grid, kThreads, 0, s, n, x + off, r_vec + off, pp[par ^ 1] + off, w.q.data() + off, op.minv.data() + off,
-					          w.state.data(), par, w.partial.data(), w.ticket.data(), *link, push, seq_base, peer_fold ? 1 : 0);
-					if (!peer_fold) { FI_LAUNCH(pcg_update_finish_peer_kernel, 1, 32, 0, s, w.state.data(), par, *link, seq_base); }
+					          w.state.data(), par, w.partial.data(), w.ticket.data(), *link, push, seq_base, (in_update ? 1 : 0) | (update_finishes ? 2 : 0));
+					if (!update_finishes) { FI_LAUNCH(pcg_update_finish_peer_kernel, 1, 32, 0, s, w.state.data(), par, *link, seq_base); }
 				} else if (fused) {
 					apply_data_term<T>(op.g, op.data, pp[par ^ 1], w.q.data(), d_pq, d_done, s);
 					if (dist) { dist->allreduce(d_pq, 1, s); }

@@ -5,63 +5,9 @@
 #include <vector>
 
 #include "internal.hpp"
+#include "peer.cuh"
 
 namespace fi {
-
-// Device-resident scalars of one PCG run; nothing here is read by the host inside the iteration loop except
-// at convergence polls.
-struct PcgState
-{
-	double rho[2];  // r.z, ping-pong by iteration parity
-	double pq;      // p.(A p)
-	double rr;      // r.r (recurrence residual)
-	double bb;      // b.b
-	double tol2bb;  // tolerance^2 * b.b  (Eigen's stopping rule: |r|^2 <= tol^2 |b|^2)
-	double rr0;     // r.r of the initial guess
-	int    done;
-	int    breakdown;
-	long long iters;
-	long long max_iters;
-	double part[4];  // multi-GPU: this rank's partial sums, all-reduced in place before the finish kernels read them
-};
-
-// ---- multi-GPU: scalar all-reduce and halo push over NVLink peer memory, inside the CG kernels -------------
-// Every rank owns a mailbox in device memory that its peers map through CUDA IPC.  A kernel publishes this
-// rank's partial sums by storing {values, sequence number} into its slot of every peer's mailbox; the kernel
-// that needs the sum spins on its local mailbox until all slots carry the expected sequence number and adds
-// them in rank order (so every rank forms bit-identical sums).  Sequence numbers only grow: no resets, no ABA.
-constexpr int kMaxPeers = 8;  // one NVSwitch domain
-
-struct PeerSlot
-{
-	double             v[2];
-	unsigned long long seq;
-	unsigned long long pad;
-};
-
-struct Mailbox
-{
-	PeerSlot slot[2 /* which sum */][2 /* iteration parity */][kMaxPeers];
-	int      error;  // set by a kernel that gave up waiting for a peer
-	// device timestamps (ns) of the last 512 iterations, for FI_B200_TRACE: [0] p.Ap published (stencil + data term
-	// done), [1] update kernel past its wait, [2] iteration finished (all ranks' r.r collected)
-	unsigned long long stamp[3][512];
-};
-
-struct PeerLink  // passed to kernels by value
-{
-	int      rank = 0, world = 1;
-	Mailbox* local = nullptr;
-	Mailbox* peer[kMaxPeers] = {};  // peer[rank] == local
-};
-
-template <typename T>
-struct HaloPush  // where the update kernel stores its boundary planes of r in the neighbours' copies of r
-{
-	T*      lo = nullptr;  // rank - 1's upper halo planes (receives my first `count` owned values), or null
-	T*      hi = nullptr;  // rank + 1's lower halo planes (receives my last `count` owned values), or null
-	int64_t count = 0;     // halo planes * cells per plane
-};
 
 // Multi-GPU plumbing of one z-slab solve (dist.cu); nullptr everywhere else.
 struct DistHooks
@@ -176,6 +122,14 @@ template <typename T>
 bool stencil_tma_3d_epilogue(const Geom& g, const StencilTables& t, const T* in, const T* res_in, T* res_out, const T* minv, T* e, T* d_new,
                              T a, T b, cudaStream_t s);
 
+// stencil_2d.cu: the same three entry points for 2D lattices (any weights, gradient smoothness included).
+template <typename T>
+bool stencil_tma_2d_fused(const Geom& g, const StencilTables& t, const T* r, const T* minv, const T* p_old, T* p_new, T* q, const PcgState* st, int par,
+                          double* d_dot_out, double* d_partial, unsigned* d_ticket, const int* d_done, cudaStream_t s);
+template <typename T>
+bool stencil_tma_2d_epilogue(const Geom& g, const StencilTables& t, const T* in, const T* res_in, T* res_out, const T* minv, T* e, T* d_new, T a, T b,
+                             cudaStream_t s);
+
 // The fused direction+stencil step in the given StencilMode; false when no fused kernel applies.
 template <typename T>
 inline bool stencil_fused_step(int mode, const Geom& g, const StencilTables& t, const T* r, const T* minv, const T* p_old, T* p_new,
@@ -183,6 +137,7 @@ inline bool stencil_fused_step(int mode, const Geom& g, const StencilTables& t, 
                                const int* d_done, cudaStream_t s)
 {
 	if (g.tile) { return false; }  // tile mode: generic kernels only
+	if (mode == kStencilAuto && g.ndim == 2) { return stencil_tma_2d_fused<T>(g, t, r, minv, p_old, p_new, q, st, par, d_dot_out, d_partial, d_ticket, d_done, s); }
 	if (mode == kStencilAuto && stencil_tma_3d_fused<T>(g, t, r, minv, p_old, p_new, q, st, par, d_dot_out, d_partial, d_ticket, d_done, s)) { return true; }
 	if (mode != kStencilGeneric && stencil_fast_3d_fused<T>(g, t, r, minv, p_old, p_new, q, st, par, d_dot_out, d_partial, d_ticket, d_done, s)) { return true; }
 	return false;
@@ -192,15 +147,48 @@ inline bool stencil_fused_step(int mode, const Geom& g, const StencilTables& t, 
 struct MgOptions
 {
 	int    nu               = 3;     // Chebyshev steps before and after the coarse-grid correction
+	int    nu_coarse        = 0;     // ... on levels >= 1 (each costs 1/2^D of the level above); 0: the same as nu
+	int    gamma            = 1;     // 1: V-cycle; 2: W-cycle (two coarse corrections per level, the second on the residual of the first)
+	int    w_levels         = 3;     // gamma = 2 applies to the coarse problems of levels 1 .. w_levels only: below, the levels are tiny and a
+	                                 // W-cycle would visit them 2^level times for no gain but launch latency
 	double cheb_ratio       = 12.0;  // the smoother targets the eigenvalues of D^-1 A in [lambda_max / ratio, lambda_max]
 	int    coarsest_cells   = 600;   // coarsen until a level has at most this many cells (dense solve there, inverse computed on the device)
 	int    power_iterations = 12;    // for lambda_max, per level, at setup
 };
 
-// Chebyshev steps when the caller leaves mg_smoothing_steps at 0: 3 for operators up to model_2 (tuned on the GPU, r1c),
-// 5 when model_3 / model_4 rows are present — their 6th / 8th-order stencils leave more high-frequency error per step
-// (model_3 alone, 32x16x24: 80 MG-PCG iterations reach 3e-7 with 5 steps, 2e-3 with 3).
-inline int default_smoothing_steps(const ModelAccum& m) { return (m.on[3] || m.on[4]) ? 5 : 3; }
+// The hierarchy's parameters when the caller leaves them alone, from the B200 sweeps of round 2
+// (profiles/r2d_mg_sweep.jsonl; fp64-outer MG-PCG to a 1e-6 true residual, default Weights):
+//   * operators up to model_2: 2 Chebyshev steps on the finest level, 4 on the coarse ones (each level costs 1/2^D of
+//     the one above) — 512^3: 27 iterations / 254 ms against 30 / 322 ms with 3 steps everywhere; 256^3: 48 against 59 ms;
+//   * 3D lattices from 50 M cells on one GPU: W-cycles over the three largest coarse levels with 6 coarse steps — 512^3:
+//     10 iterations / 169 ms.  Below that size the extra visits are launch latency, not work, and V wins; on z-slabs the
+//     replicated tail would be visited four times per rank, so sharded solves stay with V;
+//   * model_3 / model_4 rows (6th / 8th-order stencils) leave more high-frequency error per step: 5 steps everywhere, V
+//     (model_3 alone, 32x16x24: 80 MG-PCG iterations reach 3e-7 with 5 steps, 2e-3 with 3; round 1).
+// `user_nu` > 0 (fi_solve_options::mg_smoothing_steps) sets the finest level's steps; the coarse levels get at least as many.
+inline MgOptions default_mg_options(const ModelAccum& m, const Geom& g, bool sharded, int user_nu, double user_ratio)
+{
+	MgOptions o;
+	const bool high_order = m.on[3] || m.on[4];
+	o.nu        = high_order ? 5 : 2;
+	o.nu_coarse = high_order ? 0 : 4;
+	const int64_t cells = static_cast<int64_t>(g.size[0]) * g.size[1] * g.size[2];
+	if (g.ndim == 3 && !sharded && !high_order && cells >= 50000000) {
+		o.gamma     = 2;
+		o.nu_coarse = 6;
+		o.w_levels  = 3;
+	}
+	if (user_nu > 0) {
+		o.nu = user_nu;
+		if (o.nu_coarse > 0 && o.nu_coarse < user_nu) { o.nu_coarse = user_nu; }
+	}
+	if (user_ratio > 1.0) { o.cheb_ratio = user_ratio; }
+	return o;
+}
+
+// Tuning knobs of the hierarchy read from the environment (same on every rank): FI_B200_MG_COARSEST (cells of the dense
+// coarsest level), FI_B200_MG_NU_COARSE, FI_B200_MG_GAMMA, FI_B200_MG_WLEVELS.
+void mg_options_from_env(MgOptions& o);
 
 struct Multigrid
 {
@@ -209,6 +197,7 @@ struct Multigrid
 	std::vector<std::unique_ptr<Level>> levels;      // 0 = finest
 	DevBuf<float>                       coarse_inv;  // dense inverse of the coarsest operator, row-major nc x nc
 	int                                 nc = 0;
+	int                                 base_level = 0;  // level of levels[0] in the hierarchy of the root lattice (> 0: the replicated tail of a slab V-cycle)
 	cudaGraphExec_t                     exec = nullptr;  // the V-cycle for (graph_r -> graph_z)
 	const float*                        graph_r = nullptr;
 	float*                              graph_z = nullptr;
@@ -218,6 +207,9 @@ struct Multigrid
 	~Multigrid();
 	// z = V-cycle(r): one application of the preconditioner (fp32, finest-level vectors of N floats)
 	void vcycle(const float* r, float* z, cudaStream_t s);
+	// A W-cycle is a symmetric preconditioner but positive definite only while the V-cycle it repeats converges as a
+	// stationary iteration; when CG breaks down on it the solver falls back to V-cycles.  False: already V.
+	bool demote_to_v_cycle();
 };
 
 // Builds the hierarchy under `fine` (which must outlive it): re-discretised coarse operators from the same points
@@ -267,6 +259,7 @@ struct SlabMultigrid
 	~SlabMultigrid();
 	// z = V-cycle(r) on slab-local vectors of the finest level (owned planes are read / written)
 	void vcycle(const float* r, float* z, cudaStream_t s);
+	bool demote_to_v_cycle() { return false; }  // sharded levels run V-cycles only
 };
 
 // fine: this rank's slab operator of the finest level with fine.dist set (it must outlive the hierarchy); model / pts:

@@ -9,6 +9,8 @@
 // terms 2 w_gs^2 sum_{d<o} (D_1^T D_1)_d (x) (D_1^T D_1)_o  (:303-315 emits every pair twice).
 // S p is applied directly from p with per-axis coefficient rows selected by a 9-way "row class"
 // (4 classes at each end + interior); nothing is stored per node.
+#include <algorithm>
+
 #include "internal.hpp"
 
 namespace fi {
@@ -28,6 +30,7 @@ struct DevTables
 	T   band[kMaxDim][9][9];
 	T   gs2;
 	int radius;
+	bool any;
 };
 
 template <typename T>
@@ -41,6 +44,7 @@ DevTables<T> to_dev(const StencilTables& t)
 	}
 	d.gs2    = static_cast<T>(t.gs2);
 	d.radius = t.radius;
+	d.any    = t.any;
 	return d;
 }
 
@@ -66,22 +70,46 @@ __device__ __forceinline__ void coords_of(const Geom& g, int64_t index, int* c)
 	}
 }
 
+// diag += diagonal of S.  One block per (x segment, kDiagRows y rows, local z plane): the coordinates come from the block
+// index — the div / mod chain per node of the first version made this 8 B/cell kernel run at a tenth of the memory roofline.
+constexpr int kDiagRows = 8;
+
 template <typename T>
-__global__ void diagonal_kernel(Geom g, DevTables<T> tab, T* __restrict__ diag)
+__global__ void __launch_bounds__(kThreads) diagonal_kernel(Geom g, DevTables<T> tab, T* __restrict__ diag, T* __restrict__ minv)
 {
-	const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-	if (i >= g.N) { return; }
-	int c[kMaxDim];
-	coords_of(g, i, c);
-	if (c[2] < 0 || c[2] >= g.size[2]) { return; }  // slab planes beyond the lattice stay zero
-	T acc = 0;
-	for (int d = 0; d < g.ndim; ++d) { acc += tab.band[d][row_class(c[d], g.size[d])][4]; }
-	if (tab.gs2 != T(0)) {
-		for (int d = 0; d < g.ndim; ++d) {
-			for (int o = d + 1; o < g.ndim; ++o) { acc += tab.gs2 * static_cast<T>(lap1(c[d], g.size[d], 0) * lap1(c[o], g.size[o], 0)); }
+	const int nx = g.size[0], ny = g.ndim >= 2 ? g.size[1] : 1;
+	const int zl = blockIdx.z;                      // local plane (3D), 0 otherwise
+	const int z  = g.ndim == 3 ? zl + g.zoff : 0;   // lattice plane
+	const bool outside = g.ndim == 3 && (z < 0 || z >= g.size[2]);  // slab planes beyond the lattice: the diagonal stays zero
+	T   zpart = 0;
+	int lz    = 0;
+	if (g.ndim == 3 && !outside) {
+		zpart = tab.band[2][row_class(z, g.size[2])][4];
+		lz    = lap1(z, g.size[2], 0);
+	}
+	for (int r = 0; r < kDiagRows; ++r) {
+		const int y = blockIdx.y * kDiagRows + r;
+		if (y >= ny) { break; }
+		T   rest = zpart;  // what does not depend on x
+		int ly   = 0;
+		if (g.ndim >= 2) {
+			rest += tab.band[1][row_class(y, ny)][4];
+			ly = lap1(y, ny, 0);
+			if (tab.gs2 != T(0)) { rest += tab.gs2 * static_cast<T>(ly * lz); }
+		}
+		const int64_t at = (static_cast<int64_t>(zl) * ny + y) * nx;
+		for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < nx; x += gridDim.x * blockDim.x) {
+			T d = diag[at + x];
+			if (!outside && tab.any) {
+				T acc = rest + tab.band[0][row_class(x, nx)][4];
+				if (tab.gs2 != T(0) && g.ndim >= 2) { acc += tab.gs2 * static_cast<T>(lap1(x, nx, 0) * (ly + lz)); }
+				d += acc;
+				diag[at + x] = d;
+			}
+			// Eigen's DiagonalPreconditioner: 1 / diag, 1 where the diagonal is zero
+			if (minv) { minv[at + x] = d != T(0) ? T(1) / d : T(1); }
 		}
 	}
-	diag[i] += acc;
 }
 
 // Reference-shaped kernel for every dimension, order and weight combination: one thread per node, neighbours
@@ -178,11 +206,13 @@ StencilTables make_tables(const Geom& g, const ModelAccum& m)
 }
 
 template <typename T>
-void stencil_diagonal(const Geom& g, const StencilTables& t, T* d_diag, cudaStream_t s)
+void stencil_diagonal(const Geom& g, const StencilTables& t, T* d_diag, T* d_minv, cudaStream_t s)
 {
-	if (!t.any) { return; }
+	if (!t.any && !d_minv) { return; }
 	auto kern = diagonal_kernel<T>;
-	FI_LAUNCH(kern, div_up(g.N, kThreads), kThreads, 0, s, g, to_dev<T>(t), d_diag);
+	const dim3 grid(std::min(div_up(g.size[0], kThreads), 64), g.ndim >= 2 ? div_up(g.size[1], kDiagRows) : 1, g.ndim == 3 ? g.nzl : 1);
+	FI_REQUIRE(grid.y <= 65535 && grid.z <= 65535, FI_ERR_RANGE, "lattice too large along y or z for the diagonal kernel's grid");
+	FI_LAUNCH(kern, grid, kThreads, 0, s, g, to_dev<T>(t), d_diag, d_minv);
 }
 
 int stencil_partial_slots(const Geom& g) { return div_up(g.N, kThreads) + 8; }
@@ -193,12 +223,16 @@ bool stencil_fast_3d(const Geom& g, const StencilTables& t, const T* p, T* q, do
 template <typename T>
 bool stencil_tma_3d(const Geom& g, const StencilTables& t, const T* p, T* q, double* d_dot_out, double* d_partial,
                     unsigned* d_ticket, const int* d_done, cudaStream_t s);  // stencil_tma.cu
+template <typename T>
+bool stencil_tma_2d(const Geom& g, const StencilTables& t, const T* p, T* q, double* d_dot_out, double* d_partial,
+                    unsigned* d_ticket, const int* d_done, cudaStream_t s);  // stencil_2d.cu
 
 template <typename T>
 void stencil_apply(const Geom& g, const StencilTables& t, const T* p, T* q, double* d_dot_out, double* d_partial,
                    unsigned* d_ticket, const int* d_done, int mode, cudaStream_t s)
 {
 	if (g.tile) { mode = kStencilGeneric; }  // only the generic kernel knows the tile mask
+	if (mode == kStencilAuto && g.ndim == 2 && stencil_tma_2d<T>(g, t, p, q, d_dot_out, d_partial, d_ticket, d_done, s)) { return; }
 	if (mode == kStencilAuto && stencil_tma_3d<T>(g, t, p, q, d_dot_out, d_partial, d_ticket, d_done, s)) { return; }
 	if (mode != kStencilGeneric && stencil_fast_3d<T>(g, t, p, q, d_dot_out, d_partial, d_ticket, d_done, s)) { return; }
 	// the generic kernel runs over every stored node and would read beyond a slab's halo planes
@@ -207,8 +241,8 @@ void stencil_apply(const Geom& g, const StencilTables& t, const T* p, T* q, doub
 	FI_LAUNCH(kern, div_up(g.N, kThreads), kThreads, 0, s, g, to_dev<T>(t), p, q, d_dot_out, d_partial, d_ticket, d_done);
 }
 
-template void stencil_diagonal<float>(const Geom&, const StencilTables&, float*, cudaStream_t);
-template void stencil_diagonal<double>(const Geom&, const StencilTables&, double*, cudaStream_t);
+template void stencil_diagonal<float>(const Geom&, const StencilTables&, float*, float*, cudaStream_t);
+template void stencil_diagonal<double>(const Geom&, const StencilTables&, double*, double*, cudaStream_t);
 template void stencil_apply<float>(const Geom&, const StencilTables&, const float*, float*, double*, double*, unsigned*, const int*, int, cudaStream_t);
 template void stencil_apply<double>(const Geom&, const StencilTables&, const double*, double*, double*, double*, unsigned*, const int*, int, cudaStream_t);
 

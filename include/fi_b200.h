@@ -86,8 +86,10 @@ typedef struct fi_solve_options {
 	int32_t refine_max_outer; /* FI_MIXED: max fp64 refinement sweeps; <= 0: 20 */
 	double  refine_inner_tolerance; /* FI_MIXED: relative tolerance of each inner fp32 solve; <= 0: 1e-3 */
 	int32_t preconditioner;   /* fi_preconditioner.  FI_PRECOND_JACOBI is what the reference's Eigen solvers use */
-	int32_t mg_smoothing_steps; /* FI_PRECOND_MULTIGRID: Chebyshev steps before and after each coarse correction; <= 0: by the
-	                             * smoothness model — 3, or 5 when model_3 / model_4 rows (6th / 8th-order stencils) are present */
+	int32_t mg_smoothing_steps; /* FI_PRECOND_MULTIGRID: Chebyshev steps on the finest level before and after each coarse correction;
+	                             * <= 0: by the smoothness model and the lattice — 2 on the finest level and 4 (6 inside the W-cycles
+	                             * that 3D lattices from 50 M cells get on one GPU) on the coarse ones, or 5 everywhere when
+	                             * model_3 / model_4 rows (6th / 8th-order stencils) are present */
 	double  mg_cheb_ratio;    /* ... smoothed part of the spectrum is [lambda_max / ratio, lambda_max]; <= 0: 12 */
 } fi_solve_options;
 
@@ -100,7 +102,8 @@ typedef struct fi_solve_stats {
 	double  solve_ms;          /* iteration loop (device time) */
 	int32_t converged;         /* 1 if the stopping rule was met by the TRUE residual (recomputed from x), not merely by the
 	                            * recurrence: an fp32 solve that stalls at its rounding floor reports 0 */
-	int32_t outer_sweeps;      /* FI_MIXED only */
+	int32_t outer_sweeps;      /* FI_MIXED: fp64 refinement sweeps.  FI_PRECOND_MULTIGRID: coarse corrections per level the solve ended
+	                            * with — 1 V-cycle, 2 W-cycle (a W-cycle on which CG breaks down is demoted to V mid-solve) */
 	int64_t occupied_cells;    /* cells holding at least one data row */
 	int64_t generic_rows;      /* rows applied through the COO fallback */
 	int64_t widened_after;     /* -1: the solve ran in the requested arithmetic throughout.  k >= 0: an FI_F32 multigrid solve

@@ -257,9 +257,14 @@ static int scenario_value_semantics()
 	fi::Weights w;
 	fi::LatticeField a{{n, n}};
 	add_field_constraints(&a, w);
+	// (the second-difference rows leave 1, x, y, xy undetermined: five value rows pin the field)
 	const float p0[2] = {3.25f, 4.5f}, p1[2] = {9.75f, 8.125f}, p2[2] = {6.5f, 2.25f};
+	const float q0[2] = {1.5f, 11.25f}, q1[2] = {11.0f, 1.75f}, q2[2] = {6.0f, 7.0f};
 	add_value_constraint(&a, p0, 1.0f, 1.0f);
 	add_value_constraint(&a, p1, -2.0f, 1.0f);
+	add_value_constraint(&a, q0, 0.5f, 1.0f);
+	add_value_constraint(&a, q1, 3.0f, 1.0f);
+	add_value_constraint(&a, q2, -1.0f, 1.0f);
 	fi::LatticeField b = a;  // shares nothing observable with a from here on
 	add_value_constraint(&b, p2, 5.0f, 2.0f);
 	add_equation(&b.eq, fi::Weight{1.5f}, fi::Rhs{0.25f}, {{0, 1.0f}, {n * n - 1, -1.0f}});
@@ -278,6 +283,10 @@ static int scenario_value_semantics()
 	d.eq.rhs.clear();
 	add_field_constraints(&d, w);
 	add_value_constraint(&d, p2, 7.0f, 1.0f);
+	add_value_constraint(&d, p0, 2.0f, 1.0f);
+	add_value_constraint(&d, q0, -3.0f, 1.0f);
+	add_value_constraint(&d, q1, 0.25f, 1.0f);
+	add_value_constraint(&d, q2, 1.0f, 1.0f);
 	put_i("d_counts", {static_cast<int>(d.eq.rhs.size()), static_cast<int>(d.eq.triplets.size())});
 	put_f("d_exact", solve_sparse_linear_exact(d.eq, n * n));
 	// ... or truncates it (drops the last constraint) and solves without another builder call

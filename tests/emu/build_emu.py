@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "field_interpolation_b200", "csrc")
 OUT = os.path.join(HERE, "_build", "libfi_emu.so")
 # every source of the library (stencil_tma.cu: TMA loads become synchronous box copies, see its FI_B200_EMU hooks)
-CU = ["abi.cu", "assembly.cu", "sort_scan.cu", "stencil.cu", "stencil_fast.cu", "stencil_tma.cu", "solver.cu", "mg.cu", "errormap.cu", "isosurface.cu", "dist.cu"]
+CU = ["abi.cu", "assembly.cu", "sort_scan.cu", "stencil.cu", "stencil_fast.cu", "stencil_tma.cu", "stencil_2d.cu", "solver.cu", "mg.cu", "errormap.cu", "isosurface.cu", "dist.cu"]
 CPP = ["cuda_emu.cpp", "emu_glue.cpp"]
 
 

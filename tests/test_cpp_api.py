@@ -204,6 +204,9 @@ def test_copies_are_independent_and_rewritten_equations_are_noticed(tmp_path, po
         f.add_field_constraints(w)
         f.add_value_constraint(p0, 1.0, 1.0)
         f.add_value_constraint(p1, -2.0, 1.0)
+        f.add_value_constraint([1.5, 11.25], 0.5, 1.0)
+        f.add_value_constraint([11.0, 1.75], 3.0, 1.0)
+        f.add_value_constraint([6.0, 7.0], -1.0, 1.0)
         return f
     a = base().system()
     assert list(got["a_counts"]) == [a.num_rows, a.num_triplets]
@@ -220,6 +223,10 @@ def test_copies_are_independent_and_rewritten_equations_are_noticed(tmp_path, po
     fd = port.field([n, n])
     fd.add_field_constraints(w)
     fd.add_value_constraint(p2, 7.0, 1.0)
+    fd.add_value_constraint(p0, 2.0, 1.0)
+    fd.add_value_constraint([1.5, 11.25], -3.0, 1.0)
+    fd.add_value_constraint([11.0, 1.75], 0.25, 1.0)
+    fd.add_value_constraint([6.0, 7.0], 1.0, 1.0)
     d = fd.system()
     assert list(got["d_counts"]) == [d.num_rows, d.num_triplets]
     assert rel(got["d_exact"], O.exact_solve(d, n * n)) <= 1e-5
