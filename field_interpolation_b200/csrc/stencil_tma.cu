@@ -33,25 +33,27 @@ struct Tile
 	static constexpr int TY   = 8;                    // tile rows (one per warp)
 	static constexpr int BXP  = TXP + 2 * NP;         // box row in packs
 	static constexpr int BY   = TY + 2 * R;           // box rows
-	static constexpr int RING = R + 2;                // planes of the new direction kept in shared memory
+	// planes of the new direction kept in shared memory: the star reads plane z while the fastest warp may already be writing
+	// plane z + R + 1 (one barrier per plane), so R + 2; the gradient-smoothness cross terms also read plane z - 1: R + 3
+	__host__ __device__ static constexpr int ring(bool gs) { return R + 2 + (gs ? 1 : 0); }
 	static constexpr int TILE_BYTES = ((BXP * BY * 16 + 127) / 128) * 128;
 	static constexpr int BOX_BYTES  = BXP * BY * 16;  // what one TMA load delivers
 };
 
-template <typename T, int R, int S, bool Fused>
+template <typename T, int R, int S, bool Fused, bool GS>
 constexpr size_t smem_bytes()
 {
 	using G = Tile<T, R>;
-	return 128 /* alignment slack */ + static_cast<size_t>(S) * (Fused ? 3 : 1) * G::TILE_BYTES + static_cast<size_t>(G::RING) * G::TILE_BYTES +
+	return 128 /* alignment slack */ + static_cast<size_t>(S) * (Fused ? 3 : 1) * G::TILE_BYTES + static_cast<size_t>(G::ring(GS)) * G::TILE_BYTES +
 	       S * sizeof(uint64_t) + 9 * (2 * R + 1) * sizeof(T) + 32 * sizeof(double) + 64;
 }
 
-template <typename T, int R, int S, bool Fused, int MINB, bool Epi>
+template <typename T, int R, int S, bool Fused, int MINB, bool Epi, bool GS>
 __global__ void __launch_bounds__(256, MINB)
     stencil3d_tma_kernel(const __grid_constant__ CUtensorMap map_a,  // p (plain) or r (fused)
                          const __grid_constant__ CUtensorMap map_b,  // M^-1 (fused)
                          const __grid_constant__ CUtensorMap map_c,  // p_old (fused)
-                         int nx, int ny, int nzl, int zo0, int zo1, int zoff, int nzg, int zchunk, TmaTables<T> tab,
+                         int nx, int ny, int nzl, int zo0, int zo1, int zoff, int nzg, int zchunk, TmaTables<T> tab, T gs2,
                          T* __restrict__ q, T* __restrict__ p_new,
                          const PcgState* st, int par, double* dot_out, double* partial, unsigned* ticket, const int* done, EpiArgs<T> epi)
 {
@@ -61,6 +63,7 @@ __global__ void __launch_bounds__(256, MINB)
 	constexpr int NP  = G::NP;
 	constexpr int NA  = Fused ? 3 : 1;
 	constexpr int W   = 2 * R + 1;
+	constexpr int RING = G::ring(GS);
 	using Pack        = typename PackOf<T>::type;
 	using PU          = PackU<T, V>;
 
@@ -75,7 +78,7 @@ __global__ void __launch_bounds__(256, MINB)
 	auto stage_ptr = [&](int s, int a) { return reinterpret_cast<Pack*>(base + (static_cast<size_t>(s) * NA + a) * G::TILE_BYTES); };
 	unsigned char* ring_base = base + static_cast<size_t>(S) * NA * G::TILE_BYTES;
 	auto ring_ptr = [&](int slot) { return reinterpret_cast<Pack*>(ring_base + static_cast<size_t>(slot) * G::TILE_BYTES); };
-	uint64_t* full  = reinterpret_cast<uint64_t*>(ring_base + static_cast<size_t>(G::RING) * G::TILE_BYTES);
+	uint64_t* full  = reinterpret_cast<uint64_t*>(ring_base + static_cast<size_t>(RING) * G::TILE_BYTES);
 	T*        zband = reinterpret_cast<T*>(full + S);                                      // [9][W]
 	double*   red   = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(zband + 9 * W) + 7) & ~uintptr_t(7));
 
@@ -117,6 +120,17 @@ __global__ void __launch_bounds__(256, MINB)
 #pragma unroll
 		for (int t = 0; t < W; ++t) { cy[t] = tab.band[1][cls][t + 4 - R]; }
 	}
+	// gradient smoothness (GS): diagonals of (D_1^T D_1) along x (per column of the pack) and y
+	T lx0[V], ly0 = T(0);
+	if (GS) {
+#pragma unroll
+		for (int j = 0; j < V; ++j) {
+			const int xi = min(x0 + j, nx - 1);
+			lx0[j]       = static_cast<T>((xi > 0 ? 1 : 0) + (xi < nx - 1 ? 1 : 0));
+		}
+		const int yi = min(y, ny - 1);
+		ly0          = static_cast<T>((yi > 0 ? 1 : 0) + (yi < ny - 1 ? 1 : 0));
+	}
 
 	const int lp0    = zb - R;             // first plane loaded
 	const int n_iter = ze + R - lp0;       // planes loaded by this block
@@ -144,6 +158,10 @@ __global__ void __launch_bounds__(256, MINB)
 	const int  own_at = (ty + R) * G::BXP + tx + NP;
 	const int  yh_at  = yh_row * G::BXP + tx + NP;
 	const int  xh_at  = xh_r * G::BXP + xh_col;
+	// the box corners (x-halo columns of the y-halo rows) matter to the gradient-smoothness cross terms only: the first
+	// 2 NP lanes of every y-halo warp fill them
+	const bool has_ch = GS && has_yh && tx < 2 * NP;
+	const int  ch_at  = yh_row * G::BXP + (tx < NP ? tx : G::TXP + tx);
 
 	auto direction = [&](const Pack* sa, const Pack* sb, const Pack* sc, int at) -> Pack {
 		if (!Fused) { return sa[at]; }
@@ -193,6 +211,7 @@ __global__ void __launch_bounds__(256, MINB)
 			rg[own_at] = pipe[k].v;
 			if (has_yh) { rg[yh_at] = direction(sa, sb, sc, yh_at); }
 			if (has_xh) { rg[xh_at] = direction(sa, sb, sc, xh_at); }
+			if (has_ch) { rg[ch_at] = direction(sa, sb, sc, ch_at); }
 			if (Fused && in_xy && lp >= wlo && lp < whi) { *reinterpret_cast<Pack*>(pout + static_cast<size_t>(lp) * plane) = pipe[k].v; }
 			__syncthreads();
 			if (tid == 0 && i + S < n_iter) { issue(i + S); }
@@ -200,7 +219,7 @@ __global__ void __launch_bounds__(256, MINB)
 			const int z = lp - R;
 			if (z >= zb && in_xy) {
 				int zslot = slot - R;
-				if (zslot < 0) { zslot += G::RING; }
+				if (zslot < 0) { zslot += RING; }
 				const Pack* pz = ring_ptr(zslot);
 				const T*    cz = zband + row_class(z + zoff, nzg) * W;
 				const PU&   ctr = pipe[(k + 1 + R) % W];
@@ -219,6 +238,7 @@ __global__ void __launch_bounds__(256, MINB)
 					for (int t = 0; t < W; ++t) { s += cz[t] * pipe[(k + 1 + t) % W].a[j]; }
 					out.a[j] = s;
 				}
+				PU y_lo, y_hi;  // p(x, y -+ 1, z), kept for the cross terms
 #pragma unroll
 				for (int t = 0; t < W; ++t) {
 					if (t == R) {
@@ -229,6 +249,8 @@ __global__ void __launch_bounds__(256, MINB)
 						nb.v = pz[(ty + t) * G::BXP + tx + NP];
 #pragma unroll
 						for (int j = 0; j < V; ++j) { out.a[j] += cy[t] * nb.a[j]; }
+						if (GS && t == R - 1) { y_lo = nb; }
+						if (GS && t == R + 1) { y_hi = nb; }
 					}
 				}
 				T xs[(2 * NP + 1) * V];
@@ -243,6 +265,62 @@ __global__ void __launch_bounds__(256, MINB)
 				for (int j = 0; j < V; ++j) {
 #pragma unroll
 					for (int t = 0; t < W; ++t) { out.a[j] += cx[j][t] * xs[NP * V + j + t - R]; }
+				}
+				if (GS) {
+					// 2 w_gs^2 sum over axis pairs of (D_1^T D_1)_d (x) (D_1^T D_1)_o (field_interpolation.cpp:303-315): per pair
+					// l_d l_o p - l_o (p at d -+ 1) - l_d (p at o -+ 1) + the four diagonal neighbours; neighbours outside the lattice
+					// arrive as zeros.  Planes z - 1 and z + 1 of the new direction are in the ring (xy) and in the pipe (own column).
+					const int zg  = z + zoff;
+					const T   lz0 = static_cast<T>((zg > 0 ? 1 : 0) + (zg < nzg - 1 ? 1 : 0));
+					int       sm  = zslot - 1, sp = zslot + 1;
+					if (sm < 0) { sm += RING; }
+					if (sp >= RING) { sp -= RING; }
+					const Pack* pm = ring_ptr(sm);
+					const Pack* pp = ring_ptr(sp);
+					const PU&   z_lo = pipe[(k + R) % W];      // p(x, y, z - 1)
+					const PU&   z_hi = pipe[(k + 2 + R) % W];  // p(x, y, z + 1)
+					// three packs around the own column: [left, centre, right] -> element j sits at V + j
+					T a_lo[3 * V], a_hi[3 * V], b_lo[3 * V], b_hi[3 * V];  // rows y -+ 1 of plane z; row y of planes z -+ 1
+#pragma unroll
+					for (int kk = 0; kk < 3; ++kk) {
+						PU u0, u1, u2, u3;
+						if (kk == 1) {
+							u0 = y_lo;
+							u1 = y_hi;
+							u2 = z_lo;
+							u3 = z_hi;
+						} else {
+							u0.v = pz[(ty + R - 1) * G::BXP + tx + NP - 1 + kk];
+							u1.v = pz[(ty + R + 1) * G::BXP + tx + NP - 1 + kk];
+							u2.v = pm[(ty + R) * G::BXP + tx + NP - 1 + kk];
+							u3.v = pp[(ty + R) * G::BXP + tx + NP - 1 + kk];
+						}
+#pragma unroll
+						for (int j = 0; j < V; ++j) {
+							a_lo[kk * V + j] = u0.a[j];
+							a_hi[kk * V + j] = u1.a[j];
+							b_lo[kk * V + j] = u2.a[j];
+							b_hi[kk * V + j] = u3.a[j];
+						}
+					}
+					PU c0, c1, c2, c3;  // p(x, y -+ 1, z -+ 1): own column
+					c0.v = pm[(ty + R - 1) * G::BXP + tx + NP];
+					c1.v = pm[(ty + R + 1) * G::BXP + tx + NP];
+					c2.v = pp[(ty + R - 1) * G::BXP + tx + NP];
+					c3.v = pp[(ty + R + 1) * G::BXP + tx + NP];
+#pragma unroll
+					for (int j = 0; j < V; ++j) {
+						const int cc = V + j, cx0 = NP * V + j;
+						const T   lx = lx0[j];
+						T g = (lx * ly0 + lx * lz0 + ly0 * lz0) * ctr.a[j];
+						g -= (ly0 + lz0) * (xs[cx0 - 1] + xs[cx0 + 1]);
+						g -= (lx + lz0) * (y_lo.a[j] + y_hi.a[j]);
+						g -= (lx + ly0) * (z_lo.a[j] + z_hi.a[j]);
+						g += a_lo[cc - 1] + a_lo[cc + 1] + a_hi[cc - 1] + a_hi[cc + 1];  // (x -+ 1, y -+ 1)
+						g += b_lo[cc - 1] + b_lo[cc + 1] + b_hi[cc - 1] + b_hi[cc + 1];  // (x -+ 1, z -+ 1)
+						g += c0.a[j] + c1.a[j] + c2.a[j] + c3.a[j];                      // (y -+ 1, z -+ 1)
+						out.a[j] += gs2 * g;
+					}
 				}
 				if (Epi) {
 					const size_t at = static_cast<size_t>(z) * plane + xy_off;
@@ -269,7 +347,7 @@ __global__ void __launch_bounds__(256, MINB)
 				}
 			}
 			if (++stage == S) { stage = 0; phase ^= 1u; }
-			if (++slot == G::RING) { slot = 0; }
+			if (++slot == RING) { slot = 0; }
 		}
 	}
 
@@ -299,8 +377,8 @@ CUtensorMap make_map(const Geom& g, const T* ptr)
 	return m;
 }
 
-template <typename T, int R, int S, bool Fused, int MINB, bool Epi = false>
-void launch(const Geom& g, const StencilTables& t, const T* a, const T* b, const T* c, T* q, T* p_new, const PcgState* st, int par,
+template <typename T, int R, int S, bool Fused, int MINB, bool Epi, bool GS>
+void launch_gs(const Geom& g, const StencilTables& t, const T* a, const T* b, const T* c, T* q, T* p_new, const PcgState* st, int par,
             double* d_dot_out, double* d_partial, unsigned* d_ticket, const int* d_done, cudaStream_t s, const EpiArgs<T>& epi = EpiArgs<T>())
 {
 	using G = Tile<T, R>;
@@ -337,22 +415,33 @@ void launch(const Geom& g, const StencilTables& t, const T* a, const T* b, const
 	const int zchunk = div_up(nown, chunks);
 	chunks           = div_up(nown, zchunk);
 	dim3 grid(tiles_x, tiles_y, chunks);
-	auto kern = stencil3d_tma_kernel<T, R, S, Fused, MINB, Epi>;
-	constexpr size_t smem = smem_bytes<T, R, S, Fused>();
+	auto kern = stencil3d_tma_kernel<T, R, S, Fused, MINB, Epi, GS>;
+	constexpr size_t smem = smem_bytes<T, R, S, Fused, GS>();
 	static bool configured = false;  // per instantiation
 	if (!configured) {
 		FI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
 		configured = true;
 	}
-	FI_LAUNCH(kern, grid, 256, smem, s, ma, mb, mc, g.size[0], g.size[1], g.nzl, g.zown0, g.zown1, g.zoff, g.size[2], zchunk, tab, q, p_new,
-	          st, par, d_dot_out, d_partial, d_ticket, d_done, epi);
+	FI_LAUNCH(kern, grid, 256, smem, s, ma, mb, mc, g.size[0], g.size[1], g.nzl, g.zown0, g.zown1, g.zoff, g.size[2], zchunk, tab,
+	          static_cast<T>(t.gs2), q, p_new, st, par, d_dot_out, d_partial, d_ticket, d_done, epi);
+}
+
+template <typename T, int R, int S, bool Fused, int MINB, bool Epi = false>
+void launch(const Geom& g, const StencilTables& t, const T* a, const T* b, const T* c, T* q, T* p_new, const PcgState* st, int par,
+            double* d_dot_out, double* d_partial, unsigned* d_ticket, const int* d_done, cudaStream_t s, const EpiArgs<T>& epi = EpiArgs<T>())
+{
+	if (t.gs2 != 0.0) {
+		launch_gs<T, R, S, Fused, MINB, Epi, true>(g, t, a, b, c, q, p_new, st, par, d_dot_out, d_partial, d_ticket, d_done, s, epi);
+	} else {
+		launch_gs<T, R, S, Fused, MINB, Epi, false>(g, t, a, b, c, q, p_new, st, par, d_dot_out, d_partial, d_ticket, d_done, s, epi);
+	}
 }
 
 template <typename T>
 bool eligible(const Geom& g, const StencilTables& t)
 {
 	constexpr int V = 16 / sizeof(T);
-	return g.ndim == 3 && t.gs2 == 0.0 && t.radius >= 1 && g.size[0] % V == 0 && g.size[0] >= 32 && g.size[1] >= 8 && g.zown1 - g.zown0 >= 1 &&
+	return g.ndim == 3 && t.radius >= 1 && g.size[0] % V == 0 && g.size[0] >= 32 && g.size[1] >= 8 && g.zown1 - g.zown0 >= 1 &&
 	       (g.sharded() || g.size[2] >= 8) && encode_fn() != nullptr;
 }
 

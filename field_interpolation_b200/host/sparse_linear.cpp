@@ -123,6 +123,7 @@ std::vector<float> solve(const LinearEquation& eq, int num_columns, Precision pr
 		stats->converged         = fs.converged != 0;
 		stats->occupied_cells    = fs.occupied_cells;
 		stats->generic_rows      = fs.generic_rows;
+		stats->widened_after     = fs.widened_after;
 	}
 	return x;
 }

@@ -98,8 +98,9 @@ struct SolveStats  // fi_solve_stats
 	long long iterations        = 0;
 	double    relative_residual = 0, true_residual = 0, initial_residual = 0;
 	double    setup_ms = 0, solve_ms = 0;
-	bool      converged = false;
+	bool      converged = false;  ///< by the residual recomputed from the solution, not merely by the recurrence
 	long long occupied_cells = 0, generic_rows = 0;
+	long long widened_after = -1;  ///< >= 0: a float multigrid solve continued with the fp64 outer CG after this many iterations
 };
 
 /// Relative-residual target of solve_sparse_linear_exact / _fast (defaults 1e-10 / 1e-9).

@@ -54,10 +54,14 @@ def test_operator_matches_reference_normal_equations(fi, port, sizes, fast):
 
 @pytest.mark.parametrize("sizes", [[32, 8, 8], [64, 24, 17], [36, 9, 40], [128, 10, 9], [160, 19, 33]])
 @pytest.mark.parametrize("orders", [dict(model_1=0.7), dict(model_2=0.5), dict(model_0=0.2, model_1=0.3, model_2=0.5),
-                                    dict(model_3=0.4), dict(model_0=0.1, model_1=0.2, model_2=0.5, model_3=0.3, model_4=0.25)])
+                                    dict(model_3=0.4), dict(model_0=0.1, model_1=0.2, model_2=0.5, model_3=0.3, model_4=0.25),
+                                    dict(model_2=0.5, gradient_smoothness=0.3), dict(model_1=0.2, gradient_smoothness=0.4),
+                                    dict(model_0=0.1, model_1=0.2, model_2=0.5, model_3=0.3, model_4=0.25, gradient_smoothness=0.15)])
 def test_fast_stencil_matches_generic_and_oracle(fi, port, sizes, orders):
     """The TMA-staged 3D kernel (mode 1) and the tiled one without TMA (mode 2) against the generic kernel (mode 0)
-    and the explicit AtA, fp32 and fp64, radius 1 / 2 / 4, lattices with ragged tiles and short z chunks."""
+    and the explicit AtA, fp32 and fp64, radius 1 / 2 / 4, lattices with ragged tiles and short z chunks; with the
+    gradient-smoothness cross terms (field_interpolation.cpp:303-315) the TMA kernel's GS variant runs (mode 2 falls back
+    to the generic kernel there)."""
     n = int(np.prod(sizes))
     rng = np.random.default_rng(n)
     kw = dict(model_2=0.0)
