@@ -493,6 +493,7 @@ void solve_device(fi_field* f, const fi_solve_options& o, const float* d_guess, 
 		} else {
 			FI_CUDA(cudaMemsetAsync(d_out, 0, N * sizeof(float), s));
 		}
+		op.guess_is_zero  = d_guess == nullptr;
 		const PcgResult r = pcg_solve<float>(op, nullptr, d_out, o.tolerance, o.max_iterations, o.check_every, true, s);
 		fill_stats(st, r, fresh ? op.setup_ms : 0.0, op.data.nocc, op.data.nrows);
 	} else if (o.precision == FI_F64) {
@@ -501,6 +502,7 @@ void solve_device(fi_field* f, const fi_solve_options& o, const float* d_guess, 
 		op.use_fast = fast;
 		DevBuf<double> x(N);
 		if (d_guess) { convert(d_guess, x.data(), N, s); } else { x.zero(s); }
+		op.guess_is_zero  = d_guess == nullptr;
 		const PcgResult r = pcg_solve<double>(op, nullptr, x.data(), o.tolerance, o.max_iterations, o.check_every, true, s);
 		convert(x.data(), d_out, N, s);
 		fill_stats(st, r, fresh ? op.setup_ms : 0.0, op.data.nocc, op.data.nrows);
@@ -536,6 +538,7 @@ void solve_device(fi_field* f, const fi_solve_options& o, const float* d_guess, 
 			e32.zero(s);
 			// never ask the inner solve for more than the outer target needs
 			const double    inner = std::max(itol, 0.5 * tol / rel);
+			op32.guess_is_zero = true;
 			const PcgResult r = pcg_solve<float>(op32, r32.data(), e32.data(), inner, max_it - tot.iterations, o.check_every, false, s);
 			tot.iterations += r.iterations;
 			axpy_f32_into_f64(e32.data(), x.data(), N, s);
@@ -1191,7 +1194,7 @@ int fi_slab_balanced_cuts(const int32_t* sizes, int32_t world, int64_t num_point
 	return guarded([&] {
 		FI_REQUIRE(sizes && cuts && world >= 1 && world <= 64 && num_points >= 0 && (positions || num_points == 0), FI_ERR_INVALID, "bad argument");
 		for (int d = 0; d < 3; ++d) { FI_REQUIRE(sizes[d] >= 1, FI_ERR_INVALID, "lattice size must be >= 1"); }
-		balanced_cuts(sizes, world, num_points, positions, loc, point_weight > 0 ? point_weight : 9.0, min_planes, cuts);
+		balanced_cuts(sizes, world, num_points, positions, loc, point_weight > 0 ? point_weight : 30.0, min_planes, cuts);
 	});
 }
 

@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(kThreads) pcg_init_kernel(int64_t n, const T* 
 	double            acc[3] = {0, 0, 0};
 	const int64_t     stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
 	for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-		const T bi = b[i], ri = bi - q[i], zi = minv[i] * ri;
+		const T bi = b[i], ri = q ? bi - q[i] : bi, zi = minv[i] * ri;  // q == nullptr: the guess is zero
 		r[i] = ri;
 		p[i] = zi;
 		acc[0] += static_cast<double>(ri) * static_cast<double>(zi);
@@ -417,12 +417,16 @@ void ensure_work(Operator<T>& op, cudaStream_t s)
 		w.p.resize(n);
 		w.q.resize(n);
 		w.p2.resize(n);
-		// halo planes and (slabs) planes beyond the lattice are read by the stencil kernels: start finite
-		// (on the solver's own stream: it is non-blocking, so work on the null stream is not ordered with it)
-		w.r.zero(s);
+		// the fused stencil kernel reads p_old before the first direction exists (times beta = 0): it must be finite.  On a slab
+		// the halo planes and the planes beyond the lattice of r and q are read too; elsewhere every element of r and q is
+		// written before it is read.  (On the solver's own stream: it is non-blocking, so work on the null stream is not
+		// ordered with it.)
 		w.p.zero(s);
 		w.p2.zero(s);
-		w.q.zero(s);
+		if (op.g.sharded()) {
+			w.r.zero(s);
+			w.q.zero(s);
+		}
 		w.partial.resize(static_cast<size_t>(3) * (static_cast<size_t>(sm_count()) * 8 + 8));
 		w.ticket.resize(1);
 		w.state.resize(1);
@@ -536,11 +540,15 @@ PcgResult pcg_solve(Operator<T>& op, const T* b, T* x, double tol, long long max
 		if (lo) { push.lo = static_cast<T*>(lo) + halo * plane + dist->peer_own_cells(link->rank - 1); }
 		if (hi) { push.hi = static_cast<T*>(hi); }
 	}
-	if (dist) { dist->exchange_halo(x, sizeof(T), s); }
-	op.apply(x, w.q.data(), nullptr, nullptr, s);
+	const bool zero_guess = op.guess_is_zero;
+	op.guess_is_zero      = false;
+	if (!zero_guess) {
+		if (dist) { dist->exchange_halo(x, sizeof(T), s); }
+		op.apply(x, w.q.data(), nullptr, nullptr, s);
+	}
 	{
 		auto kern = pcg_init_kernel<T>;
-		FI_LAUNCH(kern, grid, kThreads, 0, s, n, rhs + off, w.q.data() + off, op.minv.data() + off, r_vec + off, w.p.data() + off,
+		FI_LAUNCH(kern, grid, kThreads, 0, s, n, rhs + off, zero_guess ? static_cast<const T*>(nullptr) : w.q.data() + off, op.minv.data() + off, r_vec + off, w.p.data() + off,
 		          w.state.data(), tol, max_iter, w.partial.data(), w.ticket.data(), dist ? 1 : 0);
 		if (dist) {
 			dist->allreduce(w.state.data()->part, 3, s);

@@ -68,6 +68,9 @@ struct Operator
 	double           setup_ms = 0;
 	PcgWork<T>       work;
 	DistHooks*       dist = nullptr;  // set for a z-slab of a lattice shared with other ranks
+	// Set by a caller that hands pcg_solve an all-zero guess: the initial residual is then b itself and the operator
+	// application that would compute A x is skipped.  Consumed (reset) by the solve.
+	bool             guess_is_zero = false;
 
 	// q = (S + P) p; when d_dot is non-null it receives p.q (deterministic apart from the order of the data
 	// term's atomics into q).

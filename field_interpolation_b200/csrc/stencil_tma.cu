@@ -14,6 +14,9 @@
 //     2R+1 taps per axis with per-thread coefficient rows that already contain the boundary truncation;
 //   * q and p are written with 128-bit coalesced stores straight from registers.
 // One __syncthreads and one mbarrier wait per plane.
+#include <cstdlib>
+#include <type_traits>
+
 #include "solver.hpp"
 #include "tma.cuh"
 
@@ -452,7 +455,19 @@ void dispatch(const Geom& g, const StencilTables& t, const T* a, const T* b, con
 	if (t.radius <= 1) {
 		launch<T, 1, 3, Fused, 2>(g, t, a, b, c, q, p_new, st, par, d_dot_out, d_partial, d_ticket, d_done, s);
 	} else if (t.radius == 2) {
-		launch<T, 2, 3, Fused, 2>(g, t, a, b, c, q, p_new, st, par, d_dot_out, d_partial, d_ticket, d_done, s);
+		// FI_B200_STENCIL_VARIANT (tuning experiments on the default model_2 operator): 3 = two stages, three blocks per SM;
+		// 4 = four stages, two blocks per SM; anything else = three stages, two blocks per SM (the measured default)
+		static const int variant = [] {
+			const char* e = getenv("FI_B200_STENCIL_VARIANT");
+			return e ? atoi(e) : 0;
+		}();
+		if (variant == 3 && std::is_same<T, float>::value) {
+			launch<T, 2, 2, Fused, 3>(g, t, a, b, c, q, p_new, st, par, d_dot_out, d_partial, d_ticket, d_done, s);
+		} else if (variant == 4 && std::is_same<T, float>::value) {
+			launch<T, 2, 4, Fused, 2>(g, t, a, b, c, q, p_new, st, par, d_dot_out, d_partial, d_ticket, d_done, s);
+		} else {
+			launch<T, 2, 3, Fused, 2>(g, t, a, b, c, q, p_new, st, par, d_dot_out, d_partial, d_ticket, d_done, s);
+		}
 	} else {
 		launch<T, 4, 2, Fused, 1>(g, t, a, b, c, q, p_new, st, par, d_dot_out, d_partial, d_ticket, d_done, s);
 	}

@@ -265,10 +265,12 @@ FI_API int fi_slab_range(int32_t nz, int32_t world, int32_t rank, int32_t* z0, i
 /* A non-uniform partition for this communicator: cuts[0] = 0 < cuts[1] < ... < cuts[world] = nz, rank k owns planes
  * [cuts[k], cuts[k+1]) of every later fi_slab_sdf_solve on an nz-plane lattice (collective in effect: every rank must set
  * the same cuts).  cuts = null: back to fi_slab_range.  The data term makes slabs unequal in cost — the occupied cells of an
- * SDF cloud cluster in a few slabs, and the slowest rank sets the pace of every iteration — so fi_slab_balanced_cuts
- * balances  planes * nx * ny + point_weight * (points whose cell starts in the plane)  instead of the plane count:
- * point_weight = the cost of one data point in units of one lattice cell of an iteration (<= 0: 9, measured on B200:
- * profiles/r1c_trace_n8_before.txt), min_planes = thinnest slab allowed (>= the stencil radius; 2 x radius for multigrid).
+ * SDF cloud cluster in a few slabs, and the slowest rank sets the pace of every iteration.  An iteration is two phases,
+ * each ended by an exchange all ranks wait in: A = stencil + data term, B = the update kernel.  fi_slab_balanced_cuts
+ * minimises  max_rank A + max_rank B  with  A = sum over the slab's planes of (nx ny + point_weight * points whose cell starts
+ * in the plane)  and  B = 1.22 nx ny planes  (bisection over a greedy fill for every cap on the planes of a slab).
+ * point_weight = the cost of one data point in lattice cells of stencil work (<= 0: 30, measured on 8 B200s:
+ * profiles/r2e_trace_n8.txt), min_planes = thinnest slab allowed (>= the stencil radius; 2 x radius for multigrid).
  * Pure function of its arguments (one histogram kernel over the points): every rank computes the same cuts. */
 FI_API int fi_slab_balanced_cuts(const int32_t* sizes /* 3 */, int32_t world, int64_t num_points, const float* positions, int32_t loc,
                           double point_weight, int32_t min_planes, int32_t* cuts /* world + 1 */);
