@@ -391,26 +391,8 @@ __global__ void slots_kernel(const uint64_t* __restrict__ keys, const uint64_t* 
 template <typename T>
 __device__ __forceinline__ void atomic_add(T* p, T v) { atomicAdd(p, v); }
 
-// q[i] += a, q[i + 1] += b.  fp32 with an 8-byte aligned pair: one vector reduction (REDG.ADD.F32x2, sm_90+) instead of
-// two — the data-term kernels are bound by the number of reductions they send to L2, not by bytes.
-template <typename T>
-__device__ __forceinline__ void atomic_add_pair(T* p, T a, T b)
-{
-	atomicAdd(p, a);
-	atomicAdd(p + 1, b);
-}
-#ifndef FI_B200_EMU
-template <>
-__device__ __forceinline__ void atomic_add_pair<float>(float* p, float a, float b)
-{
-	if ((reinterpret_cast<uintptr_t>(p) & 7u) == 0) {
-		asm volatile("red.global.v2.f32.add [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
-	} else {
-		atomicAdd(p, a);
-		atomicAdd(p + 1, b);
-	}
-}
-#endif
+// (Pairing the reductions of x-neighbouring corners into REDG.ADD.F32x2 was tried in round 2 and measured slower on the
+// B200: 0.085 vs 0.078 ms for the 512^3 bench cloud, profiles/r2f_time_iters_variant0.jsonl — scalar reductions stay.)
 
 // One lane per (cell-sorted) point.  Each lane forms its point's contribution to the cell's symmetric block,
 // right-hand side and diagonal; lanes of the same cell are contiguous, so a segmented shuffle reduction folds
@@ -711,20 +693,14 @@ __global__ void __launch_bounds__(kThreads, 3) apply_blocks_kernel(Geom g, int64
 		}
 		T dot = 0;
 #pragma unroll
-		for (int c = 0; c < C; c += 2) {  // corners c, c + 1 are neighbours along x
-			int64_t off = 0;
+		for (int c = 0; c < C; ++c) {
+			if ((mask >> (8 + c)) & 1u) {
+				int64_t off = 0;
 #pragma unroll
-			for (int d = 1; d < D; ++d) { off += ((c >> d) & 1) ? g.stride[d] : 0; }
-			const bool own0 = (mask >> (8 + c)) & 1u, own1 = (mask >> (9 + c)) & 1u;
-			if (own0 && own1) {
-				atomic_add_pair(&q[base + off], out[c], out[c + 1]);
-			} else if (own0) {
+				for (int d = 0; d < D; ++d) { off += ((c >> d) & 1) ? g.stride[d] : 0; }
 				atomic_add(&q[base + off], out[c]);
-			} else if (own1) {
-				atomic_add(&q[base + off + 1], out[c + 1]);
+				dot += pc[c] * out[c];
 			}
-			if (own0) { dot += pc[c] * out[c]; }
-			if (own1) { dot += pc[c + 1] * out[c + 1]; }
 		}
 		mine[0] = static_cast<double>(dot);
 	}
@@ -845,26 +821,14 @@ __global__ void __launch_bounds__(kThreads, 3) apply_blocks_epilogue_kernel(Geom
 		}
 	}
 #pragma unroll
-	for (int c = 0; c < C; c += 2) {  // corners c, c + 1 are neighbours along x: one vector reduction when both rows are owned
-		const int64_t node = base + off[c];
-		const bool    own0 = (mask >> (8 + c)) & 1u, own1 = (mask >> (9 + c)) & 1u;
-		T dd0 = 0, dd1 = 0;
-		if (d_new) {
-			if (own0) { dd0 = -b * minv[node] * out[c]; }
-			if (own1) { dd1 = -b * minv[node + 1] * out[c + 1]; }
-		}
-		if (own0 && own1) {
-			atomic_add_pair(&res[node], -out[c], -out[c + 1]);
+	for (int c = 0; c < C; ++c) {
+		if ((mask >> (8 + c)) & 1u) {
+			const int64_t node = base + off[c];
+			atomic_add(&res[node], -out[c]);
 			if (d_new) {
-				atomic_add_pair(&d_new[node], dd0, dd1);
-				atomic_add_pair(&e[node], dd0, dd1);
-			}
-		} else if (own0 || own1) {
-			const int64_t at = own0 ? node : node + 1;
-			atomic_add(&res[at], own0 ? -out[c] : -out[c + 1]);
-			if (d_new) {
-				atomic_add(&d_new[at], own0 ? dd0 : dd1);
-				atomic_add(&e[at], own0 ? dd0 : dd1);
+				const T dd = -b * minv[node] * out[c];
+				atomic_add(&d_new[node], dd);
+				atomic_add(&e[node], dd);
 			}
 		}
 	}

@@ -27,13 +27,13 @@ namespace {
 using namespace tma;
 
 // ---- geometry of one block -----------------------------------------------------------------------------------
-template <typename T, int R>
+template <typename T, int R, int TY_ = 8>
 struct Tile
 {
 	static constexpr int V    = 16 / sizeof(T);       // elements per 16-byte pack
 	static constexpr int NP   = (R + V - 1) / V;      // halo packs per side in x
 	static constexpr int TXP  = 32;                   // packs per tile row (one per lane)
-	static constexpr int TY   = 8;                    // tile rows (one per warp)
+	static constexpr int TY   = TY_;                  // tile rows: 8 (one per warp) or 7 (the eighth warp only fills halos; see launch)
 	static constexpr int BXP  = TXP + 2 * NP;         // box row in packs
 	static constexpr int BY   = TY + 2 * R;           // box rows
 	// planes of the new direction kept in shared memory: the star reads plane z while the fastest warp may already be writing
@@ -43,15 +43,15 @@ struct Tile
 	static constexpr int BOX_BYTES  = BXP * BY * 16;  // what one TMA load delivers
 };
 
-template <typename T, int R, int S, bool Fused, bool GS>
+template <typename T, int R, int S, bool Fused, bool GS, int TY = 8>
 constexpr size_t smem_bytes()
 {
-	using G = Tile<T, R>;
+	using G = Tile<T, R, TY>;
 	return 128 /* alignment slack */ + static_cast<size_t>(S) * (Fused ? 3 : 1) * G::TILE_BYTES + static_cast<size_t>(G::ring(GS)) * G::TILE_BYTES +
 	       S * sizeof(uint64_t) + 9 * (2 * R + 1) * sizeof(T) + 32 * sizeof(double) + 64;
 }
 
-template <typename T, int R, int S, bool Fused, int MINB, bool Epi, bool GS>
+template <typename T, int R, int S, bool Fused, int MINB, bool Epi, bool GS, int TY>
 __global__ void __launch_bounds__(256, MINB)
     stencil3d_tma_kernel(const __grid_constant__ CUtensorMap map_a,  // p (plain) or r (fused)
                          const __grid_constant__ CUtensorMap map_b,  // M^-1 (fused)
@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(256, MINB)
                          const PcgState* st, int par, double* dot_out, double* partial, unsigned* ticket, const int* done, EpiArgs<T> epi)
 {
 	static_assert(!(Fused && Epi), "the epilogue mode takes a plain input");
-	using G           = Tile<T, R>;
+	using G           = Tile<T, R, TY>;
 	constexpr int V   = G::V;
 	constexpr int NP  = G::NP;
 	constexpr int NA  = Fused ? 3 : 1;
@@ -97,7 +97,8 @@ __global__ void __launch_bounds__(256, MINB)
 	// every slab recomputes its neighbours' boundary planes instead of exchanging p)
 	const int wlo = blockIdx.z == 0 ? max(0, zo0 - R) : zb;
 	const int whi = ze == zo1 ? min(nzl, zo1 + R) : ze;
-	const bool   in_xy = (x0 < nx) && (y < ny);
+	const bool   has_own = ty < G::TY;  // with 7-row tiles the eighth warp owns no row: it only fills halos
+	const bool   in_xy = has_own && (x0 < nx) && (y < ny);
 	const size_t plane = static_cast<size_t>(nx) * ny;
 
 	if (tid == 0) {
@@ -210,8 +211,10 @@ __global__ void __launch_bounds__(256, MINB)
 			const Pack* sc = Fused ? stage_ptr(stage, 2) : nullptr;
 			Pack*       rg = ring_ptr(slot);
 			// newest plane of the own column -> pipe[k]; plane lp - 2R + t sits in pipe[(k + 1 + t) % W]
-			pipe[k].v  = direction(sa, sb, sc, own_at);
-			rg[own_at] = pipe[k].v;
+			if (has_own) {
+				pipe[k].v  = direction(sa, sb, sc, own_at);
+				rg[own_at] = pipe[k].v;
+			}
 			if (has_yh) { rg[yh_at] = direction(sa, sb, sc, yh_at); }
 			if (has_xh) { rg[xh_at] = direction(sa, sb, sc, xh_at); }
 			if (has_ch) { rg[ch_at] = direction(sa, sb, sc, ch_at); }
@@ -361,10 +364,10 @@ __global__ void __launch_bounds__(256, MINB)
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------
-template <typename T, int R>
+template <typename T, int R, int TY>
 CUtensorMap make_map(const Geom& g, const T* ptr)
 {
-	using G = Tile<T, R>;
+	using G = Tile<T, R, TY>;
 	CUtensorMap m;
 	std::memset(&m, 0, sizeof(m));
 	EncodeFn fn = encode_fn();
@@ -380,25 +383,13 @@ CUtensorMap make_map(const Geom& g, const T* ptr)
 	return m;
 }
 
-template <typename T, int R, int S, bool Fused, int MINB, bool Epi, bool GS>
-void launch_gs(const Geom& g, const StencilTables& t, const T* a, const T* b, const T* c, T* q, T* p_new, const PcgState* st, int par,
-            double* d_dot_out, double* d_partial, unsigned* d_ticket, const int* d_done, cudaStream_t s, const EpiArgs<T>& epi = EpiArgs<T>())
+// z chunking.  A block marches its chunk plane by plane and pays 2R halo planes plus the pipeline fill per chunk, so
+// chunks should be long; blocks run in waves of `resident`, so their number should fill whole waves.  Returns the chunk
+// count that minimises waves * (planes per chunk + 2R + fill) for tiles of `ty` rows, and that cost.
+inline double plan_chunks(const Geom& g, int R, int S, int minb, int tx_cells, int ty, int* out_chunks)
 {
-	using G = Tile<T, R>;
-	TmaTables<T> tab;
-	for (int ax = 0; ax < kMaxDim; ++ax) {
-		for (int cl = 0; cl < 9; ++cl) {
-			for (int k = 0; k < 9; ++k) { tab.band[ax][cl][k] = static_cast<T>(t.band[ax][cl][k]); }
-		}
-	}
-	const CUtensorMap ma = make_map<T, R>(g, a);
-	const CUtensorMap mb = Fused ? make_map<T, R>(g, b) : ma;
-	const CUtensorMap mc = Fused ? make_map<T, R>(g, c) : ma;
-	const int tiles_x = div_up(g.size[0], G::TXP * G::V), tiles_y = div_up(g.size[1], G::TY);
-	// z chunking.  A block marches its chunk plane by plane and pays 2R halo planes plus the pipeline fill per
-	// chunk, so chunks should be long; blocks run in waves of `resident`, so their number should fill whole waves.
-	// Pick the chunk count that minimises waves * (planes per chunk + 2R + fill).
-	const int64_t resident = static_cast<int64_t>(sm_count()) * MINB;
+	const int     tiles_x = div_up(g.size[0], tx_cells), tiles_y = div_up(g.size[1], ty);
+	const int64_t resident = static_cast<int64_t>(sm_count()) * minb;
 	const int64_t tiles    = static_cast<int64_t>(tiles_x) * tiles_y;
 	const int     nown     = g.zown1 - g.zown0;
 	int           chunks   = 1;
@@ -415,11 +406,31 @@ void launch_gs(const Geom& g, const StencilTables& t, const T* a, const T* b, co
 			chunks = cc;
 		}
 	}
-	const int zchunk = div_up(nown, chunks);
-	chunks           = div_up(nown, zchunk);
+	*out_chunks = chunks;
+	return best;
+}
+
+template <typename T, int R, int S, bool Fused, int MINB, bool Epi, bool GS, int TY>
+void launch_ty(const Geom& g, const StencilTables& t, int chunks, const T* a, const T* b, const T* c, T* q, T* p_new, const PcgState* st, int par,
+               double* d_dot_out, double* d_partial, unsigned* d_ticket, const int* d_done, cudaStream_t s, const EpiArgs<T>& epi)
+{
+	using G = Tile<T, R, TY>;
+	TmaTables<T> tab;
+	for (int ax = 0; ax < kMaxDim; ++ax) {
+		for (int cl = 0; cl < 9; ++cl) {
+			for (int k = 0; k < 9; ++k) { tab.band[ax][cl][k] = static_cast<T>(t.band[ax][cl][k]); }
+		}
+	}
+	const CUtensorMap ma = make_map<T, R, TY>(g, a);
+	const CUtensorMap mb = Fused ? make_map<T, R, TY>(g, b) : ma;
+	const CUtensorMap mc = Fused ? make_map<T, R, TY>(g, c) : ma;
+	const int tiles_x = div_up(g.size[0], G::TXP * G::V), tiles_y = div_up(g.size[1], G::TY);
+	const int nown    = g.zown1 - g.zown0;
+	const int zchunk  = div_up(nown, chunks);
+	chunks            = div_up(nown, zchunk);
 	dim3 grid(tiles_x, tiles_y, chunks);
-	auto kern = stencil3d_tma_kernel<T, R, S, Fused, MINB, Epi, GS>;
-	constexpr size_t smem = smem_bytes<T, R, S, Fused, GS>();
+	auto kern = stencil3d_tma_kernel<T, R, S, Fused, MINB, Epi, GS, TY>;
+	constexpr size_t smem = smem_bytes<T, R, S, Fused, GS, TY>();
 	static bool configured = false;  // per instantiation
 	if (!configured) {
 		FI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -427,6 +438,42 @@ void launch_gs(const Geom& g, const StencilTables& t, const T* a, const T* b, co
 	}
 	FI_LAUNCH(kern, grid, 256, smem, s, ma, mb, mc, g.size[0], g.size[1], g.nzl, g.zown0, g.zown1, g.zoff, g.size[2], zchunk, tab,
 	          static_cast<T>(t.gs2), q, p_new, st, par, d_dot_out, d_partial, d_ticket, d_done, epi);
+}
+
+// Tile height.  Inside a long timed loop the GPU runs power-capped (SM clock ~1.78 of 1.97 GHz) and the kernel is bound by
+// the SMs, not by HBM: what counts is the work of the busiest SM.  512^2 planes give 4 x 64 = 256 tiles of 8 rows on 296
+// resident slots — 108 SMs carry two blocks, 40 carry one; with 7-row tiles they are 4 x 74 = 296 blocks, two per SM, each
+// 7/8 of the work (the eighth warp only fills halo rows).  Measured (r2g): see profiles.  The choice minimises
+// waves x planes x rows per block over {8, 7}; FI_B200_STENCIL_TY=7|8 forces one.
+template <typename T, int R, int S, bool Fused, int MINB, bool Epi, bool GS>
+void launch_gs(const Geom& g, const StencilTables& t, const T* a, const T* b, const T* c, T* q, T* p_new, const PcgState* st, int par,
+               double* d_dot_out, double* d_partial, unsigned* d_ticket, const int* d_done, cudaStream_t s, const EpiArgs<T>& epi = EpiArgs<T>())
+{
+	using G8 = Tile<T, R, 8>;
+	int c8 = 1, c7 = 1;
+	plan_chunks(g, R, S, MINB, G8::TXP * G8::V, 8, &c8);
+	bool seven = false;
+	if (R <= 2) {
+		static const int forced = [] {
+			const char* e = getenv("FI_B200_STENCIL_TY");
+			return e ? atoi(e) : 0;
+		}();
+		plan_chunks(g, R, S, MINB, G8::TXP * G8::V, 7, &c7);
+		// work of the busiest SM: whole waves x planes marched per block x rows per block
+		auto busiest = [&](int ty, int chunks) {
+			const int64_t blocks = static_cast<int64_t>(div_up(g.size[0], G8::TXP * G8::V)) * div_up(g.size[1], ty) * chunks;
+			const int64_t waves  = (blocks + static_cast<int64_t>(sm_count()) * MINB - 1) / (static_cast<int64_t>(sm_count()) * MINB);
+			return static_cast<double>(waves) * (div_up(g.zown1 - g.zown0, chunks) + 2 * R + S + 1) * ty;
+		};
+		seven = forced == 7 || (forced != 8 && busiest(7, c7) < 0.97 * busiest(8, c8));
+	}
+	if constexpr (R <= 2) {
+		if (seven) {
+			launch_ty<T, R, S, Fused, MINB, Epi, GS, 7>(g, t, c7, a, b, c, q, p_new, st, par, d_dot_out, d_partial, d_ticket, d_done, s, epi);
+			return;
+		}
+	}
+	launch_ty<T, R, S, Fused, MINB, Epi, GS, 8>(g, t, c8, a, b, c, q, p_new, st, par, d_dot_out, d_partial, d_ticket, d_done, s, epi);
 }
 
 template <typename T, int R, int S, bool Fused, int MINB, bool Epi = false>

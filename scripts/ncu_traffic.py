@@ -26,8 +26,9 @@ for row in csv.DictReader(l for l in open(path) if not l.startswith("==")):
         continue
     a = per.setdefault((row["ID"], row["Kernel Name"]), {"r": 0.0, "w": 0.0})
     a["r" if m.endswith("read.sum") else "w"] += float(row["Metric Value"].replace(",", "")) * scale_b.get(row["Metric Unit"], 1.0)
-# the fused PCG kernel (template arguments <T, R, S, Fused = 1, MINB, Epi = 0>): skip the first launches (cold L2, beta = 0)
-fused = [(k, v) for k, v in per.items() if "stencil3d_tma_kernel" in k[1] and ", 1, 2, 0>" in k[1].replace("(bool)", "")]
+# the fused PCG kernel (template arguments <T, R, S, Fused = 1, MINB, Epi, GS, TY>): skip the first launches (cold L2, beta = 0)
+import re
+fused = [(k, v) for k, v in per.items() if re.search(r"stencil3d_tma_kernel<\w+, \d+, \d+, (1|true|\(bool\)1),", k[1])]
 if not fused:
     fused = [(k, v) for k, v in per.items() if "stencil3d_tma_kernel" in k[1]]
 use = fused[2:] if len(fused) > 4 else fused
@@ -40,6 +41,6 @@ n = {"sdf3d_512_1M": 512, "sdf3d_256_1M": 256}.get(workload, 512)
 B = 4 if precision == "f32" else 8
 doc[f"{workload}:{precision}"] = {"kernel": use[0][0][1][:80], "launches_averaged": len(use), "dram_bytes_per_launch": r + w, "dram_read_bytes": r, "dram_write_bytes": w,
                                   "algorithmic_bytes_per_launch": 5 * B * n ** 3, "kernel_source_sha": bench.kernel_source_sha(),
-                                  "captured": datetime.datetime.utcnow().strftime("%Y-%m-%dT%H:%MZ"), "source": os.path.basename(path)}
+                                  "captured": datetime.datetime.now(datetime.timezone.utc).strftime("%Y-%m-%dT%H:%MZ"), "source": os.path.basename(path)}
 json.dump(doc, open(out, "w"), indent=1)
 print(json.dumps(doc[f"{workload}:{precision}"], indent=1))
