@@ -21,6 +21,7 @@ struct PcgState
 	long long iters;
 	long long max_iters;
 	double part[4];  // multi-GPU: this rank's partial sums, all-reduced in place before the finish kernels read them
+	double alpha_prev;  // step length of the last even-numbered iteration, whose x update is applied one iteration later (solver.cu)
 };
 
 // ---- multi-GPU: scalar all-reduce and halo push over NVLink peer memory, inside the CG kernels -------------

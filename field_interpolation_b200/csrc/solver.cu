@@ -6,6 +6,10 @@
 // converge (the last iterate is returned).  A^T A is symmetric positive (semi-)definite, so CG replaces
 // Eigen's BiCGSTAB at half the operator applications per iteration.
 //
+// x is not needed by the iteration itself, and the fused path keeps the last two directions (p ping-pongs between two
+// buffers), so x is updated every SECOND iteration with both terms, x += a_k p_k + a_{k+1} p_{k+1}: the even iteration moves
+// 16 B/cell (q, r, M read, r written), the odd one 32 B/cell — 24 on average instead of 28; an odd iteration count is
+// completed by one flush after the loop.  (kXClassic / kXSkip / kXBoth below.)
 // Per iteration three kernels touch the lattice vectors:
 //   apply      q = (S+P) p, p.q                      read p, write q              8 B/cell (fp32)
 //   update     x += a p, r -= a q, r.Mr, r.r         read x,p,q,r,M, write x,r   28 B/cell
@@ -162,9 +166,61 @@ __global__ void pcg_update_finish_kernel(PcgState* st, int par)
 	if (rr <= st->tol2bb || st->iters >= st->max_iters || !(rho > 0.0)) { st->done = 1; }
 }
 
-template <typename T>
+// How an update kernel treats x (see the header comment): every iteration; not at all (even iteration of the deferred scheme:
+// the step length is parked in PcgState::alpha_prev); or with this and the previous iteration's terms (odd iteration).
+enum XMode { kXClassic = 0, kXSkip = 1, kXBoth = 2 };
+
+// x, r of `count` consecutive elements starting at i: the element-wise part shared by the update kernels.
+template <typename T, int XM, bool PACKED>
+__device__ __forceinline__ void update_elements(int64_t k, T* __restrict__ x, T* __restrict__ r, const T* __restrict__ p, const T* __restrict__ p_prev,
+                                                const T* __restrict__ q, const T* __restrict__ minv, T alpha, T alpha_prev, double (&acc)[2],
+                                                typename Pack<T>::type* r_out)
+{
+	using P         = typename Pack<T>::type;
+	constexpr int V = PACKED ? Pack<T>::V : 1;
+	T xa[V], ra[V], pa[V], ppa[V], qa[V], ma[V];
+	if (PACKED) {
+		*reinterpret_cast<P*>(ra) = reinterpret_cast<const P*>(r)[k];
+		*reinterpret_cast<P*>(qa) = reinterpret_cast<const P*>(q)[k];
+		*reinterpret_cast<P*>(ma) = reinterpret_cast<const P*>(minv)[k];
+		if (XM != kXSkip) {
+			*reinterpret_cast<P*>(xa) = reinterpret_cast<const P*>(x)[k];
+			*reinterpret_cast<P*>(pa) = reinterpret_cast<const P*>(p)[k];
+		}
+		if (XM == kXBoth) { *reinterpret_cast<P*>(ppa) = reinterpret_cast<const P*>(p_prev)[k]; }
+	} else {
+		ra[0] = r[k];
+		qa[0] = q[k];
+		ma[0] = minv[k];
+		if (XM != kXSkip) {
+			xa[0] = x[k];
+			pa[0] = p[k];
+		}
+		if (XM == kXBoth) { ppa[0] = p_prev[k]; }
+	}
+#pragma unroll
+	for (int j = 0; j < V; ++j) {
+		if (XM == kXClassic) { xa[j] += alpha * pa[j]; }
+		if (XM == kXBoth) { xa[j] += alpha_prev * ppa[j] + alpha * pa[j]; }
+		ra[j] -= alpha * qa[j];
+		const double rd = static_cast<double>(ra[j]);
+		acc[0] += rd * static_cast<double>(ma[j] * ra[j]);
+		acc[1] += rd * rd;
+	}
+	if (PACKED) {
+		if (XM != kXSkip) { reinterpret_cast<P*>(x)[k] = *reinterpret_cast<const P*>(xa); }
+		reinterpret_cast<P*>(r)[k] = *reinterpret_cast<const P*>(ra);
+		if (r_out) { *r_out = *reinterpret_cast<const P*>(ra); }
+	} else {
+		if (XM != kXSkip) { x[k] = xa[0]; }
+		r[k] = ra[0];
+		if (r_out) { reinterpret_cast<T*>(r_out)[0] = ra[0]; }
+	}
+}
+
+template <typename T, int XM>
 __global__ void __launch_bounds__(kThreads) pcg_update_kernel(int64_t n, T* __restrict__ x, T* __restrict__ r,
-                                                              const T* __restrict__ p, const T* __restrict__ q,
+                                                              const T* __restrict__ p, const T* __restrict__ p_prev, const T* __restrict__ q,
                                                               const T* __restrict__ minv, PcgState* st, int par,
                                                               double* partial, unsigned* ticket, int dist)
 {
@@ -178,41 +234,20 @@ __global__ void __launch_bounds__(kThreads) pcg_update_kernel(int64_t n, T* __re
 		}
 		return;
 	}
-	const T alpha = static_cast<T>(st->rho[par] / pq);
-	using P       = typename Pack<T>::type;
-	constexpr int V = Pack<T>::V;
+	const double alpha_d = st->rho[par] / pq;
+	const T      alpha = static_cast<T>(alpha_d), alpha_prev = XM == kXBoth ? static_cast<T>(st->alpha_prev) : T(0);
 	double acc[2] = {0, 0};
 	for_each_pack<T>(n, [&](int64_t k, bool packed) {
 		if (packed) {
-			P        xv = reinterpret_cast<P*>(x)[k], rv = reinterpret_cast<P*>(r)[k];
-			const P  pv = reinterpret_cast<const P*>(p)[k], qv = reinterpret_cast<const P*>(q)[k];
-			const P  mv = reinterpret_cast<const P*>(minv)[k];
-			T*       xa = reinterpret_cast<T*>(&xv);
-			T*       ra = reinterpret_cast<T*>(&rv);
-			const T* pa = reinterpret_cast<const T*>(&pv);
-			const T* qa = reinterpret_cast<const T*>(&qv);
-			const T* ma = reinterpret_cast<const T*>(&mv);
-#pragma unroll
-			for (int j = 0; j < V; ++j) {
-				xa[j] += alpha * pa[j];
-				ra[j] -= alpha * qa[j];
-				const double rd = static_cast<double>(ra[j]);
-				acc[0] += rd * static_cast<double>(ma[j] * ra[j]);
-				acc[1] += rd * rd;
-			}
-			reinterpret_cast<P*>(x)[k] = xv;
-			reinterpret_cast<P*>(r)[k] = rv;
+			update_elements<T, XM, true>(k, x, r, p, p_prev, q, minv, alpha, alpha_prev, acc, nullptr);
 		} else {
-			x[k] += alpha * p[k];
-			const T ri = r[k] - alpha * q[k];
-			r[k]       = ri;
-			acc[0] += static_cast<double>(ri) * static_cast<double>(minv[k] * ri);
-			acc[1] += static_cast<double>(ri) * static_cast<double>(ri);
+			update_elements<T, XM, false>(k, x, r, p, p_prev, q, minv, alpha, alpha_prev, acc, nullptr);
 		}
 	});
 	acc[0] = block_sum(acc[0], red);
 	acc[1] = block_sum(acc[1], red);
 	grid_sum<2>(acc, partial, ticket, red, [&](const double(&tot)[2]) {
+		if (XM == kXSkip) { st->alpha_prev = alpha_d; }
 		if (dist) {  // all-reduced, then pcg_update_finish_kernel
 			st->part[0] = tot[0];
 			st->part[1] = tot[1];
@@ -228,9 +263,9 @@ __global__ void __launch_bounds__(kThreads) pcg_update_kernel(int64_t n, T* __re
 // The update kernel of a slab on the peer-memory path: waits for the all-reduced p.Ap in its mailbox, updates x
 // and r, stores the boundary planes of the new r straight into the neighbours' halo planes (NVLink peer stores),
 // and the last block publishes this slab's (r.Mr, r.r) to every rank.
-template <typename T>
+template <typename T, int XM>
 __global__ void __launch_bounds__(kThreads) pcg_update_peer_kernel(int64_t n, T* __restrict__ x, T* __restrict__ r,
-                                                                   const T* __restrict__ p, const T* __restrict__ q,
+                                                                   const T* __restrict__ p, const T* __restrict__ p_prev, const T* __restrict__ q,
                                                                    const T* __restrict__ minv, PcgState* st, int par, double* partial,
                                                                    unsigned* ticket, PeerLink L, HaloPush<T> push, unsigned long long base, int fold)
 {
@@ -260,40 +295,23 @@ __global__ void __launch_bounds__(kThreads) pcg_update_peer_kernel(int64_t n, T*
 	const double pq    = s_pq;
 	const bool   bad   = !s_ok || !(pq > 0.0);  // lost peer, or breakdown (singular direction / NaN): keep the last iterate
 	double       acc[2] = {0, 0};
+	const double alpha_d = (!was_done && !bad) ? st->rho[par] / pq : 0.0;
 	if (!was_done && !bad) {
-		const T alpha = static_cast<T>(st->rho[par] / pq);
+		const T alpha = static_cast<T>(alpha_d), alpha_prev = XM == kXBoth ? static_cast<T>(st->alpha_prev) : T(0);
 		using P       = typename Pack<T>::type;
 		constexpr int V = Pack<T>::V;
 		const int64_t hi_from = n - push.count;
 		for_each_pack<T>(n, [&](int64_t k, bool packed) {
 			if (packed) {
-				P        xv = reinterpret_cast<P*>(x)[k], rv = reinterpret_cast<P*>(r)[k];
-				const P  pv = reinterpret_cast<const P*>(p)[k], qv = reinterpret_cast<const P*>(q)[k];
-				const P  mv = reinterpret_cast<const P*>(minv)[k];
-				T*       xa = reinterpret_cast<T*>(&xv);
-				T*       ra = reinterpret_cast<T*>(&rv);
-				const T* pa = reinterpret_cast<const T*>(&pv);
-				const T* qa = reinterpret_cast<const T*>(&qv);
-				const T* ma = reinterpret_cast<const T*>(&mv);
-#pragma unroll
-				for (int j = 0; j < V; ++j) {
-					xa[j] += alpha * pa[j];
-					ra[j] -= alpha * qa[j];
-					const double rd = static_cast<double>(ra[j]);
-					acc[0] += rd * static_cast<double>(ma[j] * ra[j]);
-					acc[1] += rd * rd;
-				}
-				reinterpret_cast<P*>(x)[k] = xv;
-				reinterpret_cast<P*>(r)[k] = rv;
+				P rv;
+				update_elements<T, XM, true>(k, x, r, p, p_prev, q, minv, alpha, alpha_prev, acc, &rv);
 				const int64_t i = k * V;  // halo extents are whole planes of a lattice whose x size is a multiple of V
 				if (push.lo && i < push.count) { *reinterpret_cast<P*>(push.lo + i) = rv; }
 				if (push.hi && i >= hi_from) { *reinterpret_cast<P*>(push.hi + (i - hi_from)) = rv; }
 			} else {
-				x[k] += alpha * p[k];
-				const T ri = r[k] - alpha * q[k];
-				r[k]       = ri;
-				acc[0] += static_cast<double>(ri) * static_cast<double>(minv[k] * ri);
-				acc[1] += static_cast<double>(ri) * static_cast<double>(ri);
+				P rv;
+				update_elements<T, XM, false>(k, x, r, p, p_prev, q, minv, alpha, alpha_prev, acc, &rv);
+				const T ri = reinterpret_cast<const T*>(&rv)[0];
 				if (push.lo && k < push.count) { push.lo[k] = ri; }
 				if (push.hi && k >= hi_from) { push.hi[k - hi_from] = ri; }
 			}
@@ -308,6 +326,7 @@ __global__ void __launch_bounds__(kThreads) pcg_update_peer_kernel(int64_t n, T*
 			st->breakdown = s_ok ? 1 : 2;
 			st->done      = 1;
 		}
+		if (XM == kXSkip && !was_done && !bad) { st->alpha_prev = alpha_d; }
 		s_tot[0] = tot[0];
 		s_tot[1] = tot[1];
 		s_pub    = 1;
@@ -405,6 +424,15 @@ __global__ void add_f32_f64_kernel(int64_t n, const float* __restrict__ e, doubl
 {
 	const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
 	for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) { x[i] += static_cast<double>(e[i]); }
+}
+
+// x += alpha_prev * p: completes an odd number of iterations of the deferred x update
+template <typename T>
+__global__ void __launch_bounds__(kThreads) pcg_flush_x_kernel(int64_t n, T* __restrict__ x, const T* __restrict__ p, const PcgState* st)
+{
+	const T       a      = static_cast<T>(st->alpha_prev);
+	const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+	for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) { x[i] += a * p[i]; }
 }
 
 template <typename T>
@@ -581,12 +609,14 @@ PcgResult pcg_solve(Operator<T>& op, const T* b, T* x, double tol, long long max
 		const char* fold_env  = std::getenv("FI_B200_PEER_FOLD");
 		const int   fold_mode = !link ? 0 : (fold_env && *fold_env >= '0' && *fold_env <= '3' ? *fold_env - '0' : 2);
 		const bool  data_publishes = fold_mode >= 2, update_finishes = fold_mode == 1 || fold_mode == 2;
+		bool deferred_x = false;  // the fused path updates x every second iteration (kXSkip / kXBoth)
 		auto enqueue_round = [&] {
 			for (int it = 0; it < check_every; ++it) {
 				const int par = it & 1;
 				// fused form: direction update folded into the stencil's load stage (p ping-pongs between two buffers)
 				const bool fused = stencil_fused_step<T>(op.use_fast, op.g, op.tabs, r_vec, op.minv.data(), pp[par], pp[par ^ 1], w.q.data(),
 				                                         w.state.data(), par, d_pq, op.partial.data(), op.ticket.data(), d_done, s);
+				deferred_x = deferred_x || fused;
 				if (fused && link) {
 					// peer-memory path: no NCCL inside the iteration
 					PeerPublish pub;
@@ -598,15 +628,15 @@ PcgResult pcg_solve(Operator<T>& op, const T* b, T* x, double tol, long long max
 					const bool published = apply_data_term<T>(op.g, op.data, pp[par ^ 1], w.q.data(), d_pq, d_done, s, data_publishes ? &pub : nullptr);
 					const bool in_update = fold_mode == 1;
 					if (!published && !in_update) { FI_LAUNCH(peer_publish_kernel, 1, 32, 0, s, *link, 0, par, seq_base, w.state.data(), d_pq, 1, d_done); }
-					auto ku = pcg_update_peer_kernel<T>;
-					FI_LAUNCH(ku, grid, kThreads, 0, s, n, x + off, r_vec + off, pp[par ^ 1] + off, w.q.data() + off, op.minv.data() + off,
+					auto ku = par == 0 ? pcg_update_peer_kernel<T, kXSkip> : pcg_update_peer_kernel<T, kXBoth>;
+					FI_LAUNCH(ku, grid, kThreads, 0, s, n, x + off, r_vec + off, pp[par ^ 1] + off, pp[par] + off, w.q.data() + off, op.minv.data() + off,
 					          w.state.data(), par, w.partial.data(), w.ticket.data(), *link, push, seq_base, (in_update ? 1 : 0) | (update_finishes ? 2 : 0));
 					if (!update_finishes) { FI_LAUNCH(pcg_update_finish_peer_kernel, 1, 32, 0, s, w.state.data(), par, *link, seq_base); }
 				} else if (fused) {
 					apply_data_term<T>(op.g, op.data, pp[par ^ 1], w.q.data(), d_pq, d_done, s);
 					if (dist) { dist->allreduce(d_pq, 1, s); }
-					auto ku = pcg_update_kernel<T>;
-					FI_LAUNCH(ku, grid, kThreads, 0, s, n, x + off, r_vec + off, pp[par ^ 1] + off, w.q.data() + off, op.minv.data() + off,
+					auto ku = par == 0 ? pcg_update_kernel<T, kXSkip> : pcg_update_kernel<T, kXBoth>;
+					FI_LAUNCH(ku, grid, kThreads, 0, s, n, x + off, r_vec + off, pp[par ^ 1] + off, pp[par] + off, w.q.data() + off, op.minv.data() + off,
 					          w.state.data(), par, w.partial.data(), w.ticket.data(), dist ? 1 : 0);
 					if (dist) {
 						dist->allreduce(w.state.data()->part, 2, s);
@@ -616,8 +646,8 @@ PcgResult pcg_solve(Operator<T>& op, const T* b, T* x, double tol, long long max
 				} else {
 					FI_REQUIRE(dist == nullptr, FI_ERR_UNSUPPORTED, "a slab-sharded solve needs the fused 3D stencil kernel");
 					op.apply(w.p.data(), w.q.data(), d_pq, d_done, s);
-					auto ku = pcg_update_kernel<T>;
-					FI_LAUNCH(ku, grid, kThreads, 0, s, n, x, w.r.data(), w.p.data(), w.q.data(), op.minv.data(), w.state.data(), par,
+					auto ku = pcg_update_kernel<T, kXClassic>;
+					FI_LAUNCH(ku, grid, kThreads, 0, s, n, x, w.r.data(), w.p.data(), static_cast<const T*>(nullptr), w.q.data(), op.minv.data(), w.state.data(), par,
 					          w.partial.data(), w.ticket.data(), 0);
 					auto kd = pcg_direction_kernel<T>;
 					FI_LAUNCH(kd, grid, kThreads, 0, s, n, w.r.data(), op.minv.data(), w.p.data(), w.state.data(), par);
@@ -669,6 +699,11 @@ PcgResult pcg_solve(Operator<T>& op, const T* b, T* x, double tol, long long max
 			}
 			cudaGraphExecDestroy(exec);
 			cudaGraphDestroy(graph);
+		}
+		if (deferred_x && (h.iters & 1)) {
+			// an odd number of iterations ran: the last one (even-numbered) parked its x update — p_new of an even iteration is pp[1]
+			auto kf = pcg_flush_x_kernel<T>;
+			FI_LAUNCH(kf, grid, kThreads, 0, s, n, x + off, static_cast<const T*>(pp[1] + off), static_cast<const PcgState*>(w.state.data()));
 		}
 		FI_CUDA(cudaEventRecord(l1, s));
 		FI_CUDA(cudaEventSynchronize(l1));
@@ -827,6 +862,7 @@ void time_kernels(Operator<T>& op, int iterations, int check_every, double* out,
 	h.max_iters = 1ll << 60;
 	h.tol2bb    = 0;
 	h.iters     = 1;
+	h.alpha_prev = 0;
 	if (!(h.rho[0] > 0)) { h.rho[0] = 1; }
 	if (!(h.rho[1] > 0)) { h.rho[1] = 1; }
 	if (!(h.pq > 0)) { h.pq = 1; }
@@ -862,9 +898,20 @@ void time_kernels(Operator<T>& op, int iterations, int check_every, double* out,
 	FI_CUDA(cudaMemcpyAsync(w.state.data(), &h, sizeof(h), cudaMemcpyHostToDevice, s));
 	FI_CUDA(cudaStreamSynchronize(s));
 	out[2] = timed([&](int i) {
-		auto ku = pcg_update_kernel<T>;
-		FI_LAUNCH(ku, vec_grid(n), kThreads, 0, s, n, x.data(), w.r.data(), w.p.data(), w.q.data(), op.minv.data(), w.state.data(), 0,
-		          w.partial.data(), w.ticket.data(), 0);  // reads rho[0], pq (frozen); writes rho[1], rr, iters
+		// the fused path alternates an iteration that leaves x alone with one that applies two terms (deferred x update)
+		if (!fused) {
+			auto ku = pcg_update_kernel<T, kXClassic>;
+			FI_LAUNCH(ku, vec_grid(n), kThreads, 0, s, n, x.data(), w.r.data(), w.p.data(), static_cast<const T*>(nullptr), w.q.data(), op.minv.data(), w.state.data(), 0,
+			          w.partial.data(), w.ticket.data(), 0);  // reads rho[0], pq (frozen); writes rho[1], rr, iters
+		} else if ((i & 1) == 0) {
+			auto ku = pcg_update_kernel<T, kXSkip>;
+			FI_LAUNCH(ku, vec_grid(n), kThreads, 0, s, n, x.data(), w.r.data(), w.p2.data(), w.p.data(), w.q.data(), op.minv.data(), w.state.data(), 0,
+			          w.partial.data(), w.ticket.data(), 0);
+		} else {
+			auto ku = pcg_update_kernel<T, kXBoth>;
+			FI_LAUNCH(ku, vec_grid(n), kThreads, 0, s, n, x.data(), w.r.data(), w.p.data(), w.p2.data(), w.q.data(), op.minv.data(), w.state.data(), 0,
+			          w.partial.data(), w.ticket.data(), 0);
+		}
 	});
 	out[3] = 0.0;
 	if (!fused) {
