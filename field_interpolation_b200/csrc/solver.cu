@@ -64,6 +64,24 @@ __device__ __forceinline__ void for_each_pack(int64_t n, F&& f)
 	}
 }
 
+// The same with a contiguous range of packs per block (coalesced inside the block) instead of a grid-stride walk: only the
+// first and last few blocks touch the ends of the vector.  Returns the block's element range through first / last.
+template <typename T, typename F>
+__device__ __forceinline__ void for_each_pack_blocked(int64_t n, int64_t* first, int64_t* last, F&& f)
+{
+	constexpr int V      = Pack<T>::V;
+	const int64_t npacks = n / V;
+	const int64_t chunk  = (npacks + gridDim.x - 1) / gridDim.x;
+	const int64_t k0 = static_cast<int64_t>(blockIdx.x) * chunk, k1 = min(k0 + chunk, npacks);
+	for (int64_t k = k0 + threadIdx.x; k < k1; k += blockDim.x) { f(k, true); }
+	*first = k0 * V;
+	*last  = k1 * V;
+	if (blockIdx.x == gridDim.x - 1) {
+		for (int64_t i = npacks * V + threadIdx.x; i < n; i += blockDim.x) { f(i, false); }
+		*last = n;
+	}
+}
+
 // r = b - q, p = M r; rho = r.p, rr = r.r, bb = b.b
 template <typename T>
 __global__ void __launch_bounds__(kThreads) pcg_init_kernel(int64_t n, const T* __restrict__ b, const T* __restrict__ q,
@@ -296,12 +314,14 @@ __global__ void __launch_bounds__(kThreads) pcg_update_peer_kernel(int64_t n, T*
 	const bool   bad   = !s_ok || !(pq > 0.0);  // lost peer, or breakdown (singular direction / NaN): keep the last iterate
 	double       acc[2] = {0, 0};
 	const double alpha_d = (!was_done && !bad) ? st->rho[par] / pq : 0.0;
+	bool         pushed  = false;
 	if (!was_done && !bad) {
 		const T alpha = static_cast<T>(alpha_d), alpha_prev = XM == kXBoth ? static_cast<T>(st->alpha_prev) : T(0);
 		using P       = typename Pack<T>::type;
 		constexpr int V = Pack<T>::V;
 		const int64_t hi_from = n - push.count;
-		for_each_pack<T>(n, [&](int64_t k, bool packed) {
+		int64_t       first = 0, last = 0;
+		for_each_pack_blocked<T>(n, &first, &last, [&](int64_t k, bool packed) {
 			if (packed) {
 				P rv;
 				update_elements<T, XM, true>(k, x, r, p, p_prev, q, minv, alpha, alpha_prev, acc, &rv);
@@ -316,11 +336,15 @@ __global__ void __launch_bounds__(kThreads) pcg_update_peer_kernel(int64_t n, T*
 				if (push.hi && k >= hi_from) { push.hi[k - hi_from] = ri; }
 			}
 		});
+		// only the blocks at the two ends of the slab stored into a neighbour's memory
+		pushed = (push.lo && first < push.count) || (push.hi && last > hi_from);
 	}
 	acc[0] = block_sum(acc[0], red);
 	acc[1] = block_sum(acc[1], red);
-	// peer stores of every thread of this block are ordered before the ticket below (bar.sync above, fence here)
-	if (threadIdx.x == 0) { __threadfence_system(); }
+	// peer stores of every thread of this block are ordered before the ticket below (bar.sync above, fence here).  A
+	// system-scope fence while the SM streams gigabytes of ordinary stores is expensive: only the blocks that pushed pay it
+	// (block-contiguous ranges: the first and last few blocks), the others take grid_sum's device-scope fence.
+	if (threadIdx.x == 0 && pushed) { __threadfence_system(); }
 	grid_sum<2>(acc, partial, ticket, red, [&](const double(&tot)[2]) {
 		if (!was_done && bad) {
 			st->breakdown = s_ok ? 1 : 2;
