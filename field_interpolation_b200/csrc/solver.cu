@@ -285,7 +285,8 @@ template <typename T, int XM>
 __global__ void __launch_bounds__(kThreads) pcg_update_peer_kernel(int64_t n, T* __restrict__ x, T* __restrict__ r,
                                                                    const T* __restrict__ p, const T* __restrict__ p_prev, const T* __restrict__ q,
                                                                    const T* __restrict__ minv, PcgState* st, int par, double* partial,
-                                                                   unsigned* ticket, PeerLink L, HaloPush<T> push, unsigned long long base, int fold)
+                                                                   unsigned* ticket, PeerLink L, HaloPush<T> push, unsigned long long base, int fold,
+                                                                   int blocked)
 {
 	__shared__ double red[32];
 	__shared__ double s_pq, s_tot[2];
@@ -320,8 +321,7 @@ __global__ void __launch_bounds__(kThreads) pcg_update_peer_kernel(int64_t n, T*
 		using P       = typename Pack<T>::type;
 		constexpr int V = Pack<T>::V;
 		const int64_t hi_from = n - push.count;
-		int64_t       first = 0, last = 0;
-		for_each_pack_blocked<T>(n, &first, &last, [&](int64_t k, bool packed) {
+		auto element = [&](int64_t k, bool packed) {
 			if (packed) {
 				P rv;
 				update_elements<T, XM, true>(k, x, r, p, p_prev, q, minv, alpha, alpha_prev, acc, &rv);
@@ -335,9 +335,16 @@ __global__ void __launch_bounds__(kThreads) pcg_update_peer_kernel(int64_t n, T*
 				if (push.lo && k < push.count) { push.lo[k] = ri; }
 				if (push.hi && k >= hi_from) { push.hi[k - hi_from] = ri; }
 			}
-		});
-		// only the blocks at the two ends of the slab stored into a neighbour's memory
-		pushed = (push.lo && first < push.count) || (push.hi && last > hi_from);
+		};
+		if (blocked) {
+			// only the blocks at the two ends of the slab store into a neighbour's memory
+			int64_t first = 0, last = 0;
+			for_each_pack_blocked<T>(n, &first, &last, element);
+			pushed = (push.lo && first < push.count) || (push.hi && last > hi_from);
+		} else {
+			for_each_pack<T>(n, element);
+			pushed = push.lo != nullptr || push.hi != nullptr;  // a grid-stride walk takes most blocks through both ends
+		}
 	}
 	acc[0] = block_sum(acc[0], red);
 	acc[1] = block_sum(acc[1], red);
@@ -633,6 +640,13 @@ PcgResult pcg_solve(Operator<T>& op, const T* b, T* x, double tol, long long max
 		const char* fold_env  = std::getenv("FI_B200_PEER_FOLD");
 		const int   fold_mode = !link ? 0 : (fold_env && *fold_env >= '0' && *fold_env <= '3' ? *fold_env - '0' : 2);
 		const bool  data_publishes = fold_mode >= 2, update_finishes = fold_mode == 1 || fold_mode == 2;
+		// Walk of the peer update kernel.  Block-contiguous ranges confine the halo stores — and the system-scope fence that must
+		// follow them, expensive while the SM streams ordinary stores — to the few blocks at the ends of the slab: 8 GPUs, 512^3
+		// (18 M elements per slab) 0.1913 -> 0.1852 ms per iteration (profiles/r2m_trace_n8.txt).  On large slabs 1,184 private
+		// streams cost more DRAM locality than the fences save: 1024^3 on 8 GPUs (134 M elements per slab) 1.326 ms per iteration
+		// with the grid-stride walk, 1.398 ms blocked (r2k / r2m).  FI_B200_PEER_UPDATE=blocked|stride overrides.
+		const char* walk_env = std::getenv("FI_B200_PEER_UPDATE");
+		const bool  peer_update_blocked = walk_env ? walk_env[0] == 'b' : n < (48ll << 20);
 		bool deferred_x = false;  // the fused path updates x every second iteration (kXSkip / kXBoth)
 		auto enqueue_round = [&] {
 			for (int it = 0; it < check_every; ++it) {
@@ -654,7 +668,8 @@ PcgResult pcg_solve(Operator<T>& op, const T* b, T* x, double tol, long long max
 					if (!published && !in_update) { FI_LAUNCH(peer_publish_kernel, 1, 32, 0, s, *link, 0, par, seq_base, w.state.data(), d_pq, 1, d_done); }
 					auto ku = par == 0 ? pcg_update_peer_kernel<T, kXSkip> : pcg_update_peer_kernel<T, kXBoth>;
 					FI_LAUNCH(ku, grid, kThreads, 0, s, n, x + off, r_vec + off, pp[par ^ 1] + off, pp[par] + off, w.q.data() + off, op.minv.data() + off,
-					          w.state.data(), par, w.partial.data(), w.ticket.data(), *link, push, seq_base, (in_update ? 1 : 0) | (update_finishes ? 2 : 0));
+					          w.state.data(), par, w.partial.data(), w.ticket.data(), *link, push, seq_base, (in_update ? 1 : 0) | (update_finishes ? 2 : 0),
+					          peer_update_blocked ? 1 : 0);
 					if (!update_finishes) { FI_LAUNCH(pcg_update_finish_peer_kernel, 1, 32, 0, s, w.state.data(), par, *link, seq_base); }
 				} else if (fused) {
 					apply_data_term<T>(op.g, op.data, pp[par ^ 1], w.q.data(), d_pq, d_done, s);
