@@ -900,6 +900,9 @@ int fi_field_solve(fi_field* f, const fi_solve_options* opt, const float* guess,
 		if (opt) { o = *opt; } else { fi_solve_options_default(&o); }
 		const int64_t N = f->g.N;
 		if (loc == FI_DEVICE) {
+			// the update and stencil kernels access the solution (and the guess, when it is the same buffer) in 16-byte packs
+			FI_REQUIRE((reinterpret_cast<uintptr_t>(solution) & 15u) == 0 && (reinterpret_cast<uintptr_t>(guess) & 15u) == 0, FI_ERR_INVALID,
+			           "FI_DEVICE solution / guess buffers must be 16-byte aligned");
 			solve_device(f, o, guess, solution, stats);
 		} else {
 			DevBuf<float> d(N);
@@ -926,6 +929,7 @@ int fi_field_solve_tiled(fi_field* f, const fi_solve_options* opt, int32_t tile,
 		DevBuf<float> staged;
 		float*        d_x = solution;
 		if (loc == FI_DEVICE) {
+			FI_REQUIRE((reinterpret_cast<uintptr_t>(solution) & 15u) == 0, FI_ERR_INVALID, "FI_DEVICE solution buffer must be 16-byte aligned");
 			if (guess != solution) { FI_CUDA(cudaMemcpyAsync(solution, guess, N * sizeof(float), cudaMemcpyDeviceToDevice, s)); }
 		} else {
 			staged.resize(N);

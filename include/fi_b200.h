@@ -179,8 +179,9 @@ FI_API int fi_field_diagonal(fi_field* f, int32_t precision, void* diag);
 /* Jacobi-preconditioned CG on the normal equations with Eigen's stopping rule.  Stands in for
  * solve_sparse_linear_exact / _fast (sparse_linear.cpp:115-184: pass FI_F64 and a tight tolerance),
  * solve_sparse_linear_with_guess (:186-212) and the CG phase of solve_tiled_with_guess (:392-443).
- * guess: N floats or null (zeros).  solution: N floats.  Non-convergence is not an error (Eigen returns the
- * last iterate too); stats->converged says which. */
+ * guess: N floats or null (zeros).  solution: N floats; with loc = FI_DEVICE both must be 16-byte aligned (the kernels
+ * access them in 16-byte packs; FI_ERR_INVALID otherwise).  Non-convergence is not an error (Eigen returns the last
+ * iterate too); stats->converged says which. */
 FI_API int fi_field_solve(fi_field* f, const fi_solve_options* opt, const float* guess, float* solution, int32_t loc,
                    fi_solve_stats* stats);
 
