@@ -215,7 +215,7 @@ struct fi_field
 		fi::MgOptions want = fi::default_mg_options(model, g, false, o.mg_smoothing_steps, o.mg_cheb_ratio);
 		fi::mg_options_from_env(want);
 		if (mg && (mg_opt.nu != want.nu || mg_opt.cheb_ratio != want.cheb_ratio || mg_opt.nu_coarse != want.nu_coarse || mg_opt.gamma != want.gamma ||
-		           mg_opt.coarsest_cells != want.coarsest_cells || mg_opt.w_levels != want.w_levels)) {
+		           mg_opt.coarsest_cells != want.coarsest_cells || mg_opt.w_levels != want.w_levels || mg_opt.tail_cells != want.tail_cells)) {
 			mg.reset();
 		}
 		if (!mg) {

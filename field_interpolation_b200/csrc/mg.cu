@@ -17,6 +17,7 @@
 // rounding), and is captured in one CUDA graph.
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <vector>
 
 #include "solver.hpp"
@@ -257,6 +258,263 @@ __global__ void unit_vector_kernel(int n, int k, float* v)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < n) { v[i] = i == k ? 1.0f : 0.0f; }
+}
+
+// ---- the tail of the cycle in one kernel ----------------------------------------------------------------------------
+// Levels of a few thousand nodes are pure launch latency: a Chebyshev step on 16^3 nodes is three launches of a few
+// microseconds each for a few hundred nanoseconds of work, and a W-cycle visits those levels eight times per iteration
+// (profiles/r2j_mg_launches_512_f64outer_wcycle.md: ~500 of the ~985 launches of one iteration at 512^3).  One block of
+// 1024 threads walks the whole tail instead — pre-smoothing, residual, restriction down to the dense level and back up —
+// with __syncthreads() where the launches had their boundaries.  The arithmetic is the one vcycle_level() launches
+// (same Chebyshev recurrence, the generic kernels' operator application, the same transfer tables); sums are formed in
+// a different order.  Vectors written inside the kernel are read with plain loads (never __ldg).
+constexpr int kTailThreads   = 1024;
+constexpr int kTailMaxLevels = 6;
+constexpr int kTailMaxNu     = 16;
+
+struct TailLevel
+{
+	int             ndim, n, nocc, radius, nu, any;
+	int             size[kMaxDim], stride[kMaxDim];
+	float           gs2, b0;
+	float           ca[kTailMaxNu], cb[kTailMaxNu];  // Chebyshev step k = 1 .. nu-1: d = ca[k] d + cb[k] M^-1 res
+	float           band[kMaxDim][9][9];
+	const int64_t*  cell_base;
+	const uint32_t* cell_mask;
+	const float*    blocks;
+	const float*    minv;
+	float *         r, *e, *res, *d, *q;  // r / e: the level's own (the kernel arguments replace them on the first tail level)
+	Xfer            x;                    // to the next tail level
+};
+
+__device__ __forceinline__ int tail_row_class(int i, int n) { return n <= 9 ? i : (i < 4 ? i : (i >= n - 4 ? i - n + 9 : 4)); }
+
+__device__ __forceinline__ int tail_lap1(int i, int n, int o)
+{
+	if (o == 0) { return (i > 0 ? 1 : 0) + (i < n - 1 ? 1 : 0); }
+	const int j = i + o;
+	return (j >= 0 && j < n) ? -1 : 0;
+}
+
+// out = (S + P) in on level L; ends with a block barrier
+template <int D>
+__device__ void tail_apply(const TailLevel& L, const float* in, float* out)
+{
+	constexpr int C = 1 << D;
+	for (int i = threadIdx.x; i < L.n; i += blockDim.x) {
+		int c[kMaxDim] = {0, 0, 0};
+		int rem        = i;
+#pragma unroll
+		for (int d = 0; d < D; ++d) {
+			if (d == D - 1) {
+				c[d] = rem;
+			} else {
+				c[d] = rem % L.size[d];
+				rem /= L.size[d];
+			}
+		}
+		float acc = 0.0f;
+		if (L.any) {
+			const int R = L.radius;
+#pragma unroll
+			for (int d = 0; d < D; ++d) {
+				const float* row = L.band[d][tail_row_class(c[d], L.size[d])];
+				for (int o = -R; o <= R; ++o) {
+					const float coef = row[o + 4];
+					if (coef != 0.0f) { acc += coef * in[i + o * L.stride[d]]; }  // taps beyond the lattice have zero coefficients
+				}
+			}
+			if (L.gs2 != 0.0f) {
+#pragma unroll
+				for (int d = 0; d < D; ++d) {
+#pragma unroll
+					for (int o = d + 1; o < D; ++o) {
+						for (int a = -1; a <= 1; ++a) {
+							const int la = tail_lap1(c[d], L.size[d], a);
+							if (la == 0) { continue; }
+							for (int b = -1; b <= 1; ++b) {
+								const int lb = tail_lap1(c[o], L.size[o], b);
+								if (lb != 0) { acc += L.gs2 * static_cast<float>(la * lb) * in[i + a * L.stride[d] + b * L.stride[o]]; }
+							}
+						}
+					}
+				}
+			}
+		}
+		out[i] = acc;
+	}
+	__syncthreads();
+	for (int cell = threadIdx.x; cell < L.nocc; cell += blockDim.x) {
+		const int      base = static_cast<int>(L.cell_base[cell]);
+		const uint32_t mask = L.cell_mask[cell];
+		float          pc[C], acc[C];
+		int            off[C];
+#pragma unroll
+		for (int c = 0; c < C; ++c) {
+			off[c] = 0;
+#pragma unroll
+			for (int d = 0; d < D; ++d) { off[c] += ((c >> d) & 1) ? L.stride[d] : 0; }
+			pc[c]  = ((mask >> c) & 1u) ? in[base + off[c]] : 0.0f;
+			acc[c] = 0.0f;
+		}
+		int tri = 0;
+#pragma unroll
+		for (int ci = 0; ci < C; ++ci) {
+#pragma unroll
+			for (int cj = ci; cj < C; ++cj) {
+				const float v = __ldg(&L.blocks[static_cast<size_t>(tri) * L.nocc + cell]);
+				acc[ci] += v * pc[cj];
+				if (cj != ci) { acc[cj] += v * pc[ci]; }
+				++tri;
+			}
+		}
+#pragma unroll
+		for (int c = 0; c < C; ++c) {
+			if ((mask >> (8 + c)) & 1u) { atomicAdd(&out[base + off[c]], acc[c]); }
+		}
+	}
+	__syncthreads();
+}
+
+// nu Chebyshev steps on A e = r (smooth() above); e_zero: e starts at zero.  Returns with the residual BEFORE the last
+// correction in res_src (r itself after a single step from zero) and the last correction in L.d.
+template <int D>
+__device__ const float* tail_smooth(const TailLevel& L, const float* r, float* e, bool e_zero)
+{
+	const float* res_src = r;
+	if (e_zero) {
+		for (int i = threadIdx.x; i < L.n; i += blockDim.x) {
+			const float dn = L.b0 * __ldg(&L.minv[i]) * r[i];
+			L.d[i]         = dn;
+			e[i]           = dn;
+		}
+		__syncthreads();
+	} else {
+		tail_apply<D>(L, e, L.q);
+		for (int i = threadIdx.x; i < L.n; i += blockDim.x) {
+			const float rr = r[i] - L.q[i];
+			const float dn = L.b0 * __ldg(&L.minv[i]) * rr;
+			L.res[i]       = rr;
+			L.d[i]         = dn;
+			e[i] += dn;
+		}
+		__syncthreads();
+		res_src = L.res;
+	}
+	for (int k = 1; k < L.nu; ++k) {
+		tail_apply<D>(L, L.d, L.q);
+		const float a = L.ca[k], b = L.cb[k];
+		for (int i = threadIdx.x; i < L.n; i += blockDim.x) {
+			const float rr = res_src[i] - L.q[i];
+			const float dn = a * L.d[i] + b * __ldg(&L.minv[i]) * rr;
+			L.res[i]       = rr;
+			L.d[i]         = dn;
+			e[i] += dn;
+		}
+		__syncthreads();
+		res_src = L.res;
+	}
+	return res_src;
+}
+
+template <int D>
+__global__ void __launch_bounds__(kTailThreads, 1) mg_tail_kernel(const TailLevel* __restrict__ levels, int nlev, int nc, const float* __restrict__ coarse_inv,
+                                                                   const float* r_top, float* e_top)
+{
+	__shared__ TailLevel L;
+	__shared__ double    part[kTailThreads];
+	auto load_level = [&](int l) {
+		__syncthreads();
+		const int* src = reinterpret_cast<const int*>(levels + l);
+		int*       dst = reinterpret_cast<int*>(&L);
+		for (int k = threadIdx.x; k < static_cast<int>(sizeof(TailLevel) / sizeof(int)); k += blockDim.x) { dst[k] = src[k]; }
+		__syncthreads();
+	};
+	// down: pre-smooth from zero, residual after the last correction, restrict
+	for (int l = 0; l + 1 < nlev; ++l) {
+		load_level(l);
+		const float* r   = l == 0 ? r_top : L.r;
+		float*       e   = l == 0 ? e_top : L.e;
+		const float* src = tail_smooth<D>(L, r, e, true);
+		tail_apply<D>(L, L.d, L.q);
+		for (int i = threadIdx.x; i < L.n; i += blockDim.x) { L.res[i] = src[i] - L.q[i]; }
+		__syncthreads();
+		const Xfer& x   = L.x;
+		float*      rc  = levels[l + 1].r;
+		const int   ncx = x.nc[0], ncy = x.nc[1], ncz = x.nc[2];
+		for (int cn = threadIdx.x; cn < ncx * ncy * ncz; cn += blockDim.x) {
+			const int    cx = cn % ncx, cy = (cn / ncx) % ncy, cz = cn / (ncx * ncy);
+			const int    x0 = __ldg(x.first[0] + cx), y0 = __ldg(x.first[1] + cy), z0 = __ldg(x.first[2] + cz);
+			const int    nx = __ldg(x.count[0] + cx), ny = __ldg(x.count[1] + cy), nz = __ldg(x.count[2] + cz);
+			const float* wx = x.weight[0] + static_cast<size_t>(cx) * kMaxFan;
+			const float* wy = x.weight[1] + static_cast<size_t>(cy) * kMaxFan;
+			const float* wz = x.weight[2] + static_cast<size_t>(cz) * kMaxFan;
+			float        acc = 0.0f;
+			for (int k = 0; k < nz; ++k) {
+				float plane = 0.0f;
+				for (int j = 0; j < ny; ++j) {
+					const float* row = L.res + (static_cast<size_t>(z0 + k) * x.nf[1] + (y0 + j)) * x.nf[0] + x0;
+					float        s   = 0.0f;
+					for (int i = 0; i < nx; ++i) { s += __ldg(wx + i) * row[i]; }
+					plane += __ldg(wy + j) * s;
+				}
+				acc += __ldg(wz + k) * plane;
+			}
+			rc[cn] = acc;
+		}
+	}
+	// coarsest level: e = Ainv r with the dense inverse (symmetric: column `row` is read, so that a warp reads consecutive
+	// floats); nc <= blockDim.x / 2 splits a row over several threads
+	{
+		load_level(nlev - 1);
+		const float* r     = nlev == 1 ? r_top : L.r;
+		float*       e     = nlev == 1 ? e_top : L.e;
+		const int    parts = nc < static_cast<int>(blockDim.x) ? static_cast<int>(blockDim.x) / nc : 1;
+		if (parts == 1) {
+			for (int row = threadIdx.x; row < nc; row += blockDim.x) {
+				double acc = 0.0;
+				for (int j = 0; j < nc; ++j) { acc += static_cast<double>(__ldg(&coarse_inv[static_cast<size_t>(j) * nc + row])) * static_cast<double>(r[j]); }
+				e[row] = static_cast<float>(acc);
+			}
+		} else {
+			const int row = threadIdx.x % nc, pt = threadIdx.x / nc;
+			double    acc = 0.0;
+			if (pt < parts) {
+				for (int j = pt; j < nc; j += parts) { acc += static_cast<double>(__ldg(&coarse_inv[static_cast<size_t>(j) * nc + row])) * static_cast<double>(r[j]); }
+			}
+			part[threadIdx.x] = acc;
+			__syncthreads();
+			if (pt == 0) {
+				for (int k = 1; k < parts; ++k) { acc += part[k * nc + row]; }
+				e[row] = static_cast<float>(acc);
+			}
+		}
+	}
+	// up: add the prolonged correction, post-smooth
+	for (int l = nlev - 2; l >= 0; --l) {
+		load_level(l);
+		const float* r  = l == 0 ? r_top : L.r;
+		float*       e  = l == 0 ? e_top : L.e;
+		const Xfer&  x  = L.x;
+		const float* ec = levels[l + 1].e;
+		const int    nfx = x.nf[0], nfy = x.nf[1];
+		const int    sy = x.nc[0], sz = x.nc[0] * x.nc[1];
+		for (int i = threadIdx.x; i < L.n; i += blockDim.x) {
+			const int   ix = i % nfx, iy = (i / nfx) % nfy, iz = i / (nfx * nfy);
+			const int   bx = __ldg(x.base[0] + ix), by = __ldg(x.base[1] + iy), bz = __ldg(x.base[2] + iz);
+			const float fx = __ldg(x.frac[0] + ix), fy = __ldg(x.frac[1] + iy), fz = __ldg(x.frac[2] + iz);
+			// the upper neighbour of the last node does not exist; its weight is zero, the clamped read is harmless
+			const int   bx1 = min(bx + 1, x.nc[0] - 1), by1 = min(by + 1, x.nc[1] - 1), bz1 = min(bz + 1, x.nc[2] - 1);
+			const float gx = 1.0f - fx, gy = 1.0f - fy, gz = 1.0f - fz;
+			const float v00 = gx * ec[bz * sz + by * sy + bx] + fx * ec[bz * sz + by * sy + bx1];
+			const float v01 = gx * ec[bz * sz + by1 * sy + bx] + fx * ec[bz * sz + by1 * sy + bx1];
+			const float v10 = gx * ec[bz1 * sz + by * sy + bx] + fx * ec[bz1 * sz + by * sy + bx1];
+			const float v11 = gx * ec[bz1 * sz + by1 * sy + bx] + fx * ec[bz1 * sz + by1 * sy + bx1];
+			e[i] += gz * (gy * v00 + fy * v01) + fz * (gy * v10 + fy * v11);
+		}
+		__syncthreads();
+		tail_smooth<D>(L, r, e, false);
+	}
 }
 
 // ---- power iteration helpers ----------------------------------------------------------------------------------------
@@ -544,7 +802,77 @@ void mg_options_from_env(MgOptions& o)
 	geti("FI_B200_MG_NU_COARSE", o.nu_coarse);
 	geti("FI_B200_MG_GAMMA", o.gamma);
 	geti("FI_B200_MG_WLEVELS", o.w_levels);
+	if (const char* e = getenv("FI_B200_MG_TAIL_CELLS")) { o.tail_cells = atoi(e); }  // 0: every level by its own launches
 }
+
+namespace {
+
+// Chooses the levels mg_tail_kernel walks (the last ones, from the first with at most opt.tail_cells nodes; level 0 is never
+// one of them: it is the caller's operator and may carry generic rows or a tile mask) and writes their descriptors.
+void build_tail(Multigrid& mg, cudaStream_t s)
+{
+	const int L = static_cast<int>(mg.levels.size());
+	mg.tail_from = 0;
+	mg.tail_nlev = 0;
+	if (mg.opt.tail_cells <= 0 || L < 3) { return; }
+	int from = L - 1;
+	while (from - 1 >= 1 && mg.levels[from - 1]->g.N <= mg.opt.tail_cells && L - (from - 1) <= kTailMaxLevels) { --from; }
+	if (from >= L - 1) { return; }  // only the dense level: one launch either way
+	std::vector<TailLevel> h(static_cast<size_t>(L - from));
+	for (int l = from; l < L; ++l) {
+		Multigrid::Level& lv = *mg.levels[l];
+		Operator<float>&  op = *lv.op;
+		TailLevel&        t  = h[static_cast<size_t>(l - from)];
+		std::memset(&t, 0, sizeof(t));
+		if (op.data.nrows > 0 || op.g.tile != 0 || op.g.sharded() || op.dist != nullptr) { return; }
+		t.ndim   = lv.g.ndim;
+		t.n      = static_cast<int>(lv.g.N);
+		t.nocc   = static_cast<int>(op.data.nocc);
+		t.radius = op.tabs.radius;
+		t.any    = op.tabs.any ? 1 : 0;
+		t.gs2    = static_cast<float>(op.tabs.gs2);
+		for (int d = 0; d < kMaxDim; ++d) {
+			t.size[d]   = lv.g.size[d];
+			t.stride[d] = static_cast<int>(lv.g.stride[d]);
+			for (int c = 0; c < 9; ++c) {
+				for (int k = 0; k < 9; ++k) { t.band[d][c][k] = static_cast<float>(op.tabs.band[d][c][k]); }
+			}
+		}
+		t.cell_base = op.data.cell_base.data();
+		t.cell_mask = op.data.cell_mask.data();
+		t.blocks    = op.data.blocks.data();
+		t.minv      = op.minv.data();
+		t.r         = lv.r.data();
+		t.e         = lv.e.data();
+		if (l < L - 1) {
+			// the coefficients smooth() passes to its kernels
+			const int nu = (l + mg.base_level > 0 && mg.opt.nu_coarse > 0) ? mg.opt.nu_coarse : mg.opt.nu;
+			if (nu < 1 || nu > kTailMaxNu) { return; }
+			const double lmax = lv.lmax, lmin = lmax / mg.opt.cheb_ratio;
+			const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
+			t.nu  = nu;
+			t.b0  = static_cast<float>(1.0 / theta);
+			double rho = 1.0 / sigma;
+			for (int k = 1; k < nu; ++k) {
+				const double rho_new = 1.0 / (2.0 * sigma - rho);
+				t.ca[k] = static_cast<float>(rho_new * rho);
+				t.cb[k] = static_cast<float>(2.0 * rho_new / delta);
+				rho     = rho_new;
+			}
+			t.res = lv.res.data();
+			t.d   = lv.d.data();
+			t.q   = lv.q.data();
+			t.x   = lv.to_coarser;
+		}
+	}
+	mg.tail_plan.resize(h.size() * sizeof(TailLevel));
+	FI_CUDA(cudaMemcpyAsync(mg.tail_plan.data(), h.data(), h.size() * sizeof(TailLevel), cudaMemcpyHostToDevice, s));
+	FI_CUDA(cudaStreamSynchronize(s));  // the host vector goes out of scope
+	mg.tail_from = from;
+	mg.tail_nlev = L - from;
+}
+
+}  // namespace
 
 Multigrid::Multigrid()  = default;
 Multigrid::~Multigrid()
@@ -592,6 +920,7 @@ std::unique_ptr<Multigrid> build_multigrid(Operator<float>& fine, const ModelAcc
 	FI_REQUIRE(mg->levels.back()->g.N <= 4096, FI_ERR_UNSUPPORTED, "multigrid: coarsest level too large for the dense solve");
 	// coarse operators by re-discretisation
 	for (int l = 1; l < L; ++l) {
+		TraceScope tl("coarse level operator");
 		Multigrid::Level& lv = *mg->levels[l];
 		ModelAccum        m;
 		level_inputs(D, root_size, model, pts, lv.g, fine_level + l, m, lv.pts, s);
@@ -622,6 +951,7 @@ std::unique_ptr<Multigrid> build_multigrid(Operator<float>& fine, const ModelAcc
 	}
 	// largest eigenvalue of D^-1 A per smoothed level: power iteration
 	{
+		TraceScope tp("power iterations");
 		DevBuf<double>   out(2), partial(static_cast<size_t>(2) * (static_cast<size_t>(sm_count()) * 8 + 8));
 		DevBuf<unsigned> ticket(1);
 		ticket.zero(s);
@@ -649,6 +979,7 @@ std::unique_ptr<Multigrid> build_multigrid(Operator<float>& fine, const ModelAcc
 	// dense inverse of the coarsest operator, computed on the device: the columns A e_k by n applies without a
 	// host round trip, then an in-place Gauss-Jordan sweep in fp64 (no pivoting: the matrix is SPD)
 	{
+		TraceScope        td("dense inverse of the coarsest level");
 		Multigrid::Level& lc = *mg->levels[L - 1];
 		const int         n  = static_cast<int>(lc.g.N);
 		mg->nc               = n;
@@ -675,6 +1006,7 @@ std::unique_ptr<Multigrid> build_multigrid(Operator<float>& fine, const ModelAcc
 		FI_CUDA(cudaStreamSynchronize(s));
 		FI_REQUIRE(h_bad == 0, FI_ERR_INVALID, "multigrid: the coarsest operator is singular");
 	}
+	build_tail(*mg, s);
 	return mg;
 }
 
@@ -740,6 +1072,13 @@ void vcycle_level(Multigrid& mg, int l, const float* r, float* e, cudaStream_t s
 {
 	const int L = static_cast<int>(mg.levels.size());
 	Multigrid::Level& lv = *mg.levels[l];
+	// the last levels in one kernel — unless a W-cycle would still recurse twice somewhere below this level
+	if (mg.tail_from > 0 && l == mg.tail_from && (mg.opt.gamma <= 1 || l + 1 + mg.base_level > mg.opt.w_levels)) {
+		const TailLevel* plan = reinterpret_cast<const TailLevel*>(mg.tail_plan.data());
+		auto kern = lv.g.ndim == 3 ? mg_tail_kernel<3> : (lv.g.ndim == 2 ? mg_tail_kernel<2> : mg_tail_kernel<1>);
+		FI_LAUNCH(kern, 1, kTailThreads, 0, s, plan, mg.tail_nlev, mg.nc, static_cast<const float*>(mg.coarse_inv.data()), r, e);
+		return;
+	}
 	if (l == L - 1) {
 		FI_LAUNCH(dense_matvec_kernel, mg.nc, 128, 0, s, mg.nc, mg.coarse_inv.data(), r, e);
 		return;

@@ -157,6 +157,8 @@ struct MgOptions
 	double cheb_ratio       = 12.0;  // the smoother targets the eigenvalues of D^-1 A in [lambda_max / ratio, lambda_max]
 	int    coarsest_cells   = 600;   // coarsen until a level has at most this many cells (dense solve there, inverse computed on the device)
 	int    power_iterations = 12;    // for lambda_max, per level, at setup
+	int    tail_cells       = 4096;  // coarse levels with at most this many nodes are walked by ONE kernel (mg_tail_kernel) instead of
+	                                 // three launches per smoothing step; 0: off.  FI_B200_MG_TAIL_CELLS
 };
 
 // The hierarchy's parameters when the caller leaves them alone, from the B200 sweeps of round 2
@@ -201,6 +203,8 @@ struct Multigrid
 	DevBuf<float>                       coarse_inv;  // dense inverse of the coarsest operator, row-major nc x nc
 	int                                 nc = 0;
 	int                                 base_level = 0;  // level of levels[0] in the hierarchy of the root lattice (> 0: the replicated tail of a slab V-cycle)
+	DevBuf<unsigned char>               tail_plan;       // descriptors of levels tail_from .. (mg_tail_kernel); tail_from = 0: none
+	int                                 tail_from = 0, tail_nlev = 0;
 	cudaGraphExec_t                     exec = nullptr;  // the V-cycle for (graph_r -> graph_z)
 	const float*                        graph_r = nullptr;
 	float*                              graph_z = nullptr;

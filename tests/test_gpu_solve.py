@@ -351,6 +351,36 @@ def test_multigrid_with_guess_and_cap(fi, port):
     assert not st3["converged"] and st3["iterations"] == 2, st3
 
 
+@pytest.mark.parametrize("sizes,npts,wkw", [([3000], 40, {}), ([200, 150], 2000, {}), ([40, 36, 33], 3000, {}),
+                                            ([36, 30, 28], 2500, dict(model_1=0.2, gradient_smoothness=0.2))])
+def test_multigrid_tail_kernel_matches_per_level_launches(fi, port, sizes, npts, wkw, monkeypatch):
+    """The last levels of the cycle walked by one kernel (mg_tail_kernel) against the same levels launched one kernel per
+    step (FI_B200_MG_TAIL_CELLS=0): the same preconditioner up to summation order — same iteration count, same field —
+    with far fewer launches."""
+    D = len(sizes)
+    if D == 1:
+        rng = np.random.default_rng(5)
+        cloud = {"unit_pos": rng.uniform(0.05, 0.95, (npts, 1)).astype(np.float32),
+                 "normals": np.where(rng.uniform(size=(npts, 1)) < 0.5, -1.0, 1.0).astype(np.float32)}
+    else:
+        cloud = W.circles_2d(npts, seed=4) if D == 2 else W.sphere_torus_3d(npts, seed=4)
+    pos = W.to_lattice(cloud["unit_pos"], sizes)
+    f = fi.sdf_from_points(sizes, fi.Weights(**wkw), pos, cloud["normals"])
+    opt = fi.solve_options(fi.FI_F64, 0, 1e-9, preconditioner=fi.FI_PRECOND_MULTIGRID)
+    out = {}
+    for cells in ("0", "4096"):
+        monkeypatch.setenv("FI_B200_MG_TAIL_CELLS", cells)
+        f.solve(opt)  # builds the hierarchy and its graph
+        fi.kernel_launches_reset()
+        x, st = f.solve(opt)
+        out[cells] = (x, st, fi.kernel_launches())
+    (x0, st0, n0), (x1, st1, n1) = out["0"], out["4096"]
+    assert st0["converged"] and st1["converged"], (st0, st1)
+    assert abs(st0["iterations"] - st1["iterations"]) <= 1, (st0, st1)
+    assert rel(x1, x0) <= 1e-7, rel(x1, x0)
+    assert n1 < 0.9 * n0, (n0, n1)
+
+
 # ---- tile phase of solve_tiled_with_guess (tile_solver_square, reference sparse_linear.cpp:246-390) ----------------
 def _tile_case(port, sizes, npts, seed, **wkw):
     D = len(sizes)
