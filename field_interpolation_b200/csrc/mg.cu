@@ -260,12 +260,16 @@ __global__ void unit_vector_kernel(int n, int k, float* v)
 	if (i < n) { v[i] = i == k ? 1.0f : 0.0f; }
 }
 
-// ---- the tail of the cycle in one kernel ----------------------------------------------------------------------------
-// Levels of a few thousand nodes are pure launch latency: a Chebyshev step on 16^3 nodes is three launches of a few
-// microseconds each for a few hundred nanoseconds of work, and a W-cycle visits those levels eight times per iteration
-// (profiles/r2j_mg_launches_512_f64outer_wcycle.md: ~500 of the ~985 launches of one iteration at 512^3).  One block of
-// 1024 threads walks the whole tail instead — pre-smoothing, residual, restriction down to the dense level and back up —
-// with __syncthreads() where the launches had their boundaries.  The arithmetic is the one vcycle_level() launches
+// ---- the tail of the cycle in one kernel (opt-in: MgOptions::tail_cells / FI_B200_MG_TAIL_CELLS) -----------------------
+// Levels of a few thousand nodes are launch latency: a Chebyshev step on 16^3 nodes is three launches of a few
+// microseconds each, and a W-cycle visits those levels eight times per iteration (profiles/r2j_mg_launches_512_f64outer_wcycle.md:
+// ~500 of the ~985 launches of one iteration at 512^3).  One block of 1024 threads walks the whole tail instead —
+// pre-smoothing, residual, restriction down to the dense level and back up — with __syncthreads() where the launches had
+// their boundaries.  MEASURED (B200, round 2, profiles/r2p_*): correct, 1345 instead of 1969 launches per two iterations,
+// and slower — 283 us per visit (the 16^3 level of the bench cloud has 3375 occupied cells: 27 k float reductions per
+// operator application through ONE SM's 1.3 cycles per lane, 13 applications per visit), 512^3 solve 170.6 against
+// 163.7 ms, 256^3 50.4 against 47.4 ms, 2D unchanged.  Hence off by default; what would make it pay is the data term
+// accumulated in shared memory and a cluster of blocks instead of one.  The arithmetic is the one vcycle_level() launches
 // (same Chebyshev recurrence, the generic kernels' operator application, the same transfer tables); sums are formed in
 // a different order.  Vectors written inside the kernel are read with plain loads (never __ldg).
 constexpr int kTailThreads   = 1024;
@@ -517,6 +521,85 @@ __global__ void __launch_bounds__(kTailThreads, 1) mg_tail_kernel(const TailLeve
 	}
 }
 
+// ---- the coarsest operator as a dense matrix, written directly ---------------------------------------------------------
+// cols[j * n + i] = A[i][j] for a level described by a TailLevel (no generic rows, no tile mask): the smoothness rows by one
+// thread per node — only thread i writes entries of row i, plain read-modify-writes on the zeroed matrix — then the cell
+// blocks by one thread per occupied cell with atomics.  Replaces n applications of the operator to unit vectors (3 launches
+// each: 1536 launches, 6 ms of host launch time, for the 512 nodes under a 512^3 lattice).
+template <int D>
+__global__ void dense_stencil_kernel(TailLevel L, float* __restrict__ cols)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= L.n || !L.any) { return; }
+	int c[kMaxDim] = {0, 0, 0};
+	int rem        = i;
+#pragma unroll
+	for (int d = 0; d < D; ++d) {
+		if (d == D - 1) {
+			c[d] = rem;
+		} else {
+			c[d] = rem % L.size[d];
+			rem /= L.size[d];
+		}
+	}
+	const size_t n = static_cast<size_t>(L.n);
+	const int    R = L.radius;
+#pragma unroll
+	for (int d = 0; d < D; ++d) {
+		const float* row = L.band[d][tail_row_class(c[d], L.size[d])];
+		for (int o = -R; o <= R; ++o) {
+			const float coef = row[o + 4];
+			if (coef != 0.0f) { cols[static_cast<size_t>(i + o * L.stride[d]) * n + i] += coef; }
+		}
+	}
+	if (L.gs2 != 0.0f) {
+#pragma unroll
+		for (int d = 0; d < D; ++d) {
+#pragma unroll
+			for (int o = d + 1; o < D; ++o) {
+				for (int a = -1; a <= 1; ++a) {
+					const int la = tail_lap1(c[d], L.size[d], a);
+					if (la == 0) { continue; }
+					for (int b = -1; b <= 1; ++b) {
+						const int lb = tail_lap1(c[o], L.size[o], b);
+						if (lb != 0) { cols[static_cast<size_t>(i + a * L.stride[d] + b * L.stride[o]) * n + i] += L.gs2 * static_cast<float>(la * lb); }
+					}
+				}
+			}
+		}
+	}
+}
+
+template <int D>
+__global__ void dense_blocks_kernel(TailLevel L, float* __restrict__ cols)
+{
+	constexpr int C    = 1 << D;
+	const int     cell = blockIdx.x * blockDim.x + threadIdx.x;
+	if (cell >= L.nocc) { return; }
+	const int      base = static_cast<int>(L.cell_base[cell]);
+	const uint32_t mask = L.cell_mask[cell];
+	const size_t   n    = static_cast<size_t>(L.n);
+	int            node[C];
+#pragma unroll
+	for (int c = 0; c < C; ++c) {
+		node[c] = base;
+#pragma unroll
+		for (int d = 0; d < D; ++d) { node[c] += ((c >> d) & 1) ? L.stride[d] : 0; }
+	}
+	int tri = 0;
+#pragma unroll
+	for (int ci = 0; ci < C; ++ci) {
+#pragma unroll
+		for (int cj = ci; cj < C; ++cj) {
+			const float v = L.blocks[static_cast<size_t>(tri) * L.nocc + cell];
+			// apply_blocks_kernel: out[ci] += v p[cj] when corner cj is a lattice node and the row of corner ci is owned
+			if (((mask >> cj) & 1u) && ((mask >> (8 + ci)) & 1u)) { atomicAdd(&cols[static_cast<size_t>(node[cj]) * n + node[ci]], v); }
+			if (cj != ci && ((mask >> ci) & 1u) && ((mask >> (8 + cj)) & 1u)) { atomicAdd(&cols[static_cast<size_t>(node[ci]) * n + node[cj]], v); }
+			++tri;
+		}
+	}
+}
+
 // ---- power iteration helpers ----------------------------------------------------------------------------------------
 // v[i] = pseudo-random in [-0.5, 0.5) from the lattice index i + first (a slab fills its planes with the values the
 // unsharded vector has there)
@@ -635,25 +718,20 @@ __global__ void symmetrise_kernel(int n, const float* __restrict__ cols, double*
 	M[t] = 0.5 * (static_cast<double>(cols[static_cast<size_t>(i) * n + j]) + static_cast<double>(cols[static_cast<size_t>(j) * n + i]));
 }
 
-// Gauss-Jordan step c, first half: the scaled pivot row (with the identity's column folded in) and the pivot column.
-__global__ void gj_pivot_kernel(int n, int c, const double* __restrict__ M, double* __restrict__ prow, double* __restrict__ pcol, int* bad)
-{
-	const int k = blockIdx.x * blockDim.x + threadIdx.x;
-	if (k >= n) { return; }
-	const double p = M[static_cast<size_t>(c) * n + c];
-	if (k == 0 && !(p > 0.0)) { *bad = 1; }
-	const double inv = p != 0.0 ? 1.0 / p : 0.0;
-	prow[k] = (k == c ? 1.0 : M[static_cast<size_t>(c) * n + k]) * inv;
-	pcol[k] = M[static_cast<size_t>(k) * n + c];
-}
-
-// second half: row c <- pivot row; every other row r <- row r (column c cleared) - M[r][c] * pivot row
-__global__ void gj_update_kernel(int n, int c, double* __restrict__ M, const double* __restrict__ prow, const double* __restrict__ pcol)
+// Gauss-Jordan step c, out of place: row c <- the scaled pivot row (with the identity's column folded in); every other row
+// r <- row r (column c cleared) - M[r][c] * pivot row.  Every thread reads the pivot, its pivot-row and pivot-column
+// entries from `in` itself (L1 / L2 hits), so a step is one launch; in and out alternate.
+__global__ void gj_step_kernel(int n, int c, const double* __restrict__ in, double* __restrict__ out, int* bad)
 {
 	const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
 	if (t >= static_cast<int64_t>(n) * n) { return; }
-	const int r = static_cast<int>(t / n), k = static_cast<int>(t % n);
-	M[t] = r == c ? prow[k] : (k == c ? 0.0 : M[t]) - pcol[r] * prow[k];
+	const int    r = static_cast<int>(t / n), k = static_cast<int>(t % n);
+	const double p = in[static_cast<size_t>(c) * n + c];
+	if (t == 0 && !(p > 0.0)) { *bad = 1; }
+	const double inv  = p != 0.0 ? 1.0 / p : 0.0;
+	const double prow = (k == c ? 1.0 : in[static_cast<size_t>(c) * n + k]) * inv;
+	const double pcol = in[static_cast<size_t>(r) * n + c];
+	out[t] = r == c ? prow : (k == c ? 0.0 : in[t]) - pcol * prow;
 }
 
 __global__ void narrow_kernel(int64_t n, const double* __restrict__ in, float* __restrict__ out)
@@ -807,6 +885,32 @@ void mg_options_from_env(MgOptions& o)
 
 namespace {
 
+// The operator of a small level as the single-kernel paths read it (mg_tail_kernel, dense_*_kernel).  false: it has generic
+// rows, a tile mask or a slab window — those stay with the general kernels.
+bool describe_operator(Operator<float>& op, TailLevel& t)
+{
+	std::memset(&t, 0, sizeof(t));
+	if (op.data.nrows > 0 || op.g.tile != 0 || op.g.sharded() || op.dist != nullptr || op.g.N > (1 << 20)) { return false; }
+	t.ndim   = op.g.ndim;
+	t.n      = static_cast<int>(op.g.N);
+	t.nocc   = static_cast<int>(op.data.nocc);
+	t.radius = op.tabs.radius;
+	t.any    = op.tabs.any ? 1 : 0;
+	t.gs2    = static_cast<float>(op.tabs.gs2);
+	for (int d = 0; d < kMaxDim; ++d) {
+		t.size[d]   = op.g.size[d];
+		t.stride[d] = static_cast<int>(op.g.stride[d]);
+		for (int c = 0; c < 9; ++c) {
+			for (int k = 0; k < 9; ++k) { t.band[d][c][k] = static_cast<float>(op.tabs.band[d][c][k]); }
+		}
+	}
+	t.cell_base = op.data.cell_base.data();
+	t.cell_mask = op.data.cell_mask.data();
+	t.blocks    = op.data.blocks.data();
+	t.minv      = op.minv.data();
+	return true;
+}
+
 // Chooses the levels mg_tail_kernel walks (the last ones, from the first with at most opt.tail_cells nodes; level 0 is never
 // one of them: it is the caller's operator and may carry generic rows or a tile mask) and writes their descriptors.
 void build_tail(Multigrid& mg, cudaStream_t s)
@@ -823,25 +927,7 @@ void build_tail(Multigrid& mg, cudaStream_t s)
 		Multigrid::Level& lv = *mg.levels[l];
 		Operator<float>&  op = *lv.op;
 		TailLevel&        t  = h[static_cast<size_t>(l - from)];
-		std::memset(&t, 0, sizeof(t));
-		if (op.data.nrows > 0 || op.g.tile != 0 || op.g.sharded() || op.dist != nullptr) { return; }
-		t.ndim   = lv.g.ndim;
-		t.n      = static_cast<int>(lv.g.N);
-		t.nocc   = static_cast<int>(op.data.nocc);
-		t.radius = op.tabs.radius;
-		t.any    = op.tabs.any ? 1 : 0;
-		t.gs2    = static_cast<float>(op.tabs.gs2);
-		for (int d = 0; d < kMaxDim; ++d) {
-			t.size[d]   = lv.g.size[d];
-			t.stride[d] = static_cast<int>(lv.g.stride[d]);
-			for (int c = 0; c < 9; ++c) {
-				for (int k = 0; k < 9; ++k) { t.band[d][c][k] = static_cast<float>(op.tabs.band[d][c][k]); }
-			}
-		}
-		t.cell_base = op.data.cell_base.data();
-		t.cell_mask = op.data.cell_mask.data();
-		t.blocks    = op.data.blocks.data();
-		t.minv      = op.minv.data();
+		if (!describe_operator(op, t)) { return; }
 		t.r         = lv.r.data();
 		t.e         = lv.e.data();
 		if (l < L - 1) {
@@ -952,7 +1038,11 @@ std::unique_ptr<Multigrid> build_multigrid(Operator<float>& fine, const ModelAcc
 	// largest eigenvalue of D^-1 A per smoothed level: power iteration
 	{
 		TraceScope tp("power iterations");
-		DevBuf<double>   out(2), partial(static_cast<size_t>(2) * (static_cast<size_t>(sm_count()) * 8 + 8));
+		// v_k = (D^-1 A)^k v_0 without normalising in between (|v| grows by lambda <= ~4 per round: 12 rounds stay far inside
+		// fp32) — the squared norms of all rounds and levels are read back once, lambda = |v_K| / |v_K-1|.  Normalising every
+		// round cost a kernel over the level and a host synchronisation each (16.6 ms at 512^3, profiles/r2p_trace_time_to_tol_512.txt).
+		const int        K = std::max(2, opt.power_iterations);
+		DevBuf<double>   out(static_cast<size_t>(2) * K * std::max(1, L - 1)), partial(static_cast<size_t>(2) * (static_cast<size_t>(sm_count()) * 8 + 8));
 		DevBuf<unsigned> ticket(1);
 		ticket.zero(s);
 		for (int l = 0; l < L - 1; ++l) {
@@ -960,20 +1050,22 @@ std::unique_ptr<Multigrid> build_multigrid(Operator<float>& fine, const ModelAcc
 			const int64_t     n  = lv.g.N;
 			float *           v = lv.d.data(), *w = lv.res.data();
 			FI_LAUNCH(hash_fill_kernel, vgrid(n), kThreads, 0, s, n, v, static_cast<int64_t>(0));
-			double lam = 1.0;
-			for (int it = 0; it < opt.power_iterations; ++it) {
+			for (int it = 0; it < K; ++it) {
 				lv.op->apply(v, lv.q.data(), nullptr, nullptr, s);
-				FI_LAUNCH(power_step_kernel, vgrid(n), kThreads, 0, s, n, v, lv.q.data(), lv.op->minv.data(), w, out.data(), partial.data(), ticket.data());
-				double h[2];
-				FI_CUDA(cudaMemcpyAsync(h, out.data(), sizeof(h), cudaMemcpyDeviceToHost, s));
-				FI_CUDA(cudaStreamSynchronize(s));
-				const double nw = std::sqrt(h[0]);
-				FI_REQUIRE(nw > 0 && std::isfinite(nw), FI_ERR_INVALID, "multigrid: power iteration broke down");
-				lam = nw;  // |D^-1 A v| with |v| = 1 (after the first round)
-				FI_LAUNCH(scale_kernel, vgrid(n), kThreads, 0, s, n, w, static_cast<float>(1.0 / nw));
+				FI_LAUNCH(power_step_kernel, vgrid(n), kThreads, 0, s, n, v, lv.q.data(), lv.op->minv.data(), w, out.data() + 2 * (static_cast<size_t>(l) * K + it),
+				          partial.data(), ticket.data());
 				std::swap(v, w);
 			}
-			lv.lmax = lam * 1.1;  // the power iteration approaches lambda_max from below
+		}
+		if (L > 1) {
+			std::vector<double> h(static_cast<size_t>(2) * K * (L - 1));
+			FI_CUDA(cudaMemcpyAsync(h.data(), out.data(), h.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+			FI_CUDA(cudaStreamSynchronize(s));
+			for (int l = 0; l < L - 1; ++l) {
+				const double n1 = h[2 * (static_cast<size_t>(l) * K + K - 1)], n0 = h[2 * (static_cast<size_t>(l) * K + K - 2)];
+				FI_REQUIRE(n0 > 0 && n1 > 0 && std::isfinite(n0) && std::isfinite(n1), FI_ERR_INVALID, "multigrid: power iteration broke down");
+				mg->levels[l]->lmax = std::sqrt(n1 / n0) * 1.1;  // the power iteration approaches lambda_max from below
+			}
 		}
 	}
 	// dense inverse of the coarsest operator, computed on the device: the columns A e_k by n applies without a
@@ -986,21 +1078,33 @@ std::unique_ptr<Multigrid> build_multigrid(Operator<float>& fine, const ModelAcc
 		if (L == 1) { lc.r.resize(n); }  // scratch for the unit vectors (level 0 owns no vectors otherwise)
 		const size_t   nn = static_cast<size_t>(n) * n;
 		DevBuf<float>  cols(nn);
-		DevBuf<double> M(nn), prow(n), pcol(n);
-		for (int k = 0; k < n; ++k) {
-			FI_LAUNCH(unit_vector_kernel, div_up(n, kThreads), kThreads, 0, s, n, k, lc.r.data());
-			lc.op->apply(lc.r.data(), cols.data() + static_cast<size_t>(k) * n, nullptr, nullptr, s);
+		DevBuf<double> M(nn), M2(nn);
+		TailLevel      desc;
+		const char*    by_apply = getenv("FI_B200_MG_DENSE_APPLY");  // test switch: the columns by n operator applications, as below
+		if (!(by_apply && by_apply[0] == '1') && describe_operator(*lc.op, desc)) {  // the matrix written directly: two launches
+			cols.zero(s);
+			const int D = lc.g.ndim;
+			auto ks = D == 3 ? dense_stencil_kernel<3> : (D == 2 ? dense_stencil_kernel<2> : dense_stencil_kernel<1>);
+			auto kb = D == 3 ? dense_blocks_kernel<3> : (D == 2 ? dense_blocks_kernel<2> : dense_blocks_kernel<1>);
+			FI_LAUNCH(ks, div_up(n, kThreads), kThreads, 0, s, desc, cols.data());
+			if (desc.nocc > 0) { FI_LAUNCH(kb, div_up(desc.nocc, kThreads), kThreads, 0, s, desc, cols.data()); }
+		} else {  // generic rows or a tile mask (a lattice small enough to be its own coarsest level): column k = A e_k
+			for (int k = 0; k < n; ++k) {
+				FI_LAUNCH(unit_vector_kernel, div_up(n, kThreads), kThreads, 0, s, n, k, lc.r.data());
+				lc.op->apply(lc.r.data(), cols.data() + static_cast<size_t>(k) * n, nullptr, nullptr, s);
+			}
 		}
 		const int g2 = static_cast<int>(div_up(static_cast<int64_t>(nn), kThreads));
 		FI_LAUNCH(symmetrise_kernel, g2, kThreads, 0, s, n, cols.data(), M.data());
 		DevBuf<int> bad(1);
 		bad.zero(s);
+		double *gin = M.data(), *gout = M2.data();
 		for (int c = 0; c < n; ++c) {
-			FI_LAUNCH(gj_pivot_kernel, div_up(n, kThreads), kThreads, 0, s, n, c, M.data(), prow.data(), pcol.data(), bad.data());
-			FI_LAUNCH(gj_update_kernel, g2, kThreads, 0, s, n, c, M.data(), prow.data(), pcol.data());
+			FI_LAUNCH(gj_step_kernel, g2, kThreads, 0, s, n, c, static_cast<const double*>(gin), gout, bad.data());
+			std::swap(gin, gout);
 		}
 		mg->coarse_inv.resize(nn);
-		FI_LAUNCH(narrow_kernel, g2, kThreads, 0, s, static_cast<int64_t>(nn), M.data(), mg->coarse_inv.data());
+		FI_LAUNCH(narrow_kernel, g2, kThreads, 0, s, static_cast<int64_t>(nn), static_cast<const double*>(gin), mg->coarse_inv.data());
 		int h_bad = 0;
 		FI_CUDA(cudaMemcpyAsync(&h_bad, bad.data(), sizeof(int), cudaMemcpyDeviceToHost, s));
 		FI_CUDA(cudaStreamSynchronize(s));

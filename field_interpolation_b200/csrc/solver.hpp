@@ -157,8 +157,10 @@ struct MgOptions
 	double cheb_ratio       = 12.0;  // the smoother targets the eigenvalues of D^-1 A in [lambda_max / ratio, lambda_max]
 	int    coarsest_cells   = 600;   // coarsen until a level has at most this many cells (dense solve there, inverse computed on the device)
 	int    power_iterations = 12;    // for lambda_max, per level, at setup
-	int    tail_cells       = 4096;  // coarse levels with at most this many nodes are walked by ONE kernel (mg_tail_kernel) instead of
-	                                 // three launches per smoothing step; 0: off.  FI_B200_MG_TAIL_CELLS
+	int    tail_cells       = 0;     // > 0: coarse levels with at most this many nodes are walked by ONE kernel (mg_tail_kernel) instead of
+	                                 // three launches per smoothing step (FI_B200_MG_TAIL_CELLS).  Off by default: measured slower — one SM
+	                                 // retires the data term's reductions at 1.3 cycles per lane, 283 us per visit of a 16^3 level against
+	                                 // ~130 us for the launches it replaces (profiles/r2p_time_to_tol_tail_kernel.jsonl)
 };
 
 // The hierarchy's parameters when the caller leaves them alone, from the B200 sweeps of round 2

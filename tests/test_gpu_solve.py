@@ -381,6 +381,34 @@ def test_multigrid_tail_kernel_matches_per_level_launches(fi, port, sizes, npts,
     assert n1 < 0.9 * n0, (n0, n1)
 
 
+@pytest.mark.parametrize("sizes,npts,wkw", [([700], 30, {}), ([90, 70], 900, dict(model_1=0.2, gradient_smoothness=0.3)),
+                                            ([40, 36, 33], 3000, {}), ([30, 26, 28], 2000, dict(model_2=0.2, model_3=0.3, gradient_smoothness=0.2)),
+                                            ([20, 18, 16], 900, dict(model_0=0.1, model_4=0.2))])
+def test_multigrid_dense_coarsest_matrix_written_directly(fi, port, sizes, npts, wkw, monkeypatch):
+    """The coarsest operator's dense matrix written by dense_stencil_kernel / dense_blocks_kernel against the same matrix
+    column by column from operator applications (FI_B200_MG_DENSE_APPLY=1): the same preconditioner — identical iteration
+    counts, fields equal to rounding."""
+    D = len(sizes)
+    if D == 1:
+        rng = np.random.default_rng(5)
+        cloud = {"unit_pos": rng.uniform(0.05, 0.95, (npts, 1)).astype(np.float32),
+                 "normals": np.where(rng.uniform(size=(npts, 1)) < 0.5, -1.0, 1.0).astype(np.float32)}
+    else:
+        cloud = W.circles_2d(npts, seed=7) if D == 2 else W.sphere_torus_3d(npts, seed=7)
+    pos = W.to_lattice(cloud["unit_pos"], sizes)
+    opt = fi.solve_options(fi.FI_F64, 0, 1e-9, preconditioner=fi.FI_PRECOND_MULTIGRID)
+    out = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("FI_B200_MG_DENSE_APPLY", flag)
+        f = fi.sdf_from_points(sizes, fi.Weights(**wkw), pos, cloud["normals"])  # a fresh field: the hierarchy is built per field
+        out[flag] = f.solve(opt)
+        f.close()
+    (x0, st0), (x1, st1) = out["1"], out["0"]
+    assert st0["converged"] and st1["converged"], (st0, st1)
+    assert st0["iterations"] == st1["iterations"], (st0, st1)
+    assert rel(x1, x0) <= 1e-8, rel(x1, x0)
+
+
 # ---- tile phase of solve_tiled_with_guess (tile_solver_square, reference sparse_linear.cpp:246-390) ----------------
 def _tile_case(port, sizes, npts, seed, **wkw):
     D = len(sizes)
