@@ -18,7 +18,9 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__registers_per_thread", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
         "launch__shared_mem_per_block_static", "launch__shared_mem_per_block_dynamic", "launch__grid_size",
         "launch__block_size", "launch__waves_per_multiprocessor", "smsp__inst_executed.sum",
-        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts.sum",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
+        "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sector_hit_rate.pct"]
 
 
 def short(name):
@@ -61,14 +63,22 @@ def full(path, pattern=None):
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     ix = {h: i for i, h in enumerate(hdr)}
-    seen = set()
-    for r in rows[2:]:
+
+    def volume(r):
+        return -eval(r[ix["Grid Size"]].replace("(", "").replace(")", "").replace(",", "*").replace(" ", "") or "0")
+
+    # one launch per kernel name: the one with the largest grid (the first of them), i.e. the finest level of a hierarchy
+    best = {}
+    for n, r in enumerate(rows[2:]):
+        name = short(r[ix["Kernel Name"]])
+        if name not in best or volume(r) < volume(rows[2 + best[name]]):
+            best[name] = n
+    for n, r in enumerate(rows[2:]):
         name = short(r[ix["Kernel Name"]])
         if pattern and not re.search(pattern, name):
             continue
-        if name in seen:
+        if best[name] != n:
             continue
-        seen.add(name)
         print(f"\n### `{name}`  grid {r[ix['Grid Size']]} block {r[ix['Block Size']]}\n")
         print("| metric | value | unit |\n|---|---:|---|")
         for k in KEYS:
@@ -84,11 +94,9 @@ def full(path, pattern=None):
             cur["hdr"] = r
         elif cur is not None:
             cur["rows"].append(r)
-    seen = set()
-    for s in secs:
-        if (pattern and not re.search(pattern, s["name"])) or s["name"] in seen or not s["hdr"]:
+    for n, s in enumerate(secs):
+        if (pattern and not re.search(pattern, s["name"])) or best.get(s["name"]) != n or not s["hdr"]:
             continue
-        seen.add(s["name"])
         h = s["hdr"]
         ix = {k: i for i, k in enumerate(h)}
         stalls = [k for k in h if k.startswith("stall_") and "Not Issued" not in k]
